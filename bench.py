@@ -1,0 +1,487 @@
+#!/usr/bin/env python
+"""bench.py -- IA-SSD set-abstraction backbone throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-cpu]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A step = one forward of the full KITTI IA-SSD SA stack (BASELINE.json configs[1]: D-FPS 16384->4096->1024,
+ctr-aware top-k ->512->256, vote layer, MSG ball query + shared MLP) over one batch of 16 synthetic
+16384-point scenes, eval mode.  Scenes are independent: with N > 1 every rank runs its own batches
+(weak scaling, no data-path collective); NCCL carries only the timing reduction.
+
+Prints ONE JSON line (rank 0).  `value` = whole-job scenes/s with inputs resident in HBM (a pool of
+distinct batches larger than L2 is cycled); `e2e` = the same metric through `BackbonePipeline.submit_host`
+(pinned host input -> H2D -> forward -> D2H of the centre features, every step); `roofline` describes the
+dominant kernel of the step (CUDA-event timed in an instrumented eager pass of the same run);
+`cpu_baseline` = the CPU oracle port (oracle/) timed on a bounded sample on the host cores.
+
+--impl reference runs the UNMODIFIED reference (its pointnet2_batch CUDA ops rebuilt for sm_100a +
+its own pointnet2_modules.py + IASSD_backbone.py, installed by oracle/build_ref.sh into oracle/_ref) on the
+same GPU, same weights, same inputs; when that module is unavailable it falls back to the CPU oracle port
+(--impl reference-cpu forces the CPU port).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "IA-SSD SA-backbone scenes/s (16k pts)"
+UNIT = "scenes/s"
+BATCH = 16
+NPTS = 16384
+NCOLS = 5  # [batch_idx, x, y, z, intensity]
+L2_BYTES = 126 * 1024 * 1024
+WORKLOAD = ("IA-SSD KITTI cfg full SA stack (D-FPS 16384->4096->1024, ctr-aware top-k ->512->256, vote, "
+            "MSG ball query + shared MLP), batch 16 x 16384 pts per GPU, eval")
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = Path(f"/tmp/spsk_clocks_{os.getpid()}.csv")
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        for line in self.path.read_text().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        try:
+            self.path.unlink()
+        except OSError:
+            pass
+        return out
+
+
+def build_net(seed=0):
+    from spsnet_b200 import backbone as bb
+
+    torch.manual_seed(seed)
+    net = bb.IASSD_Backbone(bb.kitti_iassd_cfg(), num_class=3, input_channels=4)
+    bb.randomize_bn_stats(net, seed=seed)
+    return net.eval()
+
+
+def make_pool(rank: int, n_batches: int):
+    """n_batches distinct batches in OpenPCDet `points` layout, pinned host tensors."""
+    from spsnet_b200 import scenes
+
+    pool = []
+    for i in range(n_batches):
+        arr = scenes.to_points(scenes.make_batch(100000 * rank + i * BATCH, BATCH, NPTS, "kitti"))
+        pool.append(torch.from_numpy(arr).pin_memory())
+    return pool
+
+
+def cpu_baseline(net_cpu, sample_scenes: int):
+    """The oracle port (oracle/oracle.py + oracle.c, all host threads) on a bounded sample of the workload."""
+    from oracle import oracle as O
+    from spsnet_b200 import scenes
+
+    pts = scenes.make_batch(0, sample_scenes, NPTS, "kitti")
+    O.backbone_forward(net_cpu, pts[:1], dtype=torch.float32)  # warm (page in, build)
+    t0 = time.perf_counter()
+    O.backbone_forward(net_cpu, pts, dtype=torch.float32)
+    dt = time.perf_counter() - t0
+    cores = max(O.num_threads(), torch.get_num_threads())
+    return {"value": sample_scenes / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{sample_scenes} scenes of the same workload (full SA stack, fp32), oracle/oracle.c ops (OpenMP) + torch-CPU "
+                      f"conv/BN, {dt:.1f} s; host has {os.cpu_count()} logical cpus"}
+
+
+# --------------------------------------------------------------------------------------------------
+# kernel table: algorithmic work per launch for the roofline object
+# --------------------------------------------------------------------------------------------------
+
+def profile_kernels(net, dev_points, steps: int):
+    """Instrumented eager pass: CUDA events around every libspsk call on the launching stream."""
+    from spsnet_b200 import _lib
+
+    records = []
+    originals = {}
+    names = [n for n in _lib.SIGNATURES if n not in ("spsk_last_error", "spsk_abi_version", "spsk_built_for_sm", "spsk_launch_count")]
+
+    def wrap(name, fn):
+        def inner(*a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*a)
+            e1.record()
+            if name == "spsk_grouped_linear":  # a[0] is byref(GroupDesc): read the row count while it is alive
+                g = a[0]._obj
+                a = (int(g.b) * int(g.m) * int(g.nsample),) + tuple(a[1:])
+            records.append((name, a, e0, e1))
+            return rc
+        return inner
+
+    for n in names:
+        originals[n] = getattr(_lib.lib, n)
+        setattr(_lib.lib, n, wrap(n, originals[n]))
+    try:
+        with torch.no_grad():
+            for i in range(steps):
+                net({"batch_size": BATCH, "points": dev_points[i % len(dev_points)]})
+        torch.cuda.synchronize()
+    finally:
+        for n in names:
+            setattr(_lib.lib, n, originals[n])
+    table = {}
+    for name, a, e0, e1 in records:
+        key = name
+        if name in ("spsk_farthest_point_sampling",):
+            key = f"{name}[n={a[1]},m={a[2]}]"
+        elif name == "spsk_ball_query_msg":
+            key = f"{name}[n={a[1]},m={a[2]}]"
+        elif name == "spsk_grouped_linear":
+            key = f"{name}[cin={a[3]},cout={a[6]}]"
+        ms = e0.elapsed_time(e1)
+        t = table.setdefault(key, {"ms": 0.0, "launches": 0, "args": a})
+        t["ms"] += ms
+        t["launches"] += 1
+    return table, steps
+
+
+def roofline_from_table(table, steps, peaks):
+    """Pick the dominant kernel by time share and state its roofline (algorithmic work / CUDA-event time)."""
+    total = sum(t["ms"] for t in table.values())
+    rows = []
+    for key, t in sorted(table.items(), key=lambda kv: -kv[1]["ms"]):
+        rows.append({"kernel": key, "ms_per_step": t["ms"] / steps, "launches_per_step": t["launches"] / steps,
+                     "share": t["ms"] / total})
+    top_key, top = max(table.items(), key=lambda kv: kv[1]["ms"])
+    avg_s = top["ms"] / top["launches"] / 1e3
+    a = top["args"]
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    if top_key.startswith("spsk_farthest_point_sampling"):
+        b, n, m = a[0], a[1], a[2]
+        alg_bytes = b * (n * 12 + m * 4)  # read xyz once + write idx
+        pairs = b * n * (m - 1)
+        lane_peak = 148 * 128 * 1.965e9  # fp32 lane-ops/s at max clock
+        roof = {"kernel": top_key, "bound": "hbm", "achieved": alg_bytes / avg_s / 1e9, "peak": hbm, "unit": "GB/s",
+                "frac": alg_bytes / avg_s / 1e9 / hbm, "traffic": None,
+                "note": "FPS is latency-bound (m-1 sequential arg-max steps, one CTA per scene): neither HBM nor tensor "
+                        "roofline applies; see us_per_iter / lane_frac",
+                "us_per_iter": avg_s * 1e6 / max(m - 1, 1), "pair_evals_per_s": pairs / avg_s,
+                "lane_frac": pairs * 10 / avg_s / lane_peak, "sms_used": b}
+    elif top_key.startswith("spsk_grouped_linear") or top_key.startswith("spsk_pointwise_linear"):
+        # FFMA GEMM: flops = 2 * rows * cin * cout ; fp32 CUDA-core peak 74.4 TFLOP/s
+        if top_key.startswith("spsk_grouped_linear"):
+            rows_n, cin, cout = a[0], a[3], a[6]
+        else:
+            rows_n, cin, cout = a[0] * a[1], a[3], a[6]
+        flops = 2.0 * rows_n * cin * cout
+        peak = 74.4
+        roof = {"kernel": top_key, "bound": "tensor", "achieved": flops / avg_s / 1e12, "peak": peak, "unit": "TFLOP/s",
+                "frac": flops / avg_s / 1e12 / peak, "traffic": None,
+                "note": "fp32 FFMA path: peak is the fp32 CUDA-core peak (148 SM x 128 lanes x 2 x 1.965 GHz), not the tensor peak"}
+    else:
+        roof = {"kernel": top_key, "bound": "hbm", "achieved": None, "peak": hbm, "unit": "GB/s", "frac": None, "traffic": None}
+    roof["peak_source"] = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
+    return roof, rows
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text())
+        except Exception:
+            return {}
+    return {}
+
+
+# --------------------------------------------------------------------------------------------------
+# arms
+# --------------------------------------------------------------------------------------------------
+
+def timed_region(pipe, inputs, steps, warmup, host: bool, world: int):
+    """W warm-up steps, then EXACTLY K steps bracketed by barrier + synchronize; device-side events."""
+    import torch.distributed as dist
+
+    submit = pipe.submit_host if host else pipe.submit_device
+    for i in range(warmup):
+        submit(inputs[i % len(inputs)])
+    pipe.sync()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    main = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(main)
+    pipe.fork(main)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        submit(inputs[(warmup + i) % len(inputs)])
+    pipe.join(main)
+    e1.record(main)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms, wall
+
+
+class EagerRef:
+    """Adapter giving the reference backbone the same submit/sync surface (no graphs: its forward host-syncs)."""
+
+    def __init__(self, net, outputs=("centers_features", "centers")):
+        self.net, self.outputs = net, outputs
+        self.stream = torch.cuda.current_stream()
+        self.host_outs = None
+        self.dev_in = torch.zeros((BATCH * NPTS, NCOLS), dtype=torch.float32, device="cuda")
+        self.last = None
+
+    def _fwd(self, pts):
+        with torch.no_grad():
+            out = self.net({"batch_size": BATCH, "points": pts})
+        self.last = {k: out[k] for k in self.outputs}
+
+    def submit_device(self, dev_points):
+        self._fwd(dev_points)
+
+    def submit_host(self, host_points):
+        self.dev_in.copy_(host_points, non_blocking=True)
+        self._fwd(self.dev_in)
+        if self.host_outs is None:
+            self.host_outs = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in self.last.items()}
+        for k, v in self.last.items():
+            self.host_outs[k].copy_(v, non_blocking=True)
+
+    def sync(self):
+        torch.cuda.synchronize()
+
+    def fork(self, stream):
+        pass
+
+    def join(self, stream):
+        pass
+
+    def h2d_bytes(self):
+        return BATCH * NPTS * NCOLS * 4
+
+    def d2h_bytes(self):
+        return sum(v.numel() * v.element_size() for v in self.last.values())
+
+
+def load_reference_backbone(state_dict):
+    ref_root = ROOT / "oracle" / "_ref"
+    so = ref_root / "pcdet" / "ops" / "pointnet2" / "pointnet2_batch" / "pointnet2_batch_cuda.so"
+    if not so.exists():
+        raise RuntimeError("oracle/_ref not built (run oracle/build_ref.sh where /root/reference exists)")
+    import importlib
+    import warnings
+
+    sys.path.insert(0, str(ref_root))
+    from spsnet_b200 import backbone as bb
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mod = importlib.import_module("pcdet.models.backbones_3d.IASSD_backbone")
+    net = mod.IASSD_Backbone(bb.kitti_iassd_cfg(), num_class=3, input_channels=4)
+    net.load_state_dict(state_dict)
+    return net.eval()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cpu"])
+    ap.add_argument("--depth", type=int, default=3, help="pipeline slots (streams) of BackbonePipeline")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--pool", type=int, default=0, help="distinct input batches (0 = enough to exceed L2)")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="scenes in the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--no-profile", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = dist_env()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference-cpu" or (args.impl == "reference" and not torch.cuda.is_available()):
+        return run_reference_cpu(args, rank, world)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    peaks = load_peaks()
+    net = build_net()
+    state = {k: v.clone() for k, v in net.state_dict().items()}
+    n_pool = args.pool or (L2_BYTES // (BATCH * NPTS * NCOLS * 4) + 2)
+    host_pool = make_pool(rank, n_pool)
+    dev_pool = [t.cuda() for t in host_pool]
+
+    line = {"metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+    cfg = {"workload": WORKLOAD, "batch_per_gpu": BATCH, "points_per_scene": NPTS,
+           "l2_policy": f"input pool of {n_pool} distinct batches ({n_pool * BATCH * NPTS * NCOLS * 4 / 2**20:.0f} MiB > 126 MiB L2) cycled",
+           "parallelism": f"scene-sharded x{world}, no data-path collective"}
+
+    if args.impl == "reference":
+        try:
+            ref = load_reference_backbone(state).cuda()
+        except Exception as e:  # fall back to the CPU port of the oracle
+            if rank == 0:
+                sys.stderr.write(f"[bench] reference CUDA module unavailable ({e}); using the CPU oracle port\n")
+            return run_reference_cpu(args, rank, world)
+        torch.backends.cudnn.allow_tf32 = True  # the reference's stock setting
+        pipe = EagerRef(ref)
+        pipe.submit_device(dev_pool[0])
+        pipe.sync()
+        sampler = ClockSampler(local)
+        sampler.start()
+        ms, _ = timed_region(pipe, dev_pool, args.steps, args.warmup, host=False, world=world)
+        ms_e2e, _ = timed_region(pipe, host_pool, args.steps, args.warmup, host=True, world=world)
+        clocks = sampler.stop()
+        value = world * BATCH * args.steps / (ms / 1e3)
+        e2e = world * BATCH * args.steps / (ms_e2e / 1e3)
+        line.update(impl="reference", value=value, ms_per_step=ms / args.steps, clocks=clocks, gpu_launches=None,
+                    e2e={"value": e2e, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes(), "d2h_bytes_per_step": pipe.d2h_bytes()},
+                    cpu_baseline={"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                                  "sample": "not a CPU run: the reference's own CUDA ops (pointnet2_batch rebuilt for sm_100a) + its "
+                                            "pointnet2_modules.py / IASSD_backbone.py on the same B200, cudnn.allow_tf32=True (stock); "
+                                            "use --impl reference-cpu for the CPU oracle port"})
+        cfg["reference"] = "unmodified reference from oracle/_ref on GPU (eager, as shipped)"
+        line["config"] = cfg
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+        return
+
+    # ---- our arm
+    from spsnet_b200 import _lib
+    from spsnet_b200.runtime import BackbonePipeline
+
+    net = net.cuda()
+    pipe = BackbonePipeline(net, BATCH, NPTS, NCOLS, depth=args.depth, use_graph=not args.no_graph)
+    pipe.prepare(dev_pool[0])
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, wall = timed_region(pipe, dev_pool, args.steps, args.warmup, host=False, world=world)
+    ms_e2e, _ = timed_region(pipe, host_pool, args.steps, args.warmup, host=True, world=world)
+    clocks = sampler.stop()
+    value = world * BATCH * args.steps / (ms / 1e3)
+    e2e = world * BATCH * args.steps / (ms_e2e / 1e3)
+    line.update(impl="ours", value=value, ms_per_step=ms / args.steps, clocks=clocks,
+                gpu_launches=int(pipe.launches_per_step * args.steps),
+                e2e={"value": e2e, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes(), "d2h_bytes_per_step": pipe.d2h_bytes()})
+    cfg.update(pipeline_depth=args.depth, cuda_graph=not args.no_graph, launches_per_step=int(pipe.launches_per_step))
+
+    if rank == 0 and not args.no_profile:
+        table, psteps = profile_kernels(net, dev_pool, steps=min(args.steps, 5))
+        roof, rows = roofline_from_table(table, psteps, peaks)
+        line["roofline"] = roof
+        line["kernels"] = rows[:12]
+        line["eager_ms_per_step_sum_of_kernels"] = sum(r["ms_per_step"] for r in rows)
+    if rank == 0 and world == 1 and args.cpu_sample > 0:
+        try:
+            line["cpu_baseline"] = cpu_baseline(build_net(), args.cpu_sample)
+        except Exception as e:  # pragma: no cover
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+    line["config"] = cfg
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference_cpu(args, rank, world):
+    """CPU oracle port as the reference arm (only when the rebuilt reference cannot run): rank 0 only."""
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    net = build_net()
+    from oracle import oracle as O
+    from spsnet_b200 import scenes
+
+    sample = 2
+    pts = [scenes.make_batch(i * sample, sample, NPTS, "kitti") for i in range(2)]
+    for _ in range(min(args.warmup, 1)):
+        O.backbone_forward(net, pts[0][:1], dtype=torch.float32)
+    steps = min(args.steps, 5)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        O.backbone_forward(net, pts[i % 2], dtype=torch.float32)
+    dt = time.perf_counter() - t0
+    v = sample * steps / dt
+    cores = max(O.num_threads(), torch.get_num_threads())
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": f"each step = {sample} scenes of the workload on the host CPU"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample} scenes per step x {steps} steps, oracle/oracle.c (OpenMP) + torch-CPU conv/BN"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

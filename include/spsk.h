@@ -1,0 +1,188 @@
+/*
+ * spsk.h -- C-ABI of the B200-native point-sampling + set-abstraction kernels (libspsk.so).
+ *
+ * This is the drop-in boundary for the hot path of AlanLiangC/SPSNet's
+ * pcdet/ops/pointnet2/pointnet2_batch.  Every entry point is `extern "C"`, takes raw DEVICE
+ * pointers, plain ints/floats and an explicit stream (a `cudaStream_t` passed as `void*`; NULL =
+ * legacy default stream), returns 0 on success or a negative spsk_status, never allocates, never
+ * synchronises and never calls exit().  No torch types appear in any signature.
+ *
+ * Section 1 mirrors, one to one, the 11 functions the reference binds through pybind11
+ * (src/pointnet2_api.cpp:10-26): same argument order and meaning, tensors replaced by their
+ * data pointers, plus the trailing stream.  INTEGRATION.md shows the ctypes / pybind stubs a
+ * maintainer of the reference adds to route `pointnet2_utils.py` through these symbols.
+ *
+ * Section 2 holds the fused entry points that replace chains of torch ops of
+ * `pointnet2_modules.py` (top-k samplers, MSG ball query, grouped shared-MLP + max-pool).
+ *
+ * Layouts (identical to the reference): xyz (B,N,3) f32, features (B,C,N) f32, indices int32,
+ * everything contiguous.  All file:line citations are relative to the reference repository.
+ */
+#ifndef SPSK_H_
+#define SPSK_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *spsk_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define SPSK_API __attribute__((visibility("default")))
+#else
+#define SPSK_API
+#endif
+
+typedef enum spsk_status {
+    SPSK_OK = 0,
+    SPSK_ERR_INVALID_ARG = -1, /* null pointer, negative size, nsample/npoint out of range */
+    SPSK_ERR_UNSUPPORTED = -2, /* shape outside what the kernels are built for (see message) */
+    SPSK_ERR_CUDA = -3,        /* launch failed; spsk_last_error() has cudaGetErrorString */
+    SPSK_ERR_WORKSPACE = -4    /* caller-provided workspace too small */
+} spsk_status;
+
+/* Human-readable description of the last error raised on the calling thread. */
+SPSK_API const char *spsk_last_error(void);
+/* ABI version of this header (bumped on any signature change). */
+SPSK_API int spsk_abi_version(void);
+/* Number of CUDA kernels this library has launched in this process (all threads). */
+SPSK_API unsigned long long spsk_launch_count(void);
+/* Compute capability the library was compiled for (100 => sm_100a). */
+SPSK_API int spsk_built_for_sm(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Section 1 -- the reference's 11 native ops
+ * ---------------------------------------------------------------------------------------------- */
+
+/* D-FPS.  Replaces farthest_point_sampling_wrapper (src/sampling.cpp:34-43 ->
+ * src/sampling_gpu.cu:93-253).  xyz (b,n,3); idx (b,m) out; idx[:,0] = 0.
+ * temp (b,n): the reference's running-min scratch, pre-filled by the caller (1e10,
+ * pointnet2_utils.py:26).  If non-NULL its contents are honoured on input and the final minima are
+ * written back, exactly like the reference.  NULL means "all 1e10" and nothing is written (the
+ * running minima live in registers).  Bit-exact indices incl. the block-tree tie-break. */
+SPSK_API int spsk_farthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx,
+                                 spsk_stream_t stream);
+
+/* F-FPS over a precomputed (b,n,n) distance matrix.  Replaces
+ * furthest_point_sampling_with_dist_wrapper (src/sampling.cpp:46-56 -> src/sampling_gpu.cu:256-416).
+ * Offsets are 64-bit here (the reference overflows int32 for b*n*n >= 2^31). */
+SPSK_API int spsk_furthest_point_sampling_with_dist(int b, int n, int m, const float *dist, float *temp,
+                                           int *idx, spsk_stream_t stream);
+
+/* out[b,c,j] = points[b,c,idx[b,j]].  Replaces gather_points_wrapper (src/sampling.cpp:11-20 ->
+ * src/sampling_gpu.cu:8-44).  points (b,c,n), idx (b,npoints), out (b,c,npoints). */
+SPSK_API int spsk_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx,
+                       float *out, spsk_stream_t stream);
+
+/* grad_points[b,c,idx[b,j]] += grad_out[b,c,j] (grad_points pre-zeroed by the caller).  Replaces
+ * gather_points_grad_wrapper (src/sampling.cpp:22-32 -> src/sampling_gpu.cu:46-84). */
+SPSK_API int spsk_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out, const int *idx,
+                            float *grad_points, spsk_stream_t stream);
+
+/* First `nsample` neighbours (index order) with d2 < radius^2; first-hit padding; rows of centres
+ * with no neighbour are left untouched (caller pre-zeroes, pointnet2_utils.py:246).  Replaces
+ * ball_query_wrapper (src/ball_query.cpp:32-42 -> src/ball_query_gpu.cu:9-67).
+ * new_xyz (b,m,3), xyz (b,n,3), idx (b,m,nsample). */
+SPSK_API int spsk_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
+                    const float *xyz, int *idx, spsk_stream_t stream);
+
+/* Shell query min_radius^2 <= d2 < max_radius^2 plus the d2 == 0 clause (a coincident point is
+ * inserted twice when min_radius == 0, as in the reference).  Replaces ball_query_dilated_wrapper
+ * (src/ball_query.cpp:45-56 -> src/ball_query_gpu.cu:70-137). */
+SPSK_API int spsk_ball_query_dilated(int b, int n, int m, float max_radius, float min_radius, int nsample,
+                            const float *new_xyz, const float *xyz, int *idx, spsk_stream_t stream);
+
+/* out[b,c,p,s] = points[b,c,idx[b,p,s]].  Replaces group_points_wrapper (src/group_points.cpp:30-40
+ * -> src/group_points_gpu.cu:53-92). */
+SPSK_API int spsk_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
+                      const int *idx, float *out, spsk_stream_t stream);
+
+/* Scatter-add backward of group_points.  Replaces group_points_grad_wrapper
+ * (src/group_points.cpp:18-28 -> src/group_points_gpu.cu:14-50). */
+SPSK_API int spsk_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,
+                           const int *idx, float *grad_points, spsk_stream_t stream);
+
+/* Three nearest known points of every unknown point: squared distances (the python layer takes the
+ * sqrt) and indices, first index wins ties.  Replaces three_nn_wrapper (src/interpolate.cpp:21-30
+ * -> src/interpolate_gpu.cu:16-81).  unknown (b,n,3), known (b,m,3), dist2/idx (b,n,3). */
+SPSK_API int spsk_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2,
+                  int *idx, spsk_stream_t stream);
+
+/* out[b,c,j] = sum_i weight[b,j,i] * points[b,c,idx[b,j,i]] with the reference build's rounding
+ * order.  Replaces three_interpolate_wrapper (src/interpolate.cpp:32-44 ->
+ * src/interpolate_gpu.cu:84-124).  points (b,c,m), idx/weight (b,n,3), out (b,c,n). */
+SPSK_API int spsk_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,
+                           const float *weight, float *out, spsk_stream_t stream);
+
+/* Backward of three_interpolate (grad_points pre-zeroed).  Replaces three_interpolate_grad_wrapper
+ * (src/interpolate.cpp:46-58 -> src/interpolate_gpu.cu:127-169). */
+SPSK_API int spsk_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                                const float *weight, float *grad_points, spsk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Section 2 -- fused replacements for torch-op chains in pointnet2_modules.py
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Score-based down-sampling: one launch replaces max -> sigmoid -> topk -> int() (IA-SSD ctr/cls-aware,
+ * pointnet2_modules.py:287-291) and, when stds != NULL, SPSNet's stability-weighted variant
+ * score = sigmoid(max_c cls) * (1 - sigmoid(stds/8 - 3)) (pointnet2_modules.py:293-303).
+ * cls (b,n,num_class) f32; stds (b,n) f32 or NULL; idx (b,npoint) out, ordered by descending score,
+ * ties broken by ascending point index; scores (b,npoint) out or NULL (the picked scores).
+ * n <= SPSK_TOPK_MAX_N. */
+#define SPSK_TOPK_MAX_N 16384
+SPSK_API int spsk_score_topk(int b, int n, int num_class, int npoint, const float *cls, const float *stds,
+                    int *idx, float *scores, spsk_stream_t stream);
+
+/* Point-major row gather: out[b,j,:] = in[b,idx[b,j],:], in (b,n,c), out (b,m,c).  With c = 3 this is
+ * new_xyz = xyz[sample_idx], replacing transpose -> gather_operation -> transpose -> contiguous
+ * (pointnet2_modules.py:261,424). */
+SPSK_API int spsk_gather_rows(int b, int n, int m, int c, const float *in, const int *idx, float *out,
+                     spsk_stream_t stream);
+
+/* Multi-scale ball query: ONE scan of xyz per centre answers up to SPSK_MAX_SCALES radii
+ * (replaces the per-scale ball_query calls of QueryAndGroup.forward, pointnet2_utils.py:307, inside
+ * the MSG loop pointnet2_modules.py:429-431).  idx[s] is (b,m,nsample[s]); unlike spsk_ball_query
+ * empty rows ARE written (zeros), so no memset is needed.  Results identical to nscales separate
+ * spsk_ball_query calls on zero-filled outputs. */
+#define SPSK_MAX_SCALES 4
+SPSK_API int spsk_ball_query_msg(int b, int n, int m, int nscales, const float *radius, const int *nsample,
+                        const float *new_xyz, const float *xyz, int *const *idx, spsk_stream_t stream);
+
+/* One shared-MLP layer over grouped rows, the unit the SA layer is built from (replaces
+ * grouping_operation x2 + subtract + cat + Conv2d1x1 + BatchNorm2d(eval) + ReLU [+ max_pool2d],
+ * pointnet2_utils.py:307-315 and pointnet2_modules.py:204-211,431-436).
+ *
+ *   rows r = (b, p, s), p < m centres, s < nsample.
+ *   input row  (gather != 0): [xyz[b,idx]-new_xyz[b,p] (3, if use_xyz), features[b,:,idx] (c_feat)]
+ *   input row  (gather == 0): in_rows[r, 0:c_in]                    (row-major workspace)
+ *   y[r, co] = relu?( bias[co] + sum_k in[r,k] * wt[k, co] )         wt is (c_in, c_out) = W^T, BN folded
+ *   pool == 0: out_rows[r, 0:c_out]                                  (row-major workspace)
+ *   pool == 1: out_pooled[b, co_off + co, p] = max_s y  (relu must be on; out_pooled pre-zeroed,
+ *              (b, c_total, m) layout = the reference's new_features)
+ *   pool == 2: avg over s (pool_method 'avg_pool'), out_pooled pre-zeroed.
+ */
+typedef struct spsk_group_desc {
+    int b, n, m, nsample;  /* scenes, source points, centres, neighbours per centre            */
+    int c_feat;            /* feature channels gathered per neighbour (0 if features == NULL)  */
+    int use_xyz;           /* prepend the 3 relative coordinates                               */
+    const float *xyz;      /* (b,n,3)                                                          */
+    const float *new_xyz;  /* (b,m,3)                                                          */
+    const float *features; /* (b,c_feat,n) or NULL                                             */
+    const int *idx;        /* (b,m,nsample)                                                    */
+} spsk_group_desc;
+
+SPSK_API int spsk_grouped_linear(const spsk_group_desc *g, int gather, const float *in_rows, int c_in,
+                        const float *wt, const float *bias, int c_out, int relu, int pool,
+                        float *out_rows, float *out_pooled, int c_total, int co_off,
+                        spsk_stream_t stream);
+
+/* Point-wise (1x1 Conv1d) layer on channel-major tensors, used for the aggregation / confidence /
+ * vote MLPs (pointnet2_modules.py:216-243,449-455,485-500):
+ *   out[b, co, p] = relu?( bias[co] + sum_k in[b, k, p] * wt[k, co] ),  in (b,c_in,m), out (b,c_out,m). */
+SPSK_API int spsk_pointwise_linear(int b, int m, const float *in, int c_in, const float *wt, const float *bias,
+                          int c_out, int relu, float *out, spsk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPSK_H_ */

@@ -1,0 +1,93 @@
+"""ctypes binding of libspsk.so (include/spsk.h) -- the only way the Python layer reaches the kernels.
+
+There is NO fallback: if the CUDA library is missing or does not export a symbol declared in
+include/spsk.h, importing this module raises.  Build it with `python -m spsnet_b200.build`
+(or `__graft_entry__.build()`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_ROOT = Path(__file__).resolve().parent
+LIB_PATH = Path(os.environ.get("SPSK_LIB", _ROOT / "_C" / "libspsk.so"))
+
+_f = C.c_float
+_i = C.c_int
+_p = C.c_void_p
+
+# name -> argtypes (all return int unless listed in _RESTYPE)
+SIGNATURES = {
+    "spsk_last_error": [],
+    "spsk_abi_version": [],
+    "spsk_built_for_sm": [],
+    "spsk_launch_count": [],
+    "spsk_farthest_point_sampling": [_i, _i, _i, _p, _p, _p, _p],
+    "spsk_furthest_point_sampling_with_dist": [_i, _i, _i, _p, _p, _p, _p],
+    "spsk_gather_points": [_i, _i, _i, _i, _p, _p, _p, _p],
+    "spsk_gather_points_grad": [_i, _i, _i, _i, _p, _p, _p, _p],
+    "spsk_ball_query": [_i, _i, _i, _f, _i, _p, _p, _p, _p],
+    "spsk_ball_query_dilated": [_i, _i, _i, _f, _f, _i, _p, _p, _p, _p],
+    "spsk_group_points": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
+    "spsk_group_points_grad": [_i, _i, _i, _i, _i, _p, _p, _p, _p],
+    "spsk_three_nn": [_i, _i, _i, _p, _p, _p, _p, _p],
+    "spsk_three_interpolate": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
+    "spsk_three_interpolate_grad": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
+    "spsk_score_topk": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
+    "spsk_gather_rows": [_i, _i, _i, _i, _p, _p, _p, _p],
+    "spsk_ball_query_msg": [_i, _i, _i, _i, C.POINTER(_f), C.POINTER(_i), _p, _p, C.POINTER(_p), _p],
+    "spsk_grouped_linear": [_p, _i, _p, _i, _p, _p, _i, _i, _i, _p, _p, _i, _i, _p],
+    "spsk_pointwise_linear": [_i, _i, _p, _i, _p, _p, _i, _i, _p, _p],
+}
+_RESTYPE = {"spsk_last_error": C.c_char_p, "spsk_launch_count": C.c_ulonglong}
+
+
+class GroupDesc(C.Structure):
+    """struct spsk_group_desc (include/spsk.h)."""
+
+    _fields_ = [
+        ("b", _i), ("n", _i), ("m", _i), ("nsample", _i),
+        ("c_feat", _i), ("use_xyz", _i),
+        ("xyz", _p), ("new_xyz", _p), ("features", _p), ("idx", _p),
+    ]
+
+
+def declared_symbols(header: Path | None = None) -> list[str]:
+    """Every function name include/spsk.h declares (used by the CPU tests to check the exports)."""
+    import re
+
+    header = header or (_ROOT.parent / "include" / "spsk.h")
+    txt = header.read_text()
+    return sorted(set(re.findall(r"SPSK_API\s+[\w\s\*]+?\b(spsk_\w+)\s*\(", txt)))
+
+
+def _load() -> C.CDLL:
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"spsnet_b200: CUDA library {LIB_PATH} not found. There is no CPU fallback; "
+            "build it with `python -m spsnet_b200.build`."
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    for name, argtypes in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:  # pragma: no cover
+            raise ImportError(f"spsnet_b200: {LIB_PATH} does not export {name}") from e
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPE.get(name, _i)
+    return lib
+
+
+lib = _load()
+
+
+class SpskError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str = "") -> None:
+    """Turn a negative spsk_status into an exception (the reference exit(-1)s instead)."""
+    if rc != 0:
+        msg = lib.spsk_last_error()
+        raise SpskError(f"{what or 'spsk'} failed with status {rc}: {msg.decode() if msg else ''}")

@@ -1,0 +1,207 @@
+"""The callers of the hot path: IA-SSD's `IASSD_Backbone` and SPSNet-IA's `PAGNet_Backbone`.
+
+Mirrors reference pcdet/models/backbones_3d/IASSD_backbone.py:10-212 and PAGNet_backbone.py:10-237: same
+constructor `(model_cfg, num_class, input_channels)`, same `SA_modules` ModuleList (so backbone
+checkpoints load), same `batch_dict` keys on output.  `model_cfg` may be the reference's EasyDict or a
+plain dict (wrapped in `Cfg`).  Differences: the per-scene point-count loop + host-sync assert
+(IASSD_backbone.py:116-120) is replaced by a shape check, and PAGNet's optional DenseEdgeConv surface
+feature (`USE_SURFACE`) is not built.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Any
+
+import torch
+import torch.nn as nn
+
+from . import pointnet2_modules
+
+
+class Cfg(dict):
+    """dict with attribute access and `.get`, enough for the reference's `model_cfg.SA_CONFIG.X` style."""
+
+    def __getattr__(self, k):
+        try:
+            v = self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+        return Cfg(v) if isinstance(v, dict) and not isinstance(v, Cfg) else v
+
+    def get(self, k, default=None):
+        v = super().get(k, default)
+        return Cfg(v) if isinstance(v, dict) and not isinstance(v, Cfg) else v
+
+
+# reference: tools/cfgs/kitti_models/IA-SSD.yaml:33-57
+KITTI_IASSD_SA_CONFIG = {
+    "NPOINT_LIST": [[4096], [1024], [512], [256], [-1], [256]],
+    "SAMPLE_RANGE_LIST": [[-1], [-1], [-1], [-1], [-1], [-1]],
+    "SAMPLE_METHOD_LIST": [["D-FPS"], ["D-FPS"], ["ctr_aware"], ["ctr_aware"], [], []],
+    "RADIUS_LIST": [[0.2, 0.8], [0.8, 1.6], [1.6, 4.8], [], [], [4.8, 6.4]],
+    "NSAMPLE_LIST": [[16, 32], [16, 32], [16, 32], [], [], [16, 32]],
+    "MLPS": [[[16, 16, 32], [32, 32, 64]],
+             [[64, 64, 128], [64, 96, 128]],
+             [[128, 128, 256], [128, 256, 256]],
+             [],
+             [128],
+             [[256, 256, 512], [256, 512, 1024]]],
+    "LAYER_TYPE": ["SA_Layer", "SA_Layer", "SA_Layer", "SA_Layer", "Vote_Layer", "SA_Layer"],
+    "DILATED_GROUP": [False, False, False, False, False, False],
+    "AGGREGATION_MLPS": [[64], [128], [256], [256], [], [512]],
+    "CONFIDENCE_MLPS": [[], [128], [256], [], [], []],
+    "LAYER_INPUT": [0, 1, 2, 3, 4, 3],
+    "CTR_INDEX": [-1, -1, -1, -1, -1, 5],
+    "MAX_TRANSLATE_RANGE": [3.0, 3.0, 2.0],
+}
+
+
+def kitti_iassd_cfg() -> Cfg:
+    """IA-SSD KITTI backbone: 16384 -> 4096 (D-FPS) -> 1024 (D-FPS) -> 512 (ctr) -> 256 (ctr) -> vote -> SA."""
+    return Cfg({"SA_CONFIG": copy.deepcopy(KITTI_IASSD_SA_CONFIG)})
+
+
+def kitti_spsnet_cfg() -> Cfg:
+    """SPSNet-IA (reference tools/cfgs/kitti_models/SPSNet.yaml:38-71): stability-aware top-k in layers 2, 3.
+    The surface-feature branch (USE_SURFACE) is out of scope, so layer 1 keeps IA-SSD's 64-wide MLP."""
+    c = copy.deepcopy(KITTI_IASSD_SA_CONFIG)
+    c["SAMPLE_METHOD_LIST"] = [["D-FPS"], ["D-FPS"], ["sss_aware"], ["sss_aware"], [], []]
+    c["SS_RADIUS_LIST"] = [[0.05], [0.2], [], [], [], []]
+    c["SS_NSAMPLE_LIST"] = [[16], [16], [], [], [], [1]]
+    return Cfg({"SA_CONFIG": c})
+
+
+def waymo_iassd_cfg() -> Cfg:
+    """reference tools/cfgs/waymo_models/IA-SSD.yaml:45-65: all point counts x4."""
+    c = copy.deepcopy(KITTI_IASSD_SA_CONFIG)
+    c["NPOINT_LIST"] = [[16384], [4096], [2048], [1024], [-1], [1024]]
+    return Cfg({"SA_CONFIG": c})
+
+
+class IASSD_Backbone(nn.Module):
+    """Backbone for IA-SSD (reference IASSD_backbone.py:7-212)."""
+
+    _pass_stds = False
+
+    def __init__(self, model_cfg: Any, num_class: int, input_channels: int, **kwargs):
+        super().__init__()
+        if isinstance(model_cfg, dict) and not isinstance(model_cfg, Cfg):
+            model_cfg = Cfg(model_cfg)
+        self.model_cfg = model_cfg
+        self.num_class = num_class
+        sa = model_cfg.SA_CONFIG
+        self.layer_types = sa.LAYER_TYPE
+        self.ctr_idx_list = sa.CTR_INDEX
+        self.layer_inputs = sa.LAYER_INPUT
+        self.aggregation_mlps = sa.get("AGGREGATION_MLPS", None)
+        self.confidence_mlps = sa.get("CONFIDENCE_MLPS", None)
+        self.max_translate_range = sa.get("MAX_TRANSLATE_RANGE", None)
+
+        self.SA_modules = nn.ModuleList()
+        channel_in = input_channels - 3
+        channel_out_list = [channel_in]
+        channel_out = channel_in
+        for k in range(len(sa.NSAMPLE_LIST)):
+            src = self.layer_inputs[k][-1] if isinstance(self.layer_inputs[k], list) else self.layer_inputs[k]
+            channel_in = channel_out_list[src]
+            if self.layer_types[k] == "SA_Layer":
+                mlps = [[channel_in] + list(spec) for spec in sa.MLPS[k]]
+                channel_out = sum(spec[-1] for spec in mlps)
+                agg = list(self.aggregation_mlps[k]) if self.aggregation_mlps and self.aggregation_mlps[k] else None
+                if agg:
+                    channel_out = agg[-1]
+                conf = list(self.confidence_mlps[k]) if self.confidence_mlps and self.confidence_mlps[k] else None
+                extra = {}
+                if sa.get("SS_RADIUS_LIST", None) is not None:
+                    extra = {"ss_radii": sa.SS_RADIUS_LIST[k], "ss_nsamples": sa.SS_NSAMPLE_LIST[k]}
+                self.SA_modules.append(pointnet2_modules.PointnetSAModuleMSG_WithSampling(
+                    npoint_list=sa.NPOINT_LIST[k], sample_range_list=sa.SAMPLE_RANGE_LIST[k],
+                    sample_type_list=sa.SAMPLE_METHOD_LIST[k], radii=sa.RADIUS_LIST[k], nsamples=sa.NSAMPLE_LIST[k],
+                    mlps=mlps, use_xyz=True, dilated_group=sa.DILATED_GROUP[k], aggregation_mlp=agg,
+                    confidence_mlp=conf, num_class=self.num_class, **extra))
+            elif self.layer_types[k] == "Vote_Layer":
+                self.SA_modules.append(pointnet2_modules.Vote_layer(
+                    mlp_list=sa.MLPS[k], pre_channel=channel_out_list[self.layer_inputs[k]],
+                    max_translate_range=self.max_translate_range))
+            channel_out_list.append(channel_out)
+        self.num_point_features = channel_out
+
+    @staticmethod
+    def break_up_pc(pc):
+        batch_idx = pc[:, 0]
+        xyz = pc[:, 1:4].contiguous()
+        features = pc[:, 4:].contiguous() if pc.size(-1) > 4 else None
+        return batch_idx, xyz, features
+
+    def forward(self, batch_dict):
+        """batch_dict['points']: (B*N, 1+3+C) rows [batch_idx, x, y, z, feat...], equal N per scene."""
+        batch_size = batch_dict["batch_size"]
+        points = batch_dict["points"]
+        if points.shape[0] % batch_size != 0:
+            raise RuntimeError("every scene must hold the same number of points (reference asserts min == max)")
+        batch_idx, xyz, features = self.break_up_pc(points)
+        stds = batch_dict.get("stds", None) if self._pass_stds else None
+        xyz = xyz.view(batch_size, -1, 3)
+        if features is not None:
+            features = features.view(batch_size, -1, features.shape[-1]).permute(0, 2, 1).contiguous()
+        bidx2d = batch_idx.view(batch_size, -1)
+
+        encoder_xyz, encoder_features, sa_ins_preds = [xyz], [features], []
+        encoder_coords = [torch.cat([bidx2d.unsqueeze(-1), xyz], dim=-1)]
+        li_cls_pred = None
+        centers = centers_origin = ctr_offsets = None
+        for i, module in enumerate(self.SA_modules):
+            xyz_input = encoder_xyz[self.layer_inputs[i]]
+            feature_input = encoder_features[self.layer_inputs[i]]
+            if self.layer_types[i] == "SA_Layer":
+                ctr_xyz = encoder_xyz[self.ctr_idx_list[i]] if self.ctr_idx_list[i] != -1 else None
+                kw = {"stds": stds} if self._pass_stds else {}
+                li_xyz, li_features, li_cls_pred, _, stds_out = module(xyz_input, feature_input, li_cls_pred, ctr_xyz=ctr_xyz, **kw)
+                if self._pass_stds:
+                    stds = stds_out
+            else:  # Vote_Layer
+                li_xyz, li_features, xyz_select, ctr_offsets = module(xyz_input, feature_input)
+                centers, centers_origin = li_xyz, xyz_select
+                encoder_coords.append(torch.cat([bidx2d[:, :centers_origin.shape[1], None].float(),
+                                                 centers_origin.view(batch_size, -1, 3)], dim=-1))
+            encoder_xyz.append(li_xyz)
+            encoder_coords.append(torch.cat([bidx2d[:, :li_xyz.shape[1], None].float(), li_xyz.view(batch_size, -1, 3)], dim=-1))
+            encoder_features.append(li_features)
+            if li_cls_pred is not None:
+                sa_ins_preds.append(torch.cat([bidx2d[:, :li_cls_pred.shape[1], None].float(),
+                                               li_cls_pred.reshape(batch_size, -1, li_cls_pred.shape[-1])], dim=-1))
+            else:
+                sa_ins_preds.append([])
+
+        ctr_batch_idx = bidx2d[:, :li_xyz.shape[1]].contiguous().view(-1)
+        batch_dict["ctr_offsets"] = torch.cat((ctr_batch_idx[:, None].float(), ctr_offsets.contiguous().view(-1, 3)), dim=1)
+        batch_dict["centers"] = torch.cat((ctr_batch_idx[:, None].float(), centers.contiguous().view(-1, 3)), dim=1)
+        batch_dict["centers_origin"] = torch.cat((ctr_batch_idx[:, None].float(), centers_origin.contiguous().view(-1, 3)), dim=1)
+        last = encoder_features[-1]
+        batch_dict["centers_features"] = last.permute(0, 2, 1).contiguous().view(-1, last.shape[1])
+        batch_dict["ctr_batch_idx"] = ctr_batch_idx
+        batch_dict["encoder_xyz"] = encoder_xyz
+        batch_dict["encoder_coords"] = encoder_coords
+        batch_dict["sa_ins_preds"] = sa_ins_preds
+        batch_dict["encoder_features"] = encoder_features
+        return batch_dict
+
+
+class PAGNet_Backbone(IASSD_Backbone):
+    """SPSNet-IA backbone (reference PAGNet_backbone.py:7-237): IA-SSD's backbone threading the
+    per-point stability `batch_dict['stds']` through every SA layer (PAGNet_backbone.py:117,150)."""
+
+    _pass_stds = True
+
+
+def randomize_bn_stats(module: nn.Module, seed: int = 0) -> None:
+    """Seeded non-trivial BN affine + running statistics so the BN fold is exercised."""
+    g = torch.Generator().manual_seed(seed)
+    for m in module.modules():
+        if isinstance(m, (nn.BatchNorm1d, nn.BatchNorm2d)):
+            with torch.no_grad():
+                n = m.num_features
+                m.weight.copy_(torch.empty(n).uniform_(0.5, 1.5, generator=g))
+                m.bias.copy_(torch.randn(n, generator=g) * 0.1)
+                m.running_mean.copy_(torch.randn(n, generator=g) * 0.1)
+                m.running_var.copy_(torch.empty(n).uniform_(0.5, 1.5, generator=g))

@@ -1,0 +1,410 @@
+"""Drop-in for the reference's `pcdet/ops/pointnet2/pointnet2_batch/pointnet2_utils.py`.
+
+Same public names, positional signatures, return dtypes and autograd behaviour
+(reference pointnet2_utils.py:36,65,101,133,181,225,256,287-384); every native call goes through the
+C-ABI of include/spsk.h (libspsk.so, hand-written sm_100a CUDA) on torch's current stream.  Differences,
+all deliberate: preconditions raise instead of `assert`/`exit(-1)`; kernels are stream-explicit; FPS
+keeps its running minima on chip (no `temp` tensor unless n > 16384).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Tuple
+
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from ._lib import GroupDesc, check, lib
+
+__all__ = [
+    "farthest_point_sample", "furthest_point_sample", "furthest_point_sample_with_dist", "gather_operation",
+    "three_nn", "three_interpolate", "grouping_operation", "ball_query", "ball_query_dilated",
+    "QueryAndGroup", "QueryDilatedAndGroup", "GroupAll",
+    "score_topk", "gather_rows", "ball_query_msg",
+]
+
+FPS_ONCHIP_MAX_N = 16384
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: torch.Tensor, name: str, dtype: torch.dtype, ndim: int) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    if t.dim() != ndim:
+        raise RuntimeError(f"{name} must have {ndim} dims, got shape {tuple(t.shape)}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+
+
+class FarthestPointSampling(Function):
+    """reference: pointnet2_utils.py:10-33 (FarthestPointSampling)."""
+
+    @staticmethod
+    def forward(ctx, xyz: torch.Tensor, npoint: int) -> torch.Tensor:
+        _chk(xyz, "xyz", torch.float32, 3)
+        B, N, _ = xyz.shape
+        if xyz.shape[2] != 3:
+            raise RuntimeError("xyz must be (B, N, 3)")
+        output = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
+        temp = None
+        if N > FPS_ONCHIP_MAX_N:
+            temp = torch.full((B, N), 1e10, dtype=torch.float32, device=xyz.device)
+        with torch.cuda.device(xyz.device):
+            check(lib.spsk_farthest_point_sampling(B, N, npoint, xyz.data_ptr(), temp.data_ptr() if temp is not None else None,
+                                                   output.data_ptr(), _stream()), "farthest_point_sampling")
+        return output
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return None, None
+
+
+farthest_point_sample = furthest_point_sample = FarthestPointSampling.apply
+
+
+class FurthestPointSamplingWithDist(Function):
+    """reference: pointnet2_utils.py:39-62 (FurthestPointSamplingWithDist); xyz is a (B,N,N) distance matrix."""
+
+    @staticmethod
+    def forward(ctx, xyz: torch.Tensor, npoint: int) -> torch.Tensor:
+        _chk(xyz, "dist", torch.float32, 3)
+        B, N, N2 = xyz.shape
+        if N != N2:
+            raise RuntimeError("distance matrix must be (B, N, N)")
+        output = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
+        temp = None
+        if N > FPS_ONCHIP_MAX_N:
+            temp = torch.full((B, N), 1e10, dtype=torch.float32, device=xyz.device)
+        with torch.cuda.device(xyz.device):
+            check(lib.spsk_furthest_point_sampling_with_dist(B, N, npoint, xyz.data_ptr(),
+                                                             temp.data_ptr() if temp is not None else None,
+                                                             output.data_ptr(), _stream()), "furthest_point_sampling_with_dist")
+        return output
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return None, None
+
+
+furthest_point_sample_with_dist = FurthestPointSamplingWithDist.apply
+
+
+class GatherOperation(Function):
+    """reference: pointnet2_utils.py:67-98 (GatherOperation)."""
+
+    @staticmethod
+    def forward(ctx, features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        _chk(features, "features", torch.float32, 3)
+        _chk(idx, "idx", torch.int32, 2)
+        B, npoint = idx.shape
+        _, Cc, N = features.shape
+        output = torch.empty((B, Cc, npoint), dtype=torch.float32, device=features.device)
+        with torch.cuda.device(features.device):
+            check(lib.spsk_gather_points(B, Cc, N, npoint, features.data_ptr(), idx.data_ptr(), output.data_ptr(), _stream()),
+                  "gather_points")
+        ctx.for_backwards = (idx, Cc, N)
+        return output
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, Cc, N = ctx.for_backwards
+        B, npoint = idx.shape
+        grad_features = torch.zeros((B, Cc, N), dtype=torch.float32, device=grad_out.device)
+        g = grad_out.detach().contiguous()
+        with torch.cuda.device(g.device):
+            check(lib.spsk_gather_points_grad(B, Cc, N, npoint, g.data_ptr(), idx.data_ptr(), grad_features.data_ptr(), _stream()),
+                  "gather_points_grad")
+        return grad_features, None
+
+
+gather_operation = GatherOperation.apply
+
+
+class ThreeNN(Function):
+    """reference: pointnet2_utils.py:104-130 (ThreeNN); returns (sqrt(dist2), idx)."""
+
+    @staticmethod
+    def forward(ctx, unknown: torch.Tensor, known: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        _chk(unknown, "unknown", torch.float32, 3)
+        _chk(known, "known", torch.float32, 3)
+        B, N, _ = unknown.shape
+        m = known.shape[1]
+        dist2 = torch.empty((B, N, 3), dtype=torch.float32, device=unknown.device)
+        idx = torch.empty((B, N, 3), dtype=torch.int32, device=unknown.device)
+        with torch.cuda.device(unknown.device):
+            check(lib.spsk_three_nn(B, N, m, unknown.data_ptr(), known.data_ptr(), dist2.data_ptr(), idx.data_ptr(), _stream()),
+                  "three_nn")
+        ctx.mark_non_differentiable(idx)
+        return torch.sqrt(dist2), idx
+
+    @staticmethod
+    def backward(ctx, a=None, b=None):
+        return None, None
+
+
+three_nn = ThreeNN.apply
+
+
+class ThreeInterpolate(Function):
+    """reference: pointnet2_utils.py:136-178 (ThreeInterpolate)."""
+
+    @staticmethod
+    def forward(ctx, features: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+        _chk(features, "features", torch.float32, 3)
+        _chk(idx, "idx", torch.int32, 3)
+        _chk(weight, "weight", torch.float32, 3)
+        B, c, m = features.shape
+        n = idx.shape[1]
+        ctx.three_interpolate_for_backward = (idx, weight, m)
+        output = torch.empty((B, c, n), dtype=torch.float32, device=features.device)
+        with torch.cuda.device(features.device):
+            check(lib.spsk_three_interpolate(B, c, m, n, features.data_ptr(), idx.data_ptr(), weight.data_ptr(),
+                                             output.data_ptr(), _stream()), "three_interpolate")
+        return output
+
+    @staticmethod
+    def backward(ctx, grad_out: torch.Tensor):
+        idx, weight, m = ctx.three_interpolate_for_backward
+        B, c, n = grad_out.shape
+        grad_features = torch.zeros((B, c, m), dtype=torch.float32, device=grad_out.device)
+        g = grad_out.detach().contiguous()
+        with torch.cuda.device(g.device):
+            check(lib.spsk_three_interpolate_grad(B, c, n, m, g.data_ptr(), idx.data_ptr(), weight.data_ptr(),
+                                                  grad_features.data_ptr(), _stream()), "three_interpolate_grad")
+        return grad_features, None, None
+
+
+three_interpolate = ThreeInterpolate.apply
+
+
+class GroupingOperation(Function):
+    """reference: pointnet2_utils.py:184-222 (GroupingOperation)."""
+
+    @staticmethod
+    def forward(ctx, features: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        _chk(features, "features", torch.float32, 3)
+        _chk(idx, "idx", torch.int32, 3)
+        B, nfeatures, nsample = idx.shape
+        _, Cc, N = features.shape
+        output = torch.empty((B, Cc, nfeatures, nsample), dtype=torch.float32, device=features.device)
+        with torch.cuda.device(features.device):
+            check(lib.spsk_group_points(B, Cc, N, nfeatures, nsample, features.data_ptr(), idx.data_ptr(),
+                                        output.data_ptr(), _stream()), "group_points")
+        ctx.for_backwards = (idx, N)
+        return output
+
+    @staticmethod
+    def backward(ctx, grad_out: torch.Tensor):
+        idx, N = ctx.for_backwards
+        B, Cc, npoint, nsample = grad_out.shape
+        grad_features = torch.zeros((B, Cc, N), dtype=torch.float32, device=grad_out.device)
+        g = grad_out.detach().contiguous()
+        with torch.cuda.device(g.device):
+            check(lib.spsk_group_points_grad(B, Cc, N, npoint, nsample, g.data_ptr(), idx.data_ptr(),
+                                             grad_features.data_ptr(), _stream()), "group_points_grad")
+        return grad_features, None
+
+
+grouping_operation = GroupingOperation.apply
+
+
+class BallQuery(Function):
+    """reference: pointnet2_utils.py:228-253 (BallQuery); note the (radius, nsample, xyz, new_xyz) order."""
+
+    @staticmethod
+    def forward(ctx, radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
+        _chk(new_xyz, "new_xyz", torch.float32, 3)
+        _chk(xyz, "xyz", torch.float32, 3)
+        B, N, _ = xyz.shape
+        npoint = new_xyz.shape[1]
+        idx = torch.zeros((B, npoint, nsample), dtype=torch.int32, device=xyz.device)
+        with torch.cuda.device(xyz.device):
+            check(lib.spsk_ball_query(B, N, npoint, float(radius), int(nsample), new_xyz.data_ptr(), xyz.data_ptr(),
+                                      idx.data_ptr(), _stream()), "ball_query")
+        return idx
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return None, None, None, None
+
+
+ball_query = BallQuery.apply
+
+
+class BallQueryDilated(Function):
+    """reference: pointnet2_utils.py:258-284 (BallQueryDilated)."""
+
+    @staticmethod
+    def forward(ctx, max_radius: float, min_radius: float, nsample: int, xyz: torch.Tensor, new_xyz: torch.Tensor) -> torch.Tensor:
+        _chk(new_xyz, "new_xyz", torch.float32, 3)
+        _chk(xyz, "xyz", torch.float32, 3)
+        B, N, _ = xyz.shape
+        npoint = new_xyz.shape[1]
+        idx = torch.zeros((B, npoint, nsample), dtype=torch.int32, device=xyz.device)
+        with torch.cuda.device(xyz.device):
+            check(lib.spsk_ball_query_dilated(B, N, npoint, float(max_radius), float(min_radius), int(nsample),
+                                              new_xyz.data_ptr(), xyz.data_ptr(), idx.data_ptr(), _stream()), "ball_query_dilated")
+        return idx
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return None, None, None, None, None
+
+
+ball_query_dilated = BallQueryDilated.apply
+
+
+def _group(xyz, new_xyz, features, idx, use_xyz):
+    """reference: pointnet2_utils.py:308-320 (shared tail of QueryAndGroup / QueryDilatedAndGroup)."""
+    xyz_trans = xyz.transpose(1, 2).contiguous()
+    grouped_xyz = grouping_operation(xyz_trans, idx)  # (B, 3, npoint, nsample)
+    grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)
+    if features is not None:
+        grouped_features = grouping_operation(features, idx)
+        if use_xyz:
+            return torch.cat([grouped_xyz, grouped_features], dim=1)  # (B, C + 3, npoint, nsample)
+        return grouped_features
+    assert use_xyz, "Cannot have not features and not use xyz as a feature!"
+    return grouped_xyz
+
+
+class QueryAndGroup(nn.Module):
+    """reference: pointnet2_utils.py:289-322."""
+
+    def __init__(self, radius: float, nsample: int, use_xyz: bool = True):
+        super().__init__()
+        self.radius, self.nsample, self.use_xyz = radius, nsample, use_xyz
+
+    def forward(self, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor = None) -> torch.Tensor:
+        idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
+        return _group(xyz, new_xyz, features, idx, self.use_xyz)
+
+
+class QueryDilatedAndGroup(nn.Module):
+    """reference: pointnet2_utils.py:324-359; (radius_in, radius_out) are forwarded as (max_radius, min_radius)."""
+
+    def __init__(self, radius_in: float, radius_out: float, nsample: int, use_xyz: bool = True):
+        super().__init__()
+        self.radius_in, self.radius_out, self.nsample, self.use_xyz = radius_in, radius_out, nsample, use_xyz
+
+    def forward(self, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor = None) -> torch.Tensor:
+        idx = ball_query_dilated(self.radius_in, self.radius_out, self.nsample, xyz, new_xyz)
+        return _group(xyz, new_xyz, features, idx, self.use_xyz)
+
+
+class GroupAll(nn.Module):
+    """reference: pointnet2_utils.py:361-384."""
+
+    def __init__(self, use_xyz: bool = True):
+        super().__init__()
+        self.use_xyz = use_xyz
+
+    def forward(self, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor = None):
+        grouped_xyz = xyz.transpose(1, 2).unsqueeze(2)
+        if features is not None:
+            grouped_features = features.unsqueeze(2)
+            if self.use_xyz:
+                return torch.cat([grouped_xyz, grouped_features], dim=1)  # (B, 3 + C, 1, N)
+            return grouped_features
+        return grouped_xyz
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused entry points (no counterpart function in the reference: they replace chains of torch ops in
+# pointnet2_modules.py; see include/spsk.h section 2)
+# ---------------------------------------------------------------------------------------------------
+
+def score_topk(cls_features: torch.Tensor, npoint: int, stds: torch.Tensor | None = None,
+               return_scores: bool = False):
+    """ctr/cls-aware (reference pointnet2_modules.py:287-291) or, with `stds`, SPSNet stability-aware
+    (:293-303) down-sampling indices: (B, npoint) int32, descending score, ties by ascending index."""
+    _chk(cls_features, "cls_features", torch.float32, 3)
+    B, N, nc = cls_features.shape
+    if stds is not None:
+        _chk(stds, "stds", torch.float32, 2)
+        if tuple(stds.shape) != (B, N):
+            raise RuntimeError(f"stds must be (B, N)=({B},{N}), got {tuple(stds.shape)}")
+    idx = torch.empty((B, npoint), dtype=torch.int32, device=cls_features.device)
+    scores = torch.empty((B, npoint), dtype=torch.float32, device=cls_features.device) if return_scores else None
+    with torch.cuda.device(cls_features.device):
+        check(lib.spsk_score_topk(B, N, nc, npoint, cls_features.data_ptr(), stds.data_ptr() if stds is not None else None,
+                                  idx.data_ptr(), scores.data_ptr() if scores is not None else None, _stream()), "score_topk")
+    return (idx, scores) if return_scores else idx
+
+
+def gather_rows(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """out[b, j, :] = points[b, idx[b, j], :] for point-major (B, N, C) tensors (new_xyz = xyz[idx])."""
+    _chk(points, "points", torch.float32, 3)
+    _chk(idx, "idx", torch.int32, 2)
+    B, N, Cc = points.shape
+    M = idx.shape[1]
+    out = torch.empty((B, M, Cc), dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        check(lib.spsk_gather_rows(B, N, M, Cc, points.data_ptr(), idx.data_ptr(), out.data_ptr(), _stream()), "gather_rows")
+    return out
+
+
+def ball_query_msg(radii, nsamples, xyz: torch.Tensor, new_xyz: torch.Tensor):
+    """All scales of an MSG layer in ONE scan; returns a list of (B, npoint, nsample_s) int32 tensors,
+    identical to [ball_query(r, ns, xyz, new_xyz) for r, ns in zip(radii, nsamples)]."""
+    _chk(new_xyz, "new_xyz", torch.float32, 3)
+    _chk(xyz, "xyz", torch.float32, 3)
+    S = len(radii)
+    B, N, _ = xyz.shape
+    M = new_xyz.shape[1]
+    outs = [torch.empty((B, M, int(ns)), dtype=torch.int32, device=xyz.device) for ns in nsamples]
+    r = (C.c_float * S)(*[float(x) for x in radii])
+    n = (C.c_int * S)(*[int(x) for x in nsamples])
+    ptrs = (C.c_void_p * S)(*[o.data_ptr() for o in outs])
+    with torch.cuda.device(xyz.device):
+        check(lib.spsk_ball_query_msg(B, N, M, S, r, n, new_xyz.data_ptr(), xyz.data_ptr(), ptrs, _stream()), "ball_query_msg")
+    return outs
+
+
+def grouped_linear(*, xyz, new_xyz, features, idx, use_xyz, in_rows, wt, bias, relu, pool, out_pooled=None, co_off=0):
+    """One shared-MLP layer over grouped rows (include/spsk.h: spsk_grouped_linear).
+    gather mode when in_rows is None.  Returns out_rows (R, c_out) for pool == 0, else out_pooled."""
+    B, M, ns = idx.shape
+    N = xyz.shape[1]
+    c_in, c_out = wt.shape
+    g = GroupDesc()
+    g.b, g.n, g.m, g.nsample = B, N, M, ns
+    g.c_feat = features.shape[1] if features is not None else 0
+    g.use_xyz = 1 if use_xyz else 0
+    g.xyz = xyz.data_ptr()
+    g.new_xyz = new_xyz.data_ptr()
+    g.features = features.data_ptr() if features is not None else None
+    g.idx = idx.data_ptr()
+    out_rows = None
+    if pool == 0:
+        out_rows = torch.empty((B * M * ns, c_out), dtype=torch.float32, device=idx.device)
+    c_total = out_pooled.shape[1] if out_pooled is not None else 0
+    with torch.cuda.device(idx.device):
+        check(lib.spsk_grouped_linear(C.byref(g), 1 if in_rows is None else 0,
+                                      in_rows.data_ptr() if in_rows is not None else None, c_in,
+                                      wt.data_ptr(), bias.data_ptr() if bias is not None else None, c_out,
+                                      1 if relu else 0, pool,
+                                      out_rows.data_ptr() if out_rows is not None else None,
+                                      out_pooled.data_ptr() if out_pooled is not None else None,
+                                      c_total, co_off, _stream()), "grouped_linear")
+    return out_rows if pool == 0 else out_pooled
+
+
+def pointwise_linear(x: torch.Tensor, wt: torch.Tensor, bias, relu: bool) -> torch.Tensor:
+    """Conv1d(kernel_size=1) [+ folded BN] [+ ReLU] on a channel-major (B, C_in, M) tensor."""
+    _chk(x, "x", torch.float32, 3)
+    B, c_in, M = x.shape
+    if wt.shape[0] != c_in:
+        raise RuntimeError(f"weight (c_in={wt.shape[0]}) does not match input channels {c_in}")
+    c_out = wt.shape[1]
+    out = torch.empty((B, c_out, M), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.spsk_pointwise_linear(B, M, x.data_ptr(), c_in, wt.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                        c_out, 1 if relu else 0, out.data_ptr(), _stream()), "pointwise_linear")
+    return out

@@ -1,0 +1,67 @@
+import os
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def _has_gpu():
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _has_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle as O
+
+    O.build()
+    return O
+
+
+@pytest.fixture(scope="session")
+def ref_ops():
+    """The reference's own pointnet2_batch (rebuilt unmodified for sm_100a by oracle/build_ref.sh), or None."""
+    ref_root = ROOT / "oracle" / "_ref"
+    so = ref_root / "pcdet" / "ops" / "pointnet2" / "pointnet2_batch" / "pointnet2_batch_cuda.so"
+    if not so.exists():
+        return None
+    import importlib
+    import warnings
+
+    if str(ref_root) not in sys.path:
+        sys.path.insert(0, str(ref_root))
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            utils = importlib.import_module("pcdet.ops.pointnet2.pointnet2_batch.pointnet2_utils")
+            modules = importlib.import_module("pcdet.ops.pointnet2.pointnet2_batch.pointnet2_modules")
+    except Exception as e:  # pragma: no cover
+        print("reference ext not importable:", e)
+        return None
+
+    class R:
+        pass
+
+    R.utils, R.modules = utils, modules
+    return R

@@ -1,0 +1,214 @@
+"""-m gpu parity tests of the native ops: candidate (libspsk.so through the C-ABI) vs the C oracle, and vs the
+reference's own CUDA ops (oracle/_ref) when that module is present.  Indices / copies: bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from spsnet_b200 import scenes  # noqa: E402
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _xyz(b, n, seed=0, kind="kitti"):
+    return np.ascontiguousarray(scenes.make_batch(seed, b, n, kind)[:, :, :3])
+
+
+FPS_CASES = [  # (b, n, m)
+    (2, 1, 1), (1, 7, 5), (2, 33, 20), (3, 100, 64), (2, 1000, 300), (2, 1024, 512), (2, 1500, 700),
+    (4, 4096, 1024), (2, 5000, 1200), (2, 8192, 2048), (2, 12000, 3000), (4, 16384, 4096),
+]
+
+
+@pytest.mark.parametrize("b,n,m", FPS_CASES)
+def test_fps_vs_oracle(oracle, ref_ops, b, n, m):
+    from spsnet_b200 import pointnet2_utils as pu
+
+    xyz = _xyz(b, n, seed=n)
+    got = pu.furthest_point_sample(dev(xyz), m).cpu().numpy()
+    want = oracle.fps(xyz, m)
+    assert got.dtype == np.int32 and got.shape == (b, m)
+    np.testing.assert_array_equal(got, want)
+    if ref_ops is not None:
+        ref = ref_ops.utils.furthest_point_sample(dev(xyz), m).cpu().numpy()
+        np.testing.assert_array_equal(ref, want, err_msg="ORACLE disagrees with the reference CUDA op")
+
+
+def test_fps_ties_grid(oracle, ref_ops):
+    """Integer lattice + many duplicates: every step is a massive tie -> checks the block-tree tie-break."""
+    from spsnet_b200 import pointnet2_utils as pu
+
+    rng = np.random.default_rng(5)
+    for n, m in [(3000, 200), (16384, 600), (700, 300)]:
+        xyz = rng.integers(0, 6, (2, n, 3)).astype(np.float32)
+        got = pu.furthest_point_sample(dev(xyz), m).cpu().numpy()
+        np.testing.assert_array_equal(got, oracle.fps(xyz, m))
+        if ref_ops is not None:
+            np.testing.assert_array_equal(ref_ops.utils.furthest_point_sample(dev(xyz), m).cpu().numpy(), got)
+
+
+def test_fps_large_n_generic(oracle):
+    from spsnet_b200 import pointnet2_utils as pu
+
+    xyz = _xyz(1, 20000, seed=3, kind="waymo")
+    got = pu.furthest_point_sample(dev(xyz), 300).cpu().numpy()
+    np.testing.assert_array_equal(got, oracle.fps(xyz, 300))
+
+
+@pytest.mark.parametrize("b,n,m", [(2, 64, 20), (2, 1000, 128), (1, 2048, 512)])
+def test_fps_with_dist(oracle, ref_ops, b, n, m):
+    from spsnet_b200 import pointnet2_utils as pu
+
+    rng = np.random.default_rng(n)
+    f = rng.standard_normal((b, n, 6)).astype(np.float32)
+    d = ((f[:, :, None, :] - f[:, None, :, :]) ** 2).sum(-1).astype(np.float32)
+    got = pu.furthest_point_sample_with_dist(dev(d), m).cpu().numpy()
+    np.testing.assert_array_equal(got, oracle.fps_with_dist(d, m))
+    if ref_ops is not None:
+        np.testing.assert_array_equal(ref_ops.utils.furthest_point_sample_with_dist(dev(d), m).cpu().numpy(), got)
+
+
+BQ_CASES = [  # (b, n, m, radius, nsample)
+    (2, 100, 10, 5.0, 8), (2, 1000, 77, 2.0, 16), (2, 4096, 1024, 0.8, 16), (2, 4096, 1024, 1.6, 32),
+    (2, 16384, 512, 0.2, 16), (1, 16384, 300, 0.8, 32), (2, 1024, 512, 4.8, 32), (2, 3000, 100, 0.01, 16),
+    (1, 2000, 50, 1000.0, 64), (1, 50, 20, 3.0, 40),
+]
+
+
+@pytest.mark.parametrize("b,n,m,radius,nsample", BQ_CASES)
+def test_ball_query(oracle, ref_ops, b, n, m, radius, nsample):
+    from spsnet_b200 import pointnet2_utils as pu
+
+    xyz = _xyz(b, n, seed=7 + n)
+    sel = oracle.fps(xyz, m)
+    new_xyz = np.ascontiguousarray(np.take_along_axis(xyz, sel[..., None].astype(np.int64), axis=1))
+    new_xyz[:, -1] += 500.0  # a centre with an empty ball -> untouched (zero) row
+    got = pu.ball_query(radius, nsample, dev(xyz), dev(new_xyz)).cpu().numpy()
+    want = oracle.ball_query(radius, nsample, xyz, new_xyz)
+    np.testing.assert_array_equal(got, want)
+    if ref_ops is not None:
+        np.testing.assert_array_equal(ref_ops.utils.ball_query(radius, nsample, dev(xyz), dev(new_xyz)).cpu().numpy(), want)
+
+
+def test_ball_query_msg_equals_separate(oracle):
+    from spsnet_b200 import pointnet2_utils as pu
+
+    xyz = _xyz(2, 4096, seed=11)
+    sel = oracle.fps(xyz, 512)
+    new_xyz = np.ascontiguousarray(np.take_along_axis(xyz, sel[..., None].astype(np.int64), axis=1))
+    new_xyz[:, 5] -= 300.0
+    radii, ns = [0.2, 0.8, 3.0], [16, 32, 48]
+    outs = pu.ball_query_msg(radii, ns, dev(xyz), dev(new_xyz))
+    for r, s, o in zip(radii, ns, outs):
+        np.testing.assert_array_equal(o.cpu().numpy(), oracle.ball_query(r, s, xyz, new_xyz))
+
+
+@pytest.mark.parametrize("rmax,rmin", [(0.8, 0.0), (1.6, 0.8), (4.8, 1.6)])
+def test_ball_query_dilated(oracle, ref_ops, rmax, rmin):
+    from spsnet_b200 import pointnet2_utils as pu
+
+    xyz = _xyz(2, 3000, seed=13)
+    sel = oracle.fps(xyz, 200)
+    new_xyz = np.ascontiguousarray(np.take_along_axis(xyz, sel[..., None].astype(np.int64), axis=1))
+    got = pu.ball_query_dilated(rmax, rmin, 16, dev(xyz), dev(new_xyz)).cpu().numpy()
+    want = oracle.ball_query_dilated(rmax, rmin, 16, xyz, new_xyz)
+    np.testing.assert_array_equal(got, want)
+    if ref_ops is not None:
+        np.testing.assert_array_equal(ref_ops.utils.ball_query_dilated(rmax, rmin, 16, dev(xyz), dev(new_xyz)).cpu().numpy(), want)
+
+
+def test_gather_group(oracle, ref_ops):
+    from spsnet_b200 import pointnet2_utils as pu
+
+    rng = np.random.default_rng(0)
+    for b, c, n, m, s in [(2, 3, 100, 17, 5), (2, 64, 4096, 1024, 32), (1, 1, 16384, 4096, 16), (3, 13, 777, 300, 7)]:
+        f = rng.standard_normal((b, c, n)).astype(np.float32)
+        i1 = rng.integers(0, n, (b, m)).astype(np.int32)
+        i2 = rng.integers(0, n, (b, m, s)).astype(np.int32)
+        np.testing.assert_array_equal(pu.gather_operation(dev(f), dev(i1)).cpu().numpy(), oracle.gather(f, i1))
+        np.testing.assert_array_equal(pu.grouping_operation(dev(f), dev(i2)).cpu().numpy(), oracle.group(f, i2))
+        pts = np.ascontiguousarray(np.transpose(f, (0, 2, 1)))
+        np.testing.assert_array_equal(pu.gather_rows(dev(pts), dev(i1)).cpu().numpy(),
+                                      np.take_along_axis(pts, i1[..., None].astype(np.int64), axis=1))
+        if ref_ops is not None:
+            np.testing.assert_array_equal(ref_ops.utils.gather_operation(dev(f), dev(i1)).cpu().numpy(), oracle.gather(f, i1))
+            np.testing.assert_array_equal(ref_ops.utils.grouping_operation(dev(f), dev(i2)).cpu().numpy(), oracle.group(f, i2))
+
+
+def test_gather_group_backward(oracle):
+    from spsnet_b200 import pointnet2_utils as pu
+
+    rng = np.random.default_rng(1)
+    b, c, n, m, s = 2, 8, 300, 64, 9
+    f = torch.from_numpy(rng.standard_normal((b, c, n)).astype(np.float32)).cuda().requires_grad_(True)
+    i1 = rng.integers(0, n, (b, m)).astype(np.int32)
+    i2 = rng.integers(0, n, (b, m, s)).astype(np.int32)
+    g1 = rng.standard_normal((b, c, m)).astype(np.float32)
+    g2 = rng.standard_normal((b, c, m, s)).astype(np.float32)
+    pu.gather_operation(f, dev(i1)).backward(dev(g1))
+    np.testing.assert_allclose(f.grad.cpu().numpy(), oracle.gather_grad(g1, i1, n), rtol=1e-5, atol=1e-5)
+    f.grad = None
+    pu.grouping_operation(f, dev(i2)).backward(dev(g2))
+    np.testing.assert_allclose(f.grad.cpu().numpy(), oracle.group_grad(g2, i2, n), rtol=1e-5, atol=1e-5)
+
+
+def test_three_nn_interpolate(oracle, ref_ops):
+    from spsnet_b200 import pointnet2_utils as pu
+
+    rng = np.random.default_rng(2)
+    for b, n, m, c in [(2, 1000, 256, 16), (1, 4096, 1024, 5), (2, 50, 2, 3), (1, 300, 2500, 4)]:
+        unknown = _xyz(b, n, seed=21)
+        known = np.ascontiguousarray(_xyz(b, max(m, 4), seed=22)[:, :m])
+        if m >= 8:
+            known[:, 3] = known[:, 1]  # exact duplicate -> tie on distance, first index must win
+        d2, idx = oracle.three_nn(unknown, known)
+        gd, gi = pu.three_nn(dev(unknown), dev(known))
+        np.testing.assert_array_equal(gi.cpu().numpy(), idx)
+        np.testing.assert_array_equal(gd.cpu().numpy(), np.sqrt(d2))
+        feats = rng.standard_normal((b, c, m)).astype(np.float32)
+        w = rng.uniform(0, 1, (b, n, 3)).astype(np.float32)
+        got = pu.three_interpolate(dev(feats), dev(idx), dev(w)).cpu().numpy()
+        np.testing.assert_array_equal(got, oracle.three_interpolate(feats, idx, w))
+        if ref_ops is not None:
+            rd, ri = ref_ops.utils.three_nn(dev(unknown), dev(known))
+            np.testing.assert_array_equal(ri.cpu().numpy(), idx)
+            np.testing.assert_array_equal(rd.cpu().numpy(), np.sqrt(d2))
+            np.testing.assert_array_equal(ref_ops.utils.three_interpolate(dev(feats), dev(idx), dev(w)).cpu().numpy(), got)
+        # backward
+        ft = dev(feats).requires_grad_(True)
+        g = rng.standard_normal((b, c, n)).astype(np.float32)
+        pu.three_interpolate(ft, dev(idx), dev(w)).backward(dev(g))
+        np.testing.assert_allclose(ft.grad.cpu().numpy(), oracle.three_interpolate_grad(g, idx, w, m), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("b,n,k", [(2, 1024, 512), (4, 512, 256), (2, 4096, 2048), (1, 1000, 333), (2, 16384, 4096)])
+def test_score_topk(oracle, b, n, k):
+    from spsnet_b200 import pointnet2_utils as pu
+
+    cls = scenes.make_cls_logits(n, b, n)
+    cls[:, : n // 8] = np.round(cls[:, : n // 8])          # exact ties
+    cls[:, n // 8: n // 6, :] = 30.0                       # saturated sigmoid == 1.0f
+    stds = scenes.make_stds(n + 1, b, n)
+    for st in (None, stds):
+        idx, sc = pu.score_topk(dev(cls), k, stds=dev(st) if st is not None else None, return_scores=True)
+        idx, sc = idx.cpu().numpy(), sc.cpu().numpy()
+        want_idx, _ = oracle.score_topk(cls, k, st)
+        full = oracle.topk_scores(cls, st)
+        assert oracle.same_topk(idx, want_idx, full), "top-k differs from the oracle beyond near-ties"
+        # internal consistency: scores descending, ties by ascending index, scores match torch's formula on device
+        assert np.all(np.diff(sc, axis=1) <= 0)
+        tie = np.diff(sc, axis=1) == 0
+        assert np.all(np.diff(idx, axis=1)[tie] > 0)
+        t = torch.sigmoid(dev(cls).max(dim=-1)[0])
+        if st is not None:
+            t = t * (1 - torch.sigmoid(dev(st) / 8 - 3))
+        tv, ti = torch.topk(t, k, dim=-1)
+        np.testing.assert_array_equal(sc, tv.cpu().numpy())  # same score bits as torch's op chain
+        mism = ti.int().cpu().numpy() != idx
+        if mism.any():  # only inside groups of exactly equal scores
+            tt = t.cpu().numpy()
+            for bb, jj in zip(*np.nonzero(mism)):
+                assert tt[bb, ti[bb, jj]] == tt[bb, idx[bb, jj]]
