@@ -188,7 +188,7 @@ def score_topk(cls, npoint, stds=None):
     return idx, np.take_along_axis(s, idx.astype(np.int64), axis=1)
 
 
-def same_topk(idx_a, idx_b, scores_full, ulps: int = 4) -> bool:
+def same_topk(idx_a, idx_b, scores_full, ulps: int = 4, atol: float = 3e-7) -> bool:
     """Tie-tolerant comparison of two top-k index lists: sequences must agree except
     where the scores of the differing entries are within `ulps` fp32 ulps of each other (a GPU expf vs
     libm expf last-bit difference, or an exact tie, may legally reorder them), and the selected SETS may
@@ -202,7 +202,9 @@ def same_topk(idx_a, idx_b, scores_full, ulps: int = 4) -> bool:
         if diff.size == 0:
             continue
         sa, sc = scores_full[b][a[diff]], scores_full[b][c[diff]]
-        tol = ulps * np.spacing(np.maximum(np.abs(sa), np.abs(sc)).astype(np.float32))
+        # scores are products / differences of sigmoids in [0, 1]: a last-bit expf difference is an ABSOLUTE
+        # error of a few ulp(1.0) (1 - sigmoid(t) cancels), so the tolerance has an absolute floor
+        tol = np.maximum(ulps * np.spacing(np.maximum(np.abs(sa), np.abs(sc)).astype(np.float32)), atol)
         if not np.all(np.abs(sa.astype(np.float64) - sc.astype(np.float64)) <= tol):
             return False
     return True

@@ -172,7 +172,7 @@ static int launch_fps(int b, int n, int m, int threads, uint32_t s_mask, uint32_
                       float *temp, int *idx, cudaStream_t st) {
     const size_t smem = DISTMAT ? 0 : sizeof(float) * 3 * (size_t)n;
     auto kern = fps_kernel<P, REGXYZ, DISTMAT>;
-    if (smem > 48 * 1024) {
+    if (smem + 2048 > 48 * 1024) {  // dynamic + the kernel's static smem must stay under the 48 KB default
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fps_kernel)");
     }

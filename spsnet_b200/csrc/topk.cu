@@ -77,7 +77,7 @@ extern "C" int spsk_score_topk(int b, int n, int num_class, int npoint, const fl
     int n_pad = 2;
     while (n_pad < n) n_pad <<= 1;
     const size_t smem = sizeof(unsigned long long) * (size_t)n_pad;
-    if (smem > 48 * 1024) {
+    if (smem + 2048 > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(score_topk_kernel)");
     }

@@ -200,6 +200,6 @@ def test_fp_module(oracle):
     interp = oracle.three_interpolate(kf, idx, w)
     x = torch.from_numpy(np.concatenate([interp, uf], axis=1)).double()
     with torch.no_grad():
-        want = copy.deepcopy(fp).double()(x.unsqueeze(-1)).squeeze(-1).float().numpy()
+        want = copy.deepcopy(fp).double().mlp(x.unsqueeze(-1)).squeeze(-1).float().numpy()
         got = fp.cuda()(dev(unknown), dev(known), dev(uf), dev(kf)).cpu().numpy()
     assert_close(got, want, what="PointnetFPModule")
