@@ -46,9 +46,90 @@ __device__ __forceinline__ uint32_t block_argmax(uint32_t u, uint32_t inv_rank, 
     return (__brev(rank) & s_mask) | ((rank & low_mask) << s_log2);
 }
 
-// T = blockDim.x is a multiple of the reference block size S (both powers of two), so all points of
-// one thread (k = tid + p*T) share k mod S and rank(k) grows with p: "first strict maximum in p
-// order" is exactly the reference's in-thread rule AND its tree tie-break restricted to this thread.
+// Main kernel, n >= 1024 (reference block size S = 1024 = T).  All points of one thread (k = tid + p*T)
+// share k mod S and rank(k) grows with p, so "first strict maximum in p order" is exactly the
+// reference's in-thread rule AND its tree tie-break restricted to this thread.  T is a compile-time
+// constant and padding points carry tmp = -1 (fminf(d, -1) = -1 never beats best >= -1), so the
+// unrolled body is branch-free straight-line code: 3 LDS (or registers) + 10 ALU per point.
+template <int P, bool REGXYZ, bool DISTMAT>
+__global__ void __launch_bounds__(1024, 1)
+fps_kernel_1024(int n, int m, const float *__restrict__ src, float *__restrict__ temp, int *__restrict__ idx) {
+    constexpr int T = 1024;
+    constexpr uint32_t s_mask = 1023u, s_log2 = 10u;
+    extern __shared__ float smem[];
+    __shared__ uint2 slots[2][32];
+    const int tid = threadIdx.x;
+    const size_t scene = blockIdx.x;
+    constexpr int NP = P * T;  // padded point count
+    float *sx = smem, *sy = smem + NP, *sz = smem + 2 * NP;
+    const float *base = DISTMAT ? src + scene * (size_t)n * n : src + scene * (size_t)n * 3;
+    if (temp) temp += scene * (size_t)n;
+    idx += scene * (size_t)m;
+
+    if (!DISTMAT) {
+        for (int i = tid; i < 3 * NP; i += T) smem[i] = 0.f;
+        __syncthreads();
+        for (int i = tid; i < 3 * n; i += T) {
+            const float v = __ldg(base + i);
+            const int k = i / 3, c = i - 3 * k;
+            smem[c * NP + k] = v;
+        }
+        __syncthreads();
+    }
+
+    float tmp[P];
+    float px[REGXYZ ? P : 1], py[REGXYZ ? P : 1], pz[REGXYZ ? P : 1];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const int k = tid + p * T;
+        tmp[p] = (k < n) ? (temp ? temp[k] : 1e10f) : -1.f;
+        if (REGXYZ) { px[p] = sx[k]; py[p] = sy[k]; pz[p] = sz[k]; }
+    }
+
+    int old = 0;
+    if (tid == 0) idx[0] = 0;
+
+    for (int j = 1; j < m; ++j) {
+        float x1 = 0.f, y1 = 0.f, z1 = 0.f;
+        const float *drow = nullptr;
+        if (DISTMAT) {
+            drow = base + (size_t)old * n;
+        } else {
+            x1 = sx[old]; y1 = sy[old]; z1 = sz[old];
+        }
+        float best = -1.f;
+        int bp = 0;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const int k = tid + p * T;
+            float d;
+            if (DISTMAT) d = (k < n) ? __ldg(drow + k) : 0.f;
+            else if (REGXYZ) d = sqdist3(px[p], py[p], pz[p], x1, y1, z1);
+            else d = sqdist3(sx[k], sy[k], sz[k], x1, y1, z1);
+            const float t = fminf(d, tmp[p]);
+            tmp[p] = t;
+            const bool gt = t > best;
+            best = gt ? t : best;
+            bp = gt ? p : bp;
+        }
+        const uint32_t kb = (uint32_t)(tid + bp * T);
+        const uint32_t u = ordered_bits(__fadd_rn(best, 0.f));
+        const uint32_t inv_rank = ~fps_rank(kb, s_mask, s_log2);
+        old = (int)block_argmax(u, inv_rank, slots[j & 1], T / 32, s_mask, s_log2);
+        if (tid == 0) idx[j] = old;
+    }
+
+    if (temp) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const int k = tid + p * T;
+            if (k < n) temp[k] = tmp[p];
+        }
+    }
+}
+
+// Small scenes, n < 1024: the reference block has S = 2^floor(log2 n) < 1024 threads; T = blockDim.x =
+// max(S, 32) is a runtime multiple of S and every thread owns at most P = 2 points (same in-thread rule).
 template <int P, bool REGXYZ, bool DISTMAT>
 __global__ void __launch_bounds__(1024, 1)
 fps_kernel(int n, int m, uint32_t s_mask, uint32_t s_log2, const float *__restrict__ src,
@@ -181,7 +262,19 @@ static int launch_fps(int b, int n, int m, int threads, uint32_t s_mask, uint32_
     return SPSK_OK;
 }
 
-static const size_t kMaxSmemXyzPoints = (227 * 1024 - 1024) / 12;  // SoA xyz must fit one CTA
+template <int P, bool REGXYZ, bool DISTMAT>
+static int launch_fps_1024(int b, int n, int m, const float *src, float *temp, int *idx, cudaStream_t st) {
+    const size_t smem = DISTMAT ? 0 : sizeof(float) * 3 * (size_t)P * 1024;
+    auto kern = fps_kernel_1024<P, REGXYZ, DISTMAT>;
+    if (smem + 2048 > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fps_kernel_1024)");
+    }
+    kern<<<b, 1024, smem, st>>>(n, m, src, temp, idx);
+    SPSK_LAUNCH_CHECK("fps_kernel_1024");
+    return SPSK_OK;
+}
+
 
 template <bool DISTMAT>
 static int fps_dispatch(int b, int n, int m, const float *src, float *temp, int *idx, cudaStream_t st) {
@@ -194,7 +287,7 @@ static int fps_dispatch(int b, int n, int m, const float *src, float *temp, int 
     const uint32_t s_mask = (uint32_t)S - 1u;
     const int threads = S < 32 ? 32 : S;  // multiple of S, >= one warp; 1024 for n >= 1024
     const int per_thread = (n + threads - 1) / threads;
-    const bool fits = per_thread <= 16 && (DISTMAT || (size_t)n <= kMaxSmemXyzPoints);
+    const bool fits = per_thread <= 16;  // 16 x 1024 padded points of SoA xyz = 192 KB of shared memory
     if (!fits) {
         SPSK_REQUIRE(temp != nullptr, SPSK_ERR_UNSUPPORTED,
                      "fps: n=%d exceeds the on-chip variant (<=16384); pass a (b,n) `temp` scratch filled with 1e10", n);
@@ -202,11 +295,15 @@ static int fps_dispatch(int b, int n, int m, const float *src, float *temp, int 
         SPSK_LAUNCH_CHECK("fps_generic_kernel");
         return SPSK_OK;
     }
+    if (threads == 1024) {
+        if (per_thread <= 1) return launch_fps_1024<1, !DISTMAT, DISTMAT>(b, n, m, src, temp, idx, st);
+        if (per_thread <= 2) return launch_fps_1024<2, !DISTMAT, DISTMAT>(b, n, m, src, temp, idx, st);
+        if (per_thread <= 4) return launch_fps_1024<4, !DISTMAT, DISTMAT>(b, n, m, src, temp, idx, st);
+        if (per_thread <= 8) return launch_fps_1024<8, !DISTMAT, DISTMAT>(b, n, m, src, temp, idx, st);
+        return launch_fps_1024<16, false, DISTMAT>(b, n, m, src, temp, idx, st);
+    }
     if (per_thread <= 1) return launch_fps<1, !DISTMAT, DISTMAT>(b, n, m, threads, s_mask, s_log2, src, temp, idx, st);
-    if (per_thread <= 2) return launch_fps<2, !DISTMAT, DISTMAT>(b, n, m, threads, s_mask, s_log2, src, temp, idx, st);
-    if (per_thread <= 4) return launch_fps<4, !DISTMAT, DISTMAT>(b, n, m, threads, s_mask, s_log2, src, temp, idx, st);
-    if (per_thread <= 8) return launch_fps<8, !DISTMAT, DISTMAT>(b, n, m, threads, s_mask, s_log2, src, temp, idx, st);
-    return launch_fps<16, false, DISTMAT>(b, n, m, threads, s_mask, s_log2, src, temp, idx, st);
+    return launch_fps<2, !DISTMAT, DISTMAT>(b, n, m, threads, s_mask, s_log2, src, temp, idx, st);
 }
 
 }  // namespace spsk
