@@ -182,6 +182,34 @@ SPSK_API int spsk_grouped_linear(const spsk_group_desc *g, int gather, const flo
 SPSK_API int spsk_pointwise_linear(int b, int m, const float *in, int c_in, const float *wt, const float *bias,
                           int c_out, int relu, float *out, spsk_stream_t stream);
 
+/* ---- tensor-core path (tcgen05 + TMEM) -------------------------------------------------------------
+ * Point-major fp16 "twin" of a channel-major feature tensor: twin[b, i, 0:c] = (half)features[b, 0:c, i],
+ * zero padded to cpad8 (multiple of 8) channels, so that gathering one neighbour is a run of 16-byte loads. */
+SPSK_API int spsk_make_twin(int b, int c, int n, int cpad8, const float *features, void *twin, spsk_stream_t stream);
+
+/* Dynamic shared memory spsk_sa_mma_forward needs for a chain with the given padded widths (-1 if it
+ * does not fit); *nstages_out receives the depth of the weight-tile ring. */
+SPSK_API int spsk_sa_mma_smem_bytes(int nlayers, const int *kpad, const int *cpad, int *nstages_out);
+
+/* One MSG scale, fully fused on the tensor cores: gather (idx) -> [features | xyz - centre] -> nlayers x
+ * (1x1 conv + folded BN + ReLU) -> max over nsample -> out_pooled[b, co_off + c, p]   (replaces
+ * QueryAndGroup.forward's grouping + cat and the shared MLP + max_pool2d, pointnet2_utils.py:307-315,
+ * pointnet2_modules.py:204-211,431-436).  fp16 operands / fp32 accumulation.
+ *   g         : xyz, new_xyz, idx as in spsk_grouped_linear (g->features unused, g->c_feat ignored)
+ *   twin      : (b, n, cpad8) fp16 from spsk_make_twin (NULL iff cpad8 == 0)
+ *   layer l   : input width kpad[l] (multiple of 16; kpad[0] >= cpad8 + 8*use_xyz, k order = [features(cpad8),
+ *               x, y, z, 0...]), output width cpad[l] (multiple of 16; last layer: multiple of 128);
+ *               cpad[l] == kpad[l+1]
+ *   wtiles    : fp16 weight tiles of 128 couts x 64 k in the canonical K-major no-swizzle UMMA layout
+ *               (byte(r,k) = (r/8)*1024 + (k/8)*128 + (r%8)*16 + (k%8)*2), zero padded, ordered
+ *               layer -> cout chunk -> k chunk; layer l starts at tile tile_off[l]
+ *   bias      : folded BN shift per layer at bias_off[l] (cpad[l] floats, zero padded)
+ *   nsample must be a power of two <= 128. */
+SPSK_API int spsk_sa_mma_forward(const spsk_group_desc *g, int cpad8, const void *twin, int nlayers, const int *kpad,
+                        const int *cpad, const int *tile_off, const int *bias_off, const void *wtiles,
+                        const float *bias, int cout_last, float *out_pooled, int c_total, int co_off,
+                        spsk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

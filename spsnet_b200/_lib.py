@@ -39,6 +39,10 @@ SIGNATURES = {
     "spsk_ball_query_msg": [_i, _i, _i, _i, C.POINTER(_f), C.POINTER(_i), _p, _p, C.POINTER(_p), _p],
     "spsk_grouped_linear": [_p, _i, _p, _i, _p, _p, _i, _i, _i, _p, _p, _i, _i, _p],
     "spsk_pointwise_linear": [_i, _i, _p, _i, _p, _p, _i, _i, _p, _p],
+    "spsk_make_twin": [_i, _i, _i, _i, _p, _p, _p],
+    "spsk_sa_mma_smem_bytes": [_i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)],
+    "spsk_sa_mma_forward": [_p, _i, _p, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _p, _p, _i, _p,
+                            _i, _i, _p],
 }
 _RESTYPE = {"spsk_last_error": C.c_char_p, "spsk_launch_count": C.c_ulonglong}
 

@@ -16,6 +16,7 @@ Two execution paths per module:
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -104,6 +105,12 @@ class _Folded:
         return out
 
 
+def mlp_backend() -> str:
+    """'mma' (default): grouped shared MLPs on the tcgen05 tensor cores (fp16 operands, fp32 accumulate);
+    'ffma': the exact-fp32 CUDA-core kernels.  Set SPSK_MLP=ffma to force the latter."""
+    return os.environ.get("SPSK_MLP", "mma").lower()
+
+
 def _fused_ok(module: nn.Module, *tensors) -> bool:
     if module.training:
         return False
@@ -147,6 +154,15 @@ class _PointnetSAModuleBase(nn.Module):
             cache[name] = _Folded()
         return cache[name].get(seq)
 
+    def _mma_chain(self, si: int, chain, c_feat: int, use_xyz: bool):
+        """Packed tensor-core weights of scale `si`, rebuilt only when the folded chain object changes."""
+        cache = self.__dict__.setdefault("_mma_cache", {})
+        hit = cache.get(si)
+        if hit is None or hit[0] is not chain or hit[1] != (c_feat, use_xyz):
+            hit = (chain, (c_feat, use_xyz), pu.MmaChain(chain, c_feat, use_xyz))
+            cache[si] = hit
+        return hit[2]
+
     # -- reference composition (training / autograd): reference :62-79, 429-445
     def _msg_composed(self, xyz, new_xyz, features):
         outs = []
@@ -185,7 +201,20 @@ class _PointnetSAModuleBase(nn.Module):
                 else:
                     idxs.append(pu.ball_query(g.radius, g.nsample, xyz, new_xyz))
         co = 0
-        for g, chain, idx in zip(self.groupers, chains, idxs):
+        use_mma = mlp_backend() == "mma" and pool == 1
+        twin = None
+        for si, (g, chain, idx) in enumerate(zip(self.groupers, chains, idxs)):
+            ns = idx.shape[2]
+            if use_mma and ns <= 128 and (ns & (ns - 1)) == 0:
+                c_feat = features.shape[1] if features is not None else 0
+                packed = self._mma_chain(si, chain, c_feat, g.use_xyz)
+                if packed.ok:
+                    if twin is None and c_feat:
+                        twin = pu.make_twin(features, packed.cpad8)
+                    pu.sa_mma_forward(xyz=xyz, new_xyz=new_xyz, twin=twin, idx=idx, use_xyz=g.use_xyz, chain=packed,
+                                      out_pooled=out, co_off=co)
+                    co += chain[-1][0].shape[1]
+                    continue
             rows = None
             for li, (wt, bias, relu) in enumerate(chain):
                 last = li == len(chain) - 1

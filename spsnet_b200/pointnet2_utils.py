@@ -408,3 +408,90 @@ def pointwise_linear(x: torch.Tensor, wt: torch.Tensor, bias, relu: bool) -> tor
         check(lib.spsk_pointwise_linear(B, M, x.data_ptr(), c_in, wt.data_ptr(), bias.data_ptr() if bias is not None else None,
                                         c_out, 1 if relu else 0, out.data_ptr(), _stream()), "pointwise_linear")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# tensor-core path (tcgen05): host-side packing + launch  (include/spsk.h "tensor-core path")
+# ---------------------------------------------------------------------------------------------------
+
+def _ceil(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class MmaChain:
+    """A folded Conv/BN/ReLU chain packed for spsk_sa_mma_forward: fp16 weight tiles of 128 couts x 64 k in the
+    canonical K-major no-swizzle UMMA layout, zero padded; layer-0 input order is [features (cpad8), x, y, z, 0...]
+    (the reference's order is [x, y, z, features], pointnet2_utils.py:315 -- a pure row permutation of W0)."""
+
+    def __init__(self, chain, c_feat: int, use_xyz: bool):
+        dev = chain[0][0].device
+        self.nlayers = len(chain)
+        self.cpad8 = _ceil(c_feat, 8) if c_feat > 0 else 0
+        k0 = self.cpad8 + (8 if use_xyz else 0)
+        kin = _ceil(max(k0, 16), 16)
+        self.kpad, self.cpad, self.tile_off, self.bias_off = [], [], [], []
+        tiles, biases = [], []
+        ntile = nbias = 0
+        self.ok = self.nlayers <= 4 and all(relu for _, _, relu in chain) and k0 > 0
+        for l, (wt, bias, _relu) in enumerate(chain):
+            cin, cout = wt.shape
+            last = l == self.nlayers - 1
+            cp = _ceil(cout, 128 if last else 16)
+            W = torch.zeros((kin, cp), dtype=torch.float32, device=dev)
+            if l == 0:
+                xr = 3 if use_xyz else 0
+                if c_feat:
+                    W[0:c_feat, :cout] = wt[xr:xr + c_feat]
+                if use_xyz:
+                    W[self.cpad8:self.cpad8 + 3, :cout] = wt[0:3]
+            else:
+                W[:cin, :cout] = wt
+            bv = torch.zeros(cp, dtype=torch.float32, device=dev)
+            bv[:cout] = bias
+            n_cc, n_kc = (cp + 127) // 128, (kin + 63) // 64
+            Wt = torch.zeros((n_cc * 128, n_kc * 64), dtype=torch.float32, device=dev)
+            Wt[:cp, :kin] = W.t()
+            T = Wt.view(n_cc, 16, 8, n_kc, 8, 8).permute(0, 3, 1, 4, 2, 5).contiguous()  # (cc, kc, rg, kg, r, k)
+            tiles.append(T.reshape(-1).to(torch.float16))
+            biases.append(bv)
+            self.kpad.append(kin)
+            self.cpad.append(cp)
+            self.tile_off.append(ntile)
+            self.bias_off.append(nbias)
+            ntile += n_cc * n_kc
+            nbias += cp
+            if kin > 1024 or (not last and cp > 512):
+                self.ok = False
+            kin = cp
+            self.cout_last = cout
+        self.wtiles = torch.cat(tiles).contiguous()
+        self.bias = torch.cat(biases).contiguous()
+        self._c = {k: (C.c_int * self.nlayers)(*getattr(self, k)) for k in ("kpad", "cpad", "tile_off", "bias_off")}
+        if self.ok:
+            ns = C.c_int(0)
+            self.ok = lib.spsk_sa_mma_smem_bytes(self.nlayers, self._c["kpad"], self._c["cpad"], C.byref(ns)) > 0
+
+
+def make_twin(features: torch.Tensor, cpad8: int) -> torch.Tensor:
+    """(B, C, N) f32 -> (B, N, cpad8) fp16 point-major, zero padded."""
+    _chk(features, "features", torch.float32, 3)
+    B, Cc, N = features.shape
+    twin = torch.empty((B, N, cpad8), dtype=torch.float16, device=features.device)
+    with torch.cuda.device(features.device):
+        check(lib.spsk_make_twin(B, Cc, N, cpad8, features.data_ptr(), twin.data_ptr(), _stream()), "make_twin")
+    return twin
+
+
+def sa_mma_forward(*, xyz, new_xyz, twin, idx, use_xyz, chain: MmaChain, out_pooled, co_off):
+    B, M, ns = idx.shape
+    g = GroupDesc()
+    g.b, g.n, g.m, g.nsample = B, xyz.shape[1], M, ns
+    g.c_feat = 0
+    g.use_xyz = 1 if use_xyz else 0
+    g.xyz, g.new_xyz, g.features, g.idx = xyz.data_ptr(), new_xyz.data_ptr(), None, idx.data_ptr()
+    with torch.cuda.device(idx.device):
+        check(lib.spsk_sa_mma_forward(C.byref(g), chain.cpad8, twin.data_ptr() if twin is not None else None, chain.nlayers,
+                                      chain._c["kpad"], chain._c["cpad"], chain._c["tile_off"], chain._c["bias_off"],
+                                      chain.wtiles.data_ptr(), chain.bias.data_ptr(), chain.cout_last,
+                                      out_pooled.data_ptr(), out_pooled.shape[1], co_off, _stream()), "sa_mma_forward")
+    return out_pooled
