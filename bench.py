@@ -160,7 +160,7 @@ def profile_kernels(net, dev_points, steps: int):
             e0.record()
             rc = fn(*a)
             e1.record()
-            if name == "spsk_grouped_linear":  # a[0] is byref(GroupDesc): read the row count while it is alive
+            if name in ("spsk_grouped_linear", "spsk_sa_mma_forward"):  # a[0] is byref(GroupDesc): read the row count while it is alive
                 g = a[0]._obj
                 a = (int(g.b) * int(g.m) * int(g.nsample),) + tuple(a[1:])
             records.append((name, a, e0, e1))
@@ -187,6 +187,8 @@ def profile_kernels(net, dev_points, steps: int):
             key = f"{name}[n={a[1]},m={a[2]}]"
         elif name == "spsk_grouped_linear":
             key = f"{name}[cin={a[3]},cout={a[6]}]"
+        elif name == "spsk_sa_mma_forward":
+            key = f"{name}[rows={a[0]},cout={a[10]}]"
         ms = e0.elapsed_time(e1)
         t = table.setdefault(key, {"ms": 0.0, "launches": 0, "args": a})
         t["ms"] += ms

@@ -148,6 +148,16 @@ SPSK_API int spsk_gather_rows(int b, int n, int m, int c, const float *in, const
 SPSK_API int spsk_ball_query_msg(int b, int n, int m, int nscales, const float *radius, const int *nsample,
                         const float *new_xyz, const float *xyz, int *const *idx, spsk_stream_t stream);
 
+/* Same contract and results as spsk_ball_query_msg, computed through a per-scene uniform xy grid (cells of
+ * edge >= 1.01 * max radius, 3 x 3 neighbourhood per centre, hits ordered through a per-warp index bitmap):
+ * the work drops from n to a few dozen pair tests per centre when the radius is small against the scene.
+ * `workspace` is caller-owned device scratch of at least spsk_ball_query_grid_workspace_bytes(b, n) bytes.
+ * n <= 65536. */
+SPSK_API long long spsk_ball_query_grid_workspace_bytes(int b, int n);
+SPSK_API int spsk_ball_query_msg_grid(int b, int n, int m, int nscales, const float *radius, const int *nsample,
+                             const float *new_xyz, const float *xyz, int *const *idx, void *workspace,
+                             long long workspace_bytes, spsk_stream_t stream);
+
 /* One shared-MLP layer over grouped rows, the unit the SA layer is built from (replaces
  * grouping_operation x2 + subtract + cat + Conv2d1x1 + BatchNorm2d(eval) + ReLU [+ max_pool2d],
  * pointnet2_utils.py:307-315 and pointnet2_modules.py:204-211,431-436).

@@ -37,6 +37,8 @@ SIGNATURES = {
     "spsk_score_topk": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
     "spsk_gather_rows": [_i, _i, _i, _i, _p, _p, _p, _p],
     "spsk_ball_query_msg": [_i, _i, _i, _i, C.POINTER(_f), C.POINTER(_i), _p, _p, C.POINTER(_p), _p],
+    "spsk_ball_query_grid_workspace_bytes": [_i, _i],
+    "spsk_ball_query_msg_grid": [_i, _i, _i, _i, C.POINTER(_f), C.POINTER(_i), _p, _p, C.POINTER(_p), _p, C.c_longlong, _p],
     "spsk_grouped_linear": [_p, _i, _p, _i, _p, _p, _i, _i, _i, _p, _p, _i, _i, _p],
     "spsk_pointwise_linear": [_i, _i, _p, _i, _p, _p, _i, _i, _p, _p],
     "spsk_make_twin": [_i, _i, _i, _i, _p, _p, _p],
@@ -44,7 +46,8 @@ SIGNATURES = {
     "spsk_sa_mma_forward": [_p, _i, _p, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _p, _p, _i, _p,
                             _i, _i, _p],
 }
-_RESTYPE = {"spsk_last_error": C.c_char_p, "spsk_launch_count": C.c_ulonglong}
+_RESTYPE = {"spsk_last_error": C.c_char_p, "spsk_launch_count": C.c_ulonglong,
+            "spsk_ball_query_grid_workspace_bytes": C.c_longlong}
 
 
 class GroupDesc(C.Structure):

@@ -1,0 +1,267 @@
+// ball_query_grid.cu -- multi-scale ball query through a per-scene uniform xy grid (large n, small radius).
+//
+// Same results as ball_query.cu / the reference kernel (src/ball_query_gpu.cu:9-45): the first `nsample`
+// point indices IN ORIGINAL INDEX ORDER with d2 < radius^2, first-hit padding, zero rows when empty.  The
+// brute-force scan tests all n points per centre (143.9 M pair tests per KITTI scene); here
+//   1. one CTA per scene bins the points into square cells of edge c >= 1.01 * r_max (counting sort in
+//      shared memory) and writes them cell-major as float4 (x, y, z, original index);
+//   2. one warp per centre tests only the 3 x 3 cell neighbourhood (three contiguous runs of the cell-major
+//      array), marks every hit in a per-warp BITMAP indexed by original point index (shared memory), and
+//      reads the bitmap back in index order -- which is exactly the reference's "first nsample in index
+//      order" without any sorting.
+// Rigour: the cell index is a monotone function of the coordinate and c carries a 1 % margin, so every point
+// whose fp32 d2 passes the strict `d2 < r^2` test lies in the 3 x 3 neighbourhood; the d2 expression and
+// the compare are the reference's (common.cuh::sqdist3).
+#include "common.cuh"
+
+namespace spsk {
+
+constexpr int BG_MAXC = 11264;        // max cells per scene (44 KB of counters)
+constexpr int BG_GMAX = 106;          // max cells per axis (106 * 106 <= BG_MAXC)
+constexpr int BG_WARPS = 8;
+constexpr int BG_MAX_N = 65536;
+
+struct GridParams {   // per scene, written by the build kernel
+    float minx, miny, inv_c;
+    int gx, gy, pad0, pad1, pad2;
+};
+
+// workspace layout (bytes): [GridParams b][cell_start b*(BG_MAXC+1) int][sorted b*n float4]
+static size_t grid_ws_bytes(int b, int n) {
+    return sizeof(GridParams) * (size_t)b + sizeof(int) * (size_t)b * (BG_MAXC + 1) + sizeof(float4) * (size_t)b * n + 256;
+}
+
+__device__ __forceinline__ int cell_coord(float v, float vmin, float inv_c, int g) {
+    const int c = (int)floorf((v - vmin) * inv_c);
+    return min(max(c, 0), g - 1);
+}
+
+__global__ void __launch_bounds__(1024, 1)
+bq_grid_build_kernel(int n, float rmax, const float *__restrict__ xyz, GridParams *__restrict__ params,
+                     int *__restrict__ cell_start, float4 *__restrict__ sorted) {
+    __shared__ int cnt[BG_MAXC];
+    __shared__ float red[4][32];
+    __shared__ int wsum[32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *pts = xyz + (size_t)b * n * 3;
+    float x0 = 3.0e38f, x1 = -3.0e38f, y0 = 3.0e38f, y1 = -3.0e38f;
+    for (int i = tid; i < n; i += 1024) {
+        const float x = __ldg(pts + (size_t)i * 3), y = __ldg(pts + (size_t)i * 3 + 1);
+        x0 = fminf(x0, x); x1 = fmaxf(x1, x); y0 = fminf(y0, y); y1 = fmaxf(y1, y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        x0 = fminf(x0, __shfl_xor_sync(0xFFFFFFFFu, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(0xFFFFFFFFu, x1, o));
+        y0 = fminf(y0, __shfl_xor_sync(0xFFFFFFFFu, y0, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xFFFFFFFFu, y1, o));
+    }
+    if (lane == 0) { red[0][warp] = x0; red[1][warp] = x1; red[2][warp] = y0; red[3][warp] = y1; }
+    for (int i = tid; i < BG_MAXC; i += 1024) cnt[i] = 0;
+    __syncthreads();
+    x0 = red[0][0]; x1 = red[1][0]; y0 = red[2][0]; y1 = red[3][0];
+    for (int w = 1; w < 32; ++w) { x0 = fminf(x0, red[0][w]); x1 = fmaxf(x1, red[1][w]); y0 = fminf(y0, red[2][w]); y1 = fmaxf(y1, red[3][w]); }
+    const float ex = fmaxf(x1 - x0, 0.f), ey = fmaxf(y1 - y0, 0.f);
+    float c = fmaxf(rmax * 1.01f, 1e-6f);
+    c = fmaxf(c, fmaxf(ex, ey) / (float)(BG_GMAX - 2));       // never more than BG_GMAX cells per axis
+    const float inv_c = 1.0f / c;
+    const int gx = min(BG_GMAX, (int)floorf(ex * inv_c) + 1), gy = min(BG_GMAX, (int)floorf(ey * inv_c) + 1);
+    const int ncell = gx * gy;
+    if (tid == 0) {
+        GridParams p;
+        p.minx = x0; p.miny = y0; p.inv_c = inv_c; p.gx = gx; p.gy = gy; p.pad0 = p.pad1 = p.pad2 = 0;
+        params[b] = p;
+    }
+    // histogram
+    for (int i = tid; i < n; i += 1024) {
+        const int cx = cell_coord(__ldg(pts + (size_t)i * 3), x0, inv_c, gx);
+        const int cy = cell_coord(__ldg(pts + (size_t)i * 3 + 1), y0, inv_c, gy);
+        atomicAdd(&cnt[cy * gx + cx], 1);
+    }
+    __syncthreads();
+    // exclusive scan of cnt[0..ncell) -> cell_start ; cnt becomes the running cursor
+    const int per = (ncell + 1023) / 1024;
+    const int beg = tid * per, end = min(beg + per, ncell);
+    int local = 0;
+    for (int i = beg; i < end; ++i) local += cnt[i];
+    int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int v = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xFFFFFFFFu, v, o);
+            if (lane >= o) v += u;
+        }
+        wsum[lane] = v;   // inclusive over warps
+    }
+    __syncthreads();
+    int run = incl - local + (warp ? wsum[warp - 1] : 0);
+    int *cs = cell_start + (size_t)b * (BG_MAXC + 1);
+    for (int i = beg; i < end; ++i) {
+        const int c0 = cnt[i];
+        cs[i] = run;
+        cnt[i] = run;
+        run += c0;
+    }
+    if (tid == 0) cs[ncell] = n;
+    __syncthreads();
+    // scatter (order inside a cell is irrelevant: the query orders hits through its bitmap)
+    float4 *out = sorted + (size_t)b * n;
+    for (int i = tid; i < n; i += 1024) {
+        const float x = __ldg(pts + (size_t)i * 3), y = __ldg(pts + (size_t)i * 3 + 1), z = __ldg(pts + (size_t)i * 3 + 2);
+        const int cx = cell_coord(x, x0, inv_c, gx), cy = cell_coord(y, y0, inv_c, gy);
+        const int pos = atomicAdd(&cnt[cy * gx + cx], 1);
+        out[pos] = make_float4(x, y, z, __int_as_float(i));
+    }
+}
+
+struct BgScales {
+    float r2[SPSK_MAX_SCALES];
+    int nsample[SPSK_MAX_SCALES];
+    int *idx[SPSK_MAX_SCALES];
+};
+
+template <int NS>
+__global__ void __launch_bounds__(BG_WARPS * 32)
+bq_grid_query_kernel(int n, int m, int words, BgScales sc, const float *__restrict__ new_xyz,
+                     const GridParams *__restrict__ params, const int *__restrict__ cell_start,
+                     const float4 *__restrict__ sorted) {
+    extern __shared__ uint32_t bitmaps[];   // [BG_WARPS][NS][words]
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+    const int p = blockIdx.x * BG_WARPS + warp;
+    uint32_t *bm = bitmaps + (size_t)warp * NS * words;
+    for (int i = lane; i < NS * words; i += 32) bm[i] = 0u;
+    __syncwarp();
+    if (p >= m) return;
+    const GridParams gp = params[b];
+    const int *cs = cell_start + (size_t)b * (BG_MAXC + 1);
+    const float4 *pts = sorted + (size_t)b * n;
+    const float *c = new_xyz + ((size_t)b * m + p) * 3;
+    const float qx = __ldg(c), qy = __ldg(c + 1), qz = __ldg(c + 2);
+    // the centre may lie outside the scene box (vote centres): unclamped cell coordinate, clamped ranges
+    const int ccx = (int)floorf((qx - gp.minx) * gp.inv_c), ccy = (int)floorf((qy - gp.miny) * gp.inv_c);
+    const int xlo = max(ccx - 1, 0), xhi = min(ccx + 1, gp.gx - 1);
+    if (xlo <= xhi) {
+        for (int cy = max(ccy - 1, 0); cy <= min(ccy + 1, gp.gy - 1); ++cy) {
+            const int beg = __ldg(cs + cy * gp.gx + xlo), end = __ldg(cs + cy * gp.gx + xhi + 1);
+            for (int k0 = beg; k0 < end; k0 += 32) {
+                const int k = k0 + (int)lane;
+                if (k < end) {
+                    const float4 v = __ldg(pts + k);
+                    const float d2 = sqdist3(qx, qy, qz, v.x, v.y, v.z);
+                    const uint32_t oi = (uint32_t)__float_as_int(v.w);
+#pragma unroll
+                    for (int s = 0; s < NS; ++s)
+                        if (d2 < sc.r2[s]) atomicOr(&bm[s * words + (oi >> 5)], 1u << (oi & 31u));
+                }
+            }
+        }
+    }
+    __syncwarp();
+    // read the bitmaps back in index order
+    const int wpl = (words + 31) / 32;   // words per lane (contiguous chunk)
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const int ns = sc.nsample[s];
+        int *out = sc.idx[s] + ((size_t)b * m + p) * ns;
+        uint32_t *w = bm + s * words;
+        const int w0 = (int)lane * wpl, w1 = min(w0 + wpl, words);
+        int cnt = 0;
+        for (int i = w0; i < w1; ++i) cnt += __popc(w[i]);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if ((int)lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        int pos = incl - cnt;
+        int first_local = -1;
+        for (int i = w0; i < w1; ++i) {
+            uint32_t bits = w[i];
+            if (bits) {
+                w[i] = 0u;
+                while (bits) {
+                    const int bit = __ffs(bits) - 1;
+                    bits &= bits - 1u;
+                    const int id = i * 32 + bit;
+                    if (first_local < 0) first_local = id;
+                    if (pos < ns) out[pos] = id;
+                    ++pos;
+                }
+            }
+        }
+        const uint32_t has = __ballot_sync(0xFFFFFFFFu, cnt > 0);
+        if (total > 0) {
+            const int first = __shfl_sync(0xFFFFFFFFu, first_local, __ffs(has) - 1);
+            for (int l = min(total, ns) + (int)lane; l < ns; l += 32) out[l] = first;   // first-hit padding
+        } else {
+            for (int l = (int)lane; l < ns; l += 32) out[l] = 0;
+        }
+    }
+}
+
+}  // namespace spsk
+
+extern "C" long long spsk_ball_query_grid_workspace_bytes(int b, int n) {
+    if (b < 0 || n < 0) return -1;
+    return (long long)spsk::grid_ws_bytes(b, n);
+}
+
+extern "C" int spsk_ball_query_msg_grid(int b, int n, int m, int nscales, const float *radius, const int *nsample,
+                                        const float *new_xyz, const float *xyz, int *const *idx, void *workspace,
+                                        long long workspace_bytes, spsk_stream_t stream) {
+    using namespace spsk;
+    SPSK_REQUIRE(b >= 0 && n >= 1 && m >= 0 && b <= 65535, SPSK_ERR_INVALID_ARG, "ball_query_msg_grid: bad sizes b=%d n=%d m=%d", b, n, m);
+    SPSK_REQUIRE(n <= BG_MAX_N, SPSK_ERR_UNSUPPORTED, "ball_query_msg_grid: n=%d > %d", n, BG_MAX_N);
+    SPSK_REQUIRE(nscales >= 1 && nscales <= SPSK_MAX_SCALES && radius && nsample && idx && new_xyz && xyz, SPSK_ERR_INVALID_ARG,
+                 "ball_query_msg_grid: nscales=%d / null pointer", nscales);
+    if (b == 0 || m == 0) return SPSK_OK;
+    SPSK_REQUIRE(workspace && workspace_bytes >= (long long)grid_ws_bytes(b, n), SPSK_ERR_WORKSPACE,
+                 "ball_query_msg_grid: workspace %lld B < %lld B", workspace_bytes, (long long)grid_ws_bytes(b, n));
+    BgScales sc{};
+    float rmax = 0.f;
+    for (int s = 0; s < nscales; ++s) {
+        SPSK_REQUIRE(nsample[s] >= 1 && idx[s], SPSK_ERR_INVALID_ARG, "ball_query_msg_grid: scale %d nsample=%d / null idx", s, nsample[s]);
+        sc.r2[s] = radius[s] * radius[s];
+        sc.nsample[s] = nsample[s];
+        sc.idx[s] = idx[s];
+        rmax = fmaxf(rmax, fabsf(radius[s]));
+    }
+    uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
+    ws = reinterpret_cast<uint8_t *>(((uintptr_t)ws + 15) & ~(uintptr_t)15);
+    GridParams *params = reinterpret_cast<GridParams *>(ws);
+    float4 *sorted = reinterpret_cast<float4 *>(ws + ((sizeof(GridParams) * (size_t)b + 15) & ~(size_t)15));
+    int *cell_start = reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(sorted) + sizeof(float4) * (size_t)b * n);
+    cudaStream_t st = as_stream(stream);
+    bq_grid_build_kernel<<<b, 1024, 0, st>>>(n, rmax, xyz, params, cell_start, sorted);
+    SPSK_LAUNCH_CHECK("bq_grid_build_kernel");
+    const int words = (n + 31) / 32;
+    const size_t smem = sizeof(uint32_t) * (size_t)BG_WARPS * nscales * words;
+    SPSK_REQUIRE(smem <= 200 * 1024, SPSK_ERR_UNSUPPORTED, "ball_query_msg_grid: bitmap of %zu B does not fit shared memory", smem);
+    dim3 grid((m + BG_WARPS - 1) / BG_WARPS, b);
+#define SPSK_BG_LAUNCH(NSV)                                                                                          \
+    do {                                                                                                             \
+        if (smem > 48 * 1024) {                                                                                      \
+            cudaError_t e = cudaFuncSetAttribute(bq_grid_query_kernel<NSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(bq_grid_query_kernel)");              \
+        }                                                                                                            \
+        bq_grid_query_kernel<NSV><<<grid, BG_WARPS * 32, smem, st>>>(n, m, words, sc, new_xyz, params, cell_start, sorted); \
+    } while (0)
+    switch (nscales) {
+        case 1: SPSK_BG_LAUNCH(1); break;
+        case 2: SPSK_BG_LAUNCH(2); break;
+        case 3: SPSK_BG_LAUNCH(3); break;
+        default: SPSK_BG_LAUNCH(4); break;
+    }
+#undef SPSK_BG_LAUNCH
+    SPSK_LAUNCH_CHECK("bq_grid_query_kernel");
+    return SPSK_OK;
+}

@@ -15,6 +15,7 @@
 //
 // FPS is latency bound: m-1 strictly sequential arg-max steps per scene.  One CTA per scene.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace spsk {
 
@@ -126,6 +127,203 @@ fps_kernel_1024(int n, int m, const float *__restrict__ src, float *__restrict__
             if (k < n) temp[k] = tmp[p];
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Spatially pruned D-FPS (same winners, far less work per step).
+//
+// The update temp[k] = min(temp[k], |p_k - q|^2) cannot change temp[k] when |p_k - q|^2 >= temp[k].  Points
+// are sorted once along a Morton curve (in-kernel bitonic sort of 32-bit (cell code, index) keys) and cut
+// into sub-buckets of 32 consecutive points (one per lane).  Each sub-bucket keeps its bounding box, the
+// maximum of its running minima (bmax) and the rank of its best point.  Per step a lane evaluates the
+// box-to-query lower bound lb of "its" sub-bucket with THE SAME fp32 expression as the distance itself
+// (fl() is monotone, so lb <= every fl(|p_k - q|^2) in the box) and the warp skips the sub-bucket when
+// lb >= bmax -- exactly the sub-buckets whose temps provably do not change.  Surviving sub-buckets are
+// updated with the reference arithmetic, so temps, maxima and the (value, rank) arg-max are bit-identical
+// to the unpruned kernel; only the amount of work differs (after a few hundred samples a new point touches
+// a handful of the 512 sub-buckets).  The sort only decides HOW MUCH is skipped, never the result.
+//
+// 512 threads, P points per lane (P*512 >= n), sub-bucket s = p*16 + warp (round-robin over warps so that
+// neighbouring sub-buckets are processed by different warps), sorted xyz in shared memory (SoA), running
+// minima / original indices in registers, orig->sorted position map (u16) in shared memory.
+template <int P>
+__global__ void __launch_bounds__(512, 1)
+fps_pruned_kernel(int n, int m, const float *__restrict__ src, float *__restrict__ temp, int *__restrict__ idx) {
+    constexpr int T = 512, W = 16, NP = T * P;
+    constexpr uint32_t s_mask = 1023u, s_log2 = 10u;   // reference block size is 1024 for n >= 1024
+    extern __shared__ float smem[];
+    __shared__ uint2 slots[2][32];
+    __shared__ float red[6][W];
+    float *sx = smem, *sy = smem + NP, *sz = smem + 2 * NP;
+    uint32_t *keys = reinterpret_cast<uint32_t *>(smem);              // sort phase only (aliases sx)
+    unsigned short *pos_of = reinterpret_cast<unsigned short *>(smem + 3 * NP);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t scene = blockIdx.x;
+    const float *base = src + scene * (size_t)n * 3;
+    if (temp) temp += scene * (size_t)n;
+    idx += scene * (size_t)m;
+
+    // ---- scene bounding box
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int i = tid; i < n; i += T) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = __ldg(base + (size_t)i * 3 + c);
+            lo[c] = fminf(lo[c], v);
+            hi[c] = fmaxf(hi[c], v);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = fminf(lo[c], __shfl_xor_sync(0xFFFFFFFFu, lo[c], o));
+            hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xFFFFFFFFu, hi[c], o));
+        }
+        if (lane == 0) { red[c][warp] = lo[c]; red[3 + c][warp] = hi[c]; }
+    }
+    __syncthreads();
+    float scl[3], org[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float l = red[c][0], h = red[3 + c][0];
+        for (int w = 1; w < W; ++w) { l = fminf(l, red[c][w]); h = fmaxf(h, red[3 + c][w]); }
+        org[c] = l;
+        const float cells = (c == 2) ? 16.f : 128.f;
+        scl[c] = cells / fmaxf(h - l, 1e-20f);
+    }
+    // ---- keys: (7+7-bit xy Morton code, 4-bit z cell) << 14 | index ; padding sorts last
+    for (int i = tid; i < NP; i += T) {
+        uint32_t key = 0xFFFFFFFFu;
+        if (i < n) {
+            const float x = __ldg(base + (size_t)i * 3), y = __ldg(base + (size_t)i * 3 + 1), z = __ldg(base + (size_t)i * 3 + 2);
+            uint32_t cx = min(127, max(0, (int)((x - org[0]) * scl[0])));
+            uint32_t cy = min(127, max(0, (int)((y - org[1]) * scl[1])));
+            const uint32_t cz = min(15, max(0, (int)((z - org[2]) * scl[2])));
+            cx = (cx | (cx << 4)) & 0x0F0Fu; cx = (cx | (cx << 2)) & 0x3333u; cx = (cx | (cx << 1)) & 0x5555u;
+            cy = (cy | (cy << 4)) & 0x0F0Fu; cy = (cy | (cy << 2)) & 0x3333u; cy = (cy | (cy << 1)) & 0x5555u;
+            const uint32_t code = (((cx | (cy << 1)) & 0x3FFFu) << 4) | cz;
+            key = (code << 14) | (uint32_t)i;
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    for (int k = 2; k <= NP; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < NP; i += T) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const uint32_t a = keys[i], b = keys[ixj];
+                    const bool up = (i & k) == 0;
+                    if (up ? (a > b) : (a < b)) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- take ownership: slot p of this lane = sorted position ((p*W + warp)*32 + lane)
+    uint32_t oidx[P];
+    float tmp[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) oidx[p] = keys[(p * W + warp) * 32 + lane];
+    __syncthreads();   // keys consumed; the region becomes sx/sy/sz
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const int pos = (p * W + warp) * 32 + lane;
+        const bool valid = oidx[p] != 0xFFFFFFFFu;
+        const uint32_t oi = valid ? (oidx[p] & 0x3FFFu) : 0u;
+        oidx[p] = valid ? oi : 0xFFFFFFFFu;
+        sx[pos] = valid ? __ldg(base + (size_t)oi * 3) : 0.f;
+        sy[pos] = valid ? __ldg(base + (size_t)oi * 3 + 1) : 0.f;
+        sz[pos] = valid ? __ldg(base + (size_t)oi * 3 + 2) : 0.f;
+        tmp[p] = valid ? (temp ? temp[oi] : 1e10f) : -1.f;
+        if (valid) pos_of[oi] = (unsigned short)pos;
+    }
+    __syncthreads();
+    // ---- sub-bucket boxes: lane p keeps the box / bmax / best-rank of slot p of this warp
+    float bx0 = 3.0e38f, bx1 = -3.0e38f, by0 = 3.0e38f, by1 = -3.0e38f, bz0 = 3.0e38f, bz1 = -3.0e38f;
+    uint32_t bmax_bits = 0u, brank = 0u;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        const int pos = (p * W + warp) * 32 + lane;
+        const bool valid = oidx[p] != 0xFFFFFFFFu;
+        float a0 = valid ? sx[pos] : 3.0e38f, a1 = valid ? sx[pos] : -3.0e38f;
+        float c0 = valid ? sy[pos] : 3.0e38f, c1 = valid ? sy[pos] : -3.0e38f;
+        float e0 = valid ? sz[pos] : 3.0e38f, e1 = valid ? sz[pos] : -3.0e38f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a0 = fminf(a0, __shfl_xor_sync(0xFFFFFFFFu, a0, o)); a1 = fmaxf(a1, __shfl_xor_sync(0xFFFFFFFFu, a1, o));
+            c0 = fminf(c0, __shfl_xor_sync(0xFFFFFFFFu, c0, o)); c1 = fmaxf(c1, __shfl_xor_sync(0xFFFFFFFFu, c1, o));
+            e0 = fminf(e0, __shfl_xor_sync(0xFFFFFFFFu, e0, o)); e1 = fmaxf(e1, __shfl_xor_sync(0xFFFFFFFFu, e1, o));
+        }
+        const bool any_valid = __any_sync(0xFFFFFFFFu, valid);
+        if (lane == p) {
+            bx0 = a0; bx1 = a1; by0 = c0; by1 = c1; bz0 = e0; bz1 = e1;
+            bmax_bits = any_valid ? 0x7F800000u : 0u;   // +inf: the first step visits every populated sub-bucket
+        }
+    }
+
+    int old = 0;
+    if (tid == 0) idx[0] = 0;
+    for (int j = 1; j < m; ++j) {
+        const int qpos = pos_of[old];
+        const float x1 = sx[qpos], y1 = sy[qpos], z1 = sz[qpos];
+        // box lower bound with the distance's own expression (monotone => rigorous in fp32)
+        const float lx = fmaxf(fmaxf(__fsub_rn(bx0, x1), __fsub_rn(x1, bx1)), 0.f);
+        const float ly = fmaxf(fmaxf(__fsub_rn(by0, y1), __fsub_rn(y1, by1)), 0.f);
+        const float lz = fmaxf(fmaxf(__fsub_rn(bz0, z1), __fsub_rn(z1, bz1)), 0.f);
+        const float lb = __fmaf_rn(lz, lz, __fmaf_rn(lx, lx, __fmul_rn(ly, ly)));
+        const bool act = (lane < P) && (lb < __uint_as_float(bmax_bits));
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, act);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            if ((mask >> p) & 1u) {
+                const int pos = (p * W + warp) * 32 + lane;
+                const float d = sqdist3(sx[pos], sy[pos], sz[pos], x1, y1, z1);
+                const float t = fminf(d, tmp[p]);
+                tmp[p] = t;
+                const bool valid = oidx[p] != 0xFFFFFFFFu;
+                const uint32_t u = (valid && t > 0.f) ? __float_as_uint(t) : 0u;
+                const uint32_t mx = __reduce_max_sync(0xFFFFFFFFu, u);
+                const uint32_t cand = (valid && u == mx) ? ~fps_rank(oidx[p], s_mask, s_log2) : 0u;
+                const uint32_t rr = __reduce_max_sync(0xFFFFFFFFu, cand);
+                if (lane == p) { bmax_bits = mx; brank = rr; }
+            }
+        }
+        // warp best over its P sub-buckets, then the block
+        const uint32_t wv = (lane < P) ? bmax_bits : 0u;
+        const uint32_t wm = __reduce_max_sync(0xFFFFFFFFu, wv);
+        const uint32_t wc = (lane < P && bmax_bits == wm) ? brank : 0u;
+        const uint32_t wr = __reduce_max_sync(0xFFFFFFFFu, wc);
+        uint2 *sl = slots[j & 1];
+        if (lane == 0) sl[warp] = make_uint2(wm, wr);
+        __syncthreads();
+        const uint2 v = (lane < W) ? sl[lane] : make_uint2(0u, 0u);
+        const uint32_t m2 = __reduce_max_sync(0xFFFFFFFFu, v.x);
+        const uint32_t c2 = (v.x == m2) ? v.y : 0u;
+        const uint32_t r2 = __reduce_max_sync(0xFFFFFFFFu, c2);
+        const uint32_t rank = ~r2;
+        old = (int)((__brev(rank) & s_mask) | ((rank & ((1u << (32u - s_log2)) - 1u)) << s_log2));
+        if (tid == 0) idx[j] = old;
+    }
+    if (temp) {
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+            if (oidx[p] != 0xFFFFFFFFu) temp[oidx[p]] = tmp[p];
+    }
+}
+
+template <int P>
+static int launch_fps_pruned(int b, int n, int m, const float *src, float *temp, int *idx, cudaStream_t st) {
+    const size_t smem = sizeof(float) * 3 * 512 * P + sizeof(unsigned short) * 512 * P;
+    auto kern = fps_pruned_kernel<P>;
+    if (smem + 4096 > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fps_pruned_kernel)");
+    }
+    kern<<<b, 512, smem, st>>>(n, m, src, temp, idx);
+    SPSK_LAUNCH_CHECK("fps_pruned_kernel");
+    return SPSK_OK;
 }
 
 // Small scenes, n < 1024: the reference block has S = 2^floor(log2 n) < 1024 threads; T = blockDim.x =
@@ -276,6 +474,12 @@ static int launch_fps_1024(int b, int n, int m, const float *src, float *temp, i
 }
 
 
+// SPSK_FPS=dense selects the unpruned kernels (same results; used by the tests to cross-check both)
+static bool fps_dense_forced() {
+    const char *e = getenv("SPSK_FPS");
+    return e && e[0] == 'd';
+}
+
 template <bool DISTMAT>
 static int fps_dispatch(int b, int n, int m, const float *src, float *temp, int *idx, cudaStream_t st) {
     SPSK_REQUIRE(b >= 0 && n >= 1 && m >= 0, SPSK_ERR_INVALID_ARG, "fps: bad sizes b=%d n=%d m=%d", b, n, m);
@@ -294,6 +498,13 @@ static int fps_dispatch(int b, int n, int m, const float *src, float *temp, int 
         fps_generic_kernel<DISTMAT><<<b, threads, 0, st>>>(n, m, s_mask, s_log2, src, temp, idx);
         SPSK_LAUNCH_CHECK("fps_generic_kernel");
         return SPSK_OK;
+    }
+    if (!DISTMAT && threads == 1024 && n <= 16384 && !fps_dense_forced()) {
+        if (n <= 1024) return launch_fps_pruned<2>(b, n, m, src, temp, idx, st);
+        if (n <= 2048) return launch_fps_pruned<4>(b, n, m, src, temp, idx, st);
+        if (n <= 4096) return launch_fps_pruned<8>(b, n, m, src, temp, idx, st);
+        if (n <= 8192) return launch_fps_pruned<16>(b, n, m, src, temp, idx, st);
+        return launch_fps_pruned<32>(b, n, m, src, temp, idx, st);
     }
     if (threads == 1024) {
         if (per_thread <= 1) return launch_fps_1024<1, !DISTMAT, DISTMAT>(b, n, m, src, temp, idx, st);

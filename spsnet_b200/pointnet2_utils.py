@@ -350,9 +350,13 @@ def gather_rows(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def ball_query_msg(radii, nsamples, xyz: torch.Tensor, new_xyz: torch.Tensor):
-    """All scales of an MSG layer in ONE scan; returns a list of (B, npoint, nsample_s) int32 tensors,
-    identical to [ball_query(r, ns, xyz, new_xyz) for r, ns in zip(radii, nsamples)]."""
+GRID_MIN_N = 2048  # below this the brute-force scan (early exit, smem tiles) is as fast as building a grid
+
+
+def ball_query_msg(radii, nsamples, xyz: torch.Tensor, new_xyz: torch.Tensor, grid=None):
+    """All scales of an MSG layer in ONE pass; returns a list of (B, npoint, nsample_s) int32 tensors,
+    identical to [ball_query(r, ns, xyz, new_xyz) for r, ns in zip(radii, nsamples)].  grid=None picks the
+    uniform-grid kernel for n >= GRID_MIN_N and the brute-force scan otherwise (same results)."""
     _chk(new_xyz, "new_xyz", torch.float32, 3)
     _chk(xyz, "xyz", torch.float32, 3)
     S = len(radii)
@@ -362,8 +366,15 @@ def ball_query_msg(radii, nsamples, xyz: torch.Tensor, new_xyz: torch.Tensor):
     r = (C.c_float * S)(*[float(x) for x in radii])
     n = (C.c_int * S)(*[int(x) for x in nsamples])
     ptrs = (C.c_void_p * S)(*[o.data_ptr() for o in outs])
+    use_grid = GRID_MIN_N <= N <= 65536 if grid is None else bool(grid)
     with torch.cuda.device(xyz.device):
-        check(lib.spsk_ball_query_msg(B, N, M, S, r, n, new_xyz.data_ptr(), xyz.data_ptr(), ptrs, _stream()), "ball_query_msg")
+        if use_grid:
+            nbytes = int(lib.spsk_ball_query_grid_workspace_bytes(B, N))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=xyz.device)
+            check(lib.spsk_ball_query_msg_grid(B, N, M, S, r, n, new_xyz.data_ptr(), xyz.data_ptr(), ptrs, ws.data_ptr(),
+                                               nbytes, _stream()), "ball_query_msg_grid")
+        else:
+            check(lib.spsk_ball_query_msg(B, N, M, S, r, n, new_xyz.data_ptr(), xyz.data_ptr(), ptrs, _stream()), "ball_query_msg")
     return outs
 
 

@@ -212,3 +212,52 @@ def test_score_topk(oracle, b, n, k):
             tt = t.cpu().numpy()
             for bb, jj in zip(*np.nonzero(mism)):
                 assert tt[bb, ti[bb, jj]] == tt[bb, idx[bb, jj]]
+
+
+def test_fps_pruned_equals_dense(oracle, monkeypatch):
+    """The Morton-pruned kernel and the dense kernel return identical indices (and both equal the oracle)."""
+    from spsnet_b200 import pointnet2_utils as pu
+
+    rng = np.random.default_rng(17)
+    cases = [(_xyz(2, 16384, seed=31), 4096), (_xyz(3, 4096, seed=32), 1024), (_xyz(2, 3000, seed=33), 2999),
+             (rng.integers(0, 4, (2, 9000, 3)).astype(np.float32), 500),          # massive ties
+             (np.ascontiguousarray(_xyz(1, 8192, seed=34, kind="waymo")), 2048),
+             (np.zeros((1, 2048, 3), np.float32), 64)]                              # all points identical
+    for xyz, m in cases:
+        monkeypatch.setenv("SPSK_FPS", "dense")
+        a = pu.furthest_point_sample(dev(xyz), m).cpu().numpy()
+        monkeypatch.delenv("SPSK_FPS")
+        b = pu.furthest_point_sample(dev(xyz), m).cpu().numpy()
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(b, oracle.fps(xyz, m))
+
+
+@pytest.mark.parametrize("b,n,m,radii,ns", [
+    (2, 16384, 1024, [0.2, 0.8], [16, 32]), (2, 4096, 700, [0.8, 1.6], [16, 32]), (1, 2048, 300, [1.6, 4.8], [16, 32]),
+    (2, 5000, 333, [0.05], [8]), (1, 3000, 64, [1000.0, 2.0, 0.5], [64, 32, 4]), (1, 65536, 512, [0.4, 1.0], [16, 32]),
+])
+def test_ball_query_grid_equals_bruteforce(oracle, b, n, m, radii, ns):
+    """Grid kernel == brute-force kernel == oracle, incl. centres far outside the scene (empty rows), duplicates,
+    a radius larger than the scene, and lattice data where many points sit exactly on cell borders."""
+    from spsnet_b200 import pointnet2_utils as pu
+
+    kind = "waymo" if n > 16384 else "kitti"
+    xyz = _xyz(b, n, seed=50 + n, kind=kind)
+    rng = np.random.default_rng(n)
+    sel = np.stack([rng.choice(n, m, replace=False) for _ in range(b)])
+    new_xyz = np.ascontiguousarray(np.take_along_axis(xyz, sel[..., None], axis=1))
+    new_xyz[:, 0] += 500.0
+    new_xyz[:, 1] -= 0.3           # off-point centres
+    new_xyz[:, 2, 1] += 2000.0
+    g = pu.ball_query_msg(radii, ns, dev(xyz), dev(new_xyz), grid=True)
+    bf = pu.ball_query_msg(radii, ns, dev(xyz), dev(new_xyz), grid=False)
+    for r, s, a, c in zip(radii, ns, g, bf):
+        np.testing.assert_array_equal(a.cpu().numpy(), c.cpu().numpy())
+        if n <= 16384:
+            np.testing.assert_array_equal(a.cpu().numpy(), oracle.ball_query(r, s, xyz, new_xyz))
+    # lattice: coordinates are exact multiples of the cell edge candidates
+    lat = rng.integers(0, 40, (1, 4096, 3)).astype(np.float32) * np.float32(0.25)
+    ctr = np.ascontiguousarray(lat[:, :256])
+    a = pu.ball_query_msg([0.5, 1.0], [16, 32], dev(lat), dev(ctr), grid=True)
+    for r, s, o in zip([0.5, 1.0], [16, 32], a):
+        np.testing.assert_array_equal(o.cpu().numpy(), oracle.ball_query(r, s, lat, ctr))
