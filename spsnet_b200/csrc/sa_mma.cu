@@ -56,6 +56,8 @@ struct MmaArgs {
     long long rows;  // b*m*nsample
     int ntiles;
     int nstages;
+    int tmem_cols;   // 256 or 512 (power of two >= every accumulator this chain needs)
+    int nbuf;        // last-layer accumulator buffers of 128 columns: tmem_cols / 128
     int xa_bytes, xb_bytes;
     const float *xyz, *new_xyz;
     const __half *twin;   // (b, n, cpad8)
@@ -139,9 +141,67 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&h);
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// 16 accumulator columns -> + bias -> ReLU -> fp16 -> two 16-byte stores into the next operand (K-major)
+__device__ __forceinline__ void store_hidden16(const float *v, const float *bias16, uint8_t *dst) {
+    const float4 *b4 = reinterpret_cast<const float4 *>(bias16);
+    uint32_t h[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 bb = __ldg(b4 + i);
+        h[2 * i] = pack_h2(fmaxf(v[4 * i] + bb.x, 0.f), fmaxf(v[4 * i + 1] + bb.y, 0.f));
+        h[2 * i + 1] = pack_h2(fmaxf(v[4 * i + 2] + bb.z, 0.f), fmaxf(v[4 * i + 3] + bb.w, 0.f));
+    }
+    *reinterpret_cast<uint4 *>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4 *>(dst + 128) = make_uint4(h[4], h[5], h[6], h[7]);
+}
+
+// Last-layer epilogue of one 128-cout chunk: thread = cout; max over each centre's NS consecutive columns,
+// + bias, ReLU, store to out[b, co_off + ch, p].  NS is a compile-time power of two, so the group
+// boundaries cost nothing; (scene, centre) of consecutive groups is advanced incrementally.
+template <int NS>
+__device__ __forceinline__ void pool_chunk(uint32_t taddr, float bv, bool ch_ok, float *outc, long long q0, long long qmax,
+                                           int m, size_t scene_stride, int p) {
+    // outc points at out[b(q0), co_off + ch, p(q0)]
+    long long q = q0;
+    float run = -3.0e38f;
+#pragma unroll
+    for (int c0 = 0; c0 < MM_ROWS; c0 += 32) {
+        float v[32];
+        tmem_ld32(taddr + (uint32_t)c0, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            run = fmaxf(run, v[i]);
+            if (((c0 + i + 1) % NS) == 0) {
+                if (ch_ok && q < qmax) *outc = fmaxf(run + bv, 0.f);
+                run = -3.0e38f;
+                ++q;
+                ++outc;
+                if (++p == m) { p = 0; outc += scene_stride - (size_t)m; }
+            }
+        }
+    }
+}
+__device__ __forceinline__ uint32_t pack_h2_unused_(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
 
 // ---- the kernel -----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MM_THREADS, 1)
+__global__ void __launch_bounds__(MM_THREADS, 2)
 sa_mma_kernel(const MmaArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     // carve: [barriers 256 B][XA][XB][W stages]
@@ -168,7 +228,7 @@ sa_mma_kernel(const MmaArgs a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(a.tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -219,7 +279,7 @@ sa_mma_kernel(const MmaArgs a) {
                             d_tmem = tmem_base + (uint32_t)(cc * 128);
                             idesc = umma_idesc(128, ncols);           // M = rows, N = couts
                         } else {
-                            buf = cc & 3;
+                            buf = cc & (a.nbuf - 1);
                             if (bu[buf] > 0) { mbar_wait(ACC_EMPTY(buf), (bu[buf] - 1) & 1u); tc_fence_after(); }
                             ++bu[buf];
                             d_tmem = tmem_base + (uint32_t)(buf * 128);
@@ -308,18 +368,17 @@ sa_mma_kernel(const MmaArgs a) {
                 ++af[0];
                 tc_fence_after();
                 const float *bias = a.bias + Ly.bias_off;
-                for (int c0 = 0; c0 < Ly.cpad; c0 += 16) {
+                int c0 = 0;
+                for (; c0 + 32 <= Ly.cpad; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(tmem_base + lane_field + (uint32_t)c0, v);
+                    store_hidden16(v, bias + c0, xrow + (size_t)(c0 >> 3) * 128);
+                    store_hidden16(v + 16, bias + c0 + 16, xrow + (size_t)((c0 >> 3) + 2) * 128);
+                }
+                if (c0 < Ly.cpad) {
                     float v[16];
                     tmem_ld16(tmem_base + lane_field + (uint32_t)c0, v);
-                    uint32_t h[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float y0 = fmaxf(v[2 * i] + __ldg(bias + c0 + 2 * i), 0.f);
-                        const float y1 = fmaxf(v[2 * i + 1] + __ldg(bias + c0 + 2 * i + 1), 0.f);
-                        h[i] = pack_h2(y0, y1);
-                    }
-                    *reinterpret_cast<uint4 *>(xrow + (size_t)(c0 >> 3) * 128) = make_uint4(h[0], h[1], h[2], h[3]);
-                    *reinterpret_cast<uint4 *>(xrow + (size_t)((c0 >> 3) + 1) * 128) = make_uint4(h[4], h[5], h[6], h[7]);
+                    store_hidden16(v, bias + c0, xrow + (size_t)(c0 >> 3) * 128);
                 }
                 // zero the K padding of the next layer's operand (kpad_{l+1} == cpad_l by construction, so none)
                 tc_fence_before();
@@ -333,31 +392,28 @@ sa_mma_kernel(const MmaArgs a) {
                 const long long q0 = ((long long)tile * MM_ROWS) >> a.ns_log2;  // first centre of the tile
                 const long long qmax = (long long)a.b * a.m;
                 const int ns = a.nsample;
+                const long long bb0 = q0 / a.m;
+                const int p0 = (int)(q0 - bb0 * a.m);
                 for (int cc = 0; cc < Ly.n_cc; ++cc) {
-                    const int buf = cc & 3;
+                    const int buf = cc & (a.nbuf - 1);
                     mbar_wait(ACC_FULL(buf), af[buf] & 1u);
                     ++af[buf];
                     tc_fence_after();
                     const int ch = cc * 128 + r;
                     const bool ch_ok = ch < a.cout_last;
                     const float bv = ch_ok ? __ldg(bias + ch) : 0.f;
-                    float run = -3.0e38f;
-                    for (int c0 = 0; c0 < MM_ROWS; c0 += 16) {
-                        float v[16];
-                        tmem_ld16(tmem_base + lane_field + (uint32_t)(buf * 128 + c0), v);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            run = fmaxf(run, v[i]);
-                            if (((c0 + i + 1) & (ns - 1)) == 0) {
-                                const long long q = q0 + ((c0 + i) >> a.ns_log2);
-                                if (ch_ok && q < qmax) {
-                                    const long long bb = q / a.m;
-                                    const long long p = q - bb * a.m;
-                                    a.out[((size_t)bb * a.c_total + a.co_off + ch) * a.m + p] = fmaxf(run + bv, 0.f);
-                                }
-                                run = -3.0e38f;
-                            }
-                        }
+                    float *outc = a.out + ((size_t)bb0 * a.c_total + a.co_off + (ch_ok ? ch : 0)) * a.m + (size_t)p0;
+                    const size_t sstride = (size_t)a.c_total * a.m;
+                    const uint32_t taddr = tmem_base + lane_field + (uint32_t)(buf * 128);
+                    switch (ns) {
+                        case 1: pool_chunk<1>(taddr, bv, ch_ok, outc, q0, qmax, a.m, sstride, p0); break;
+                        case 2: pool_chunk<2>(taddr, bv, ch_ok, outc, q0, qmax, a.m, sstride, p0); break;
+                        case 4: pool_chunk<4>(taddr, bv, ch_ok, outc, q0, qmax, a.m, sstride, p0); break;
+                        case 8: pool_chunk<8>(taddr, bv, ch_ok, outc, q0, qmax, a.m, sstride, p0); break;
+                        case 16: pool_chunk<16>(taddr, bv, ch_ok, outc, q0, qmax, a.m, sstride, p0); break;
+                        case 32: pool_chunk<32>(taddr, bv, ch_ok, outc, q0, qmax, a.m, sstride, p0); break;
+                        case 64: pool_chunk<64>(taddr, bv, ch_ok, outc, q0, qmax, a.m, sstride, p0); break;
+                        default: pool_chunk<128>(taddr, bv, ch_ok, outc, q0, qmax, a.m, sstride, p0); break;
                     }
                     tc_fence_before();
                     mbar_arrive(ACC_EMPTY(buf));
@@ -370,7 +426,7 @@ sa_mma_kernel(const MmaArgs a) {
     __syncthreads();
     if (warp == 5) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols));
     }
 }
 
@@ -421,7 +477,21 @@ extern "C" int spsk_sa_mma_smem_bytes(int nlayers, const int *kpad, const int *c
     if (stages < 2) return -1;
     if (nstages_out) *nstages_out = stages;
     int total = 256 + xa + xbv + stages * MM_WTILE_BYTES;
-    if (total < 120 * 1024) total = 120 * 1024;  // force one CTA per SM (each CTA allocates all 512 TMEM columns)
+    // TMEM: 256 columns per CTA when every hidden accumulator fits (two CTAs can then share an SM and overlap one
+    // tile's gather / epilogue with the other's MMAs); the shared-memory floors keep the CTA count per SM within
+    // the TMEM budget (3 x 76 KB and 2 x 120 KB both exceed 227 KB).
+    int hidden_max = 0;
+    for (int l = 0; l + 1 < nlayers; ++l) hidden_max = max(hidden_max, cpad[l]);
+    const bool two = hidden_max <= 256 && (256 + xa + xbv + 2 * MM_WTILE_BYTES) <= 112 * 1024;
+    if (two) {
+        stages = (112 * 1024 - 256 - xa - xbv) / MM_WTILE_BYTES;
+        if (stages > MM_MAX_STAGES) stages = MM_MAX_STAGES;
+        if (nstages_out) *nstages_out = stages;
+        total = 256 + xa + xbv + stages * MM_WTILE_BYTES;
+        if (total < 76 * 1024) total = 76 * 1024;
+        return -total;  // negative: "two CTAs per SM" variant (256 TMEM columns)
+    }
+    if (total < 120 * 1024) total = 120 * 1024;
     return total;
 }
 
@@ -464,9 +534,13 @@ extern "C" int spsk_sa_mma_forward(const spsk_group_desc *g, int cpad8, const vo
     SPSK_REQUIRE(ntiles <= 0x7FFFFFFF, SPSK_ERR_UNSUPPORTED, "sa_mma: too many rows");
     a.ntiles = (int)ntiles;
     int nstages = 0;
-    const int smem = spsk_sa_mma_smem_bytes(nlayers, kpad, cpad, &nstages);
-    SPSK_REQUIRE(smem > 0, SPSK_ERR_UNSUPPORTED, "sa_mma: activation tiles do not fit shared memory (max layer width too large)");
+    int smem = spsk_sa_mma_smem_bytes(nlayers, kpad, cpad, &nstages);
+    SPSK_REQUIRE(smem != -1, SPSK_ERR_UNSUPPORTED, "sa_mma: activation tiles do not fit shared memory (max layer width too large)");
+    const bool two_per_sm = smem < 0;
+    if (two_per_sm) smem = -smem;
     a.nstages = nstages;
+    a.tmem_cols = two_per_sm ? 256 : 512;
+    a.nbuf = a.tmem_cols / 128;
     a.xa_bytes = 0; a.xb_bytes = 0;
     for (int l = 0; l < nlayers; ++l) {
         const int bytes = kpad[l] * MM_ROWS * 2;
@@ -482,7 +556,10 @@ extern "C" int spsk_sa_mma_forward(const spsk_group_desc *g, int cpad8, const vo
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(sa_mma_kernel)");
         attr_set_for = 227 * 1024;
     }
-    const int grid = a.ntiles < SPSK_NUM_SMS ? a.ntiles : SPSK_NUM_SMS;
+    // a few CTAs per SM slot (static tile striding): when another stream's kernels hold some SMs, late CTAs start
+    // as soon as any SM frees up instead of doubling the kernel's duration
+    const int slots = SPSK_NUM_SMS * (two_per_sm ? 2 : 1) * 2;
+    const int grid = a.ntiles < slots ? a.ntiles : slots;
     sa_mma_kernel<<<grid, MM_THREADS, smem, as_stream(stream)>>>(a);
     SPSK_LAUNCH_CHECK("sa_mma_kernel");
     return SPSK_OK;

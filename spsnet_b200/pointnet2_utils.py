@@ -480,7 +480,8 @@ class MmaChain:
         self._c = {k: (C.c_int * self.nlayers)(*getattr(self, k)) for k in ("kpad", "cpad", "tile_off", "bias_off")}
         if self.ok:
             ns = C.c_int(0)
-            self.ok = lib.spsk_sa_mma_smem_bytes(self.nlayers, self._c["kpad"], self._c["cpad"], C.byref(ns)) > 0
+            # > 0: one CTA per SM (512 TMEM columns); < -1: two CTAs per SM (256 columns); -1: does not fit
+            self.ok = lib.spsk_sa_mma_smem_bytes(self.nlayers, self._c["kpad"], self._c["cpad"], C.byref(ns)) != -1
 
 
 def make_twin(features: torch.Tensor, cpad8: int) -> torch.Tensor:

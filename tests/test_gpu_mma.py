@@ -1,6 +1,8 @@
 """-m gpu tests of the tcgen05 tensor-core scale kernel (sa_mma.cu) against the exact-fp32 FFMA path of the same
 library and a float64 torch reference.  Tolerance: 1e-3 of the output range (BASELINE.json north_star);
 the measured error is printed so it lands in the logs."""
+import zlib
+
 import numpy as np
 import pytest
 import torch
@@ -37,7 +39,7 @@ def test_mma_scale_vs_fp32(oracle, name, B, N, M):
     from spsnet_b200 import pointnet2_utils as pu
 
     c_feat, ns, radius, widths = SCALES[name]
-    rng = np.random.default_rng(hash(name) % 1000)
+    rng = np.random.default_rng(zlib.crc32(name.encode()) % 1000)  # str hash() is salted per process
     xyz_np = np.ascontiguousarray(scenes.make_batch(3, B, N)[:, :, :3])
     xyz = torch.from_numpy(xyz_np).cuda()
     feats = torch.from_numpy(rng.standard_normal((B, c_feat, N)).astype(np.float32)).cuda() if c_feat else None
