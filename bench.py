@@ -160,9 +160,17 @@ def profile_kernels(net, dev_points, steps: int):
             e0.record()
             rc = fn(*a)
             e1.record()
-            if name in ("spsk_grouped_linear", "spsk_sa_mma_forward"):  # a[0] is byref(GroupDesc): read the row count while it is alive
+            if name == "spsk_grouped_linear":  # a[0] is byref(GroupDesc): read the row count while it is alive
                 g = a[0]._obj
                 a = (int(g.b) * int(g.m) * int(g.nsample),) + tuple(a[1:])
+            elif name == "spsk_sa_mma_forward":
+                g = a[0]._obj
+                nl = int(g.nlayers)
+                a = (int(g.b) * int(g.m) * int(g.nsample), [int(g.kpad[i]) for i in range(nl)], [int(g.cpad[i]) for i in range(nl)],
+                     int(g.cout_last), int(g.split))
+            elif name == "spsk_pw_mma_forward":
+                g = a[0]._obj
+                a = (int(g.rows), int(g.k), int(g.n))
             records.append((name, a, e0, e1))
             return rc
         return inner
@@ -188,7 +196,9 @@ def profile_kernels(net, dev_points, steps: int):
         elif name == "spsk_grouped_linear":
             key = f"{name}[cin={a[3]},cout={a[6]}]"
         elif name == "spsk_sa_mma_forward":
-            key = f"{name}[rows={a[0]},cout={a[10]}]"
+            key = f"{name}[rows={a[0]},cout={a[3]}{',split' if a[4] else ''}]"
+        elif name == "spsk_pw_mma_forward":
+            key = f"{name}[rows={a[0]},k={a[1]},n={a[2]}]"
         ms = e0.elapsed_time(e1)
         t = table.setdefault(key, {"ms": 0.0, "launches": 0, "args": a})
         t["ms"] += ms

@@ -197,28 +197,80 @@ SPSK_API int spsk_pointwise_linear(int b, int m, const float *in, int c_in, cons
  * zero padded to cpad8 (multiple of 8) channels, so that gathering one neighbour is a run of 16-byte loads. */
 SPSK_API int spsk_make_twin(int b, int c, int n, int cpad8, const float *features, void *twin, spsk_stream_t stream);
 
-/* Dynamic shared memory spsk_sa_mma_forward needs for a chain with the given padded widths (-1 if it
- * does not fit); *nstages_out receives the depth of the weight-tile ring. */
-SPSK_API int spsk_sa_mma_smem_bytes(int nlayers, const int *kpad, const int *cpad, int *nstages_out);
-
 /* One MSG scale, fully fused on the tensor cores: gather (idx) -> [features | xyz - centre] -> nlayers x
- * (1x1 conv + folded BN + ReLU) -> max over nsample -> out_pooled[b, co_off + c, p]   (replaces
- * QueryAndGroup.forward's grouping + cat and the shared MLP + max_pool2d, pointnet2_utils.py:307-315,
- * pointnet2_modules.py:204-211,431-436).  fp16 operands / fp32 accumulation.
- *   g         : xyz, new_xyz, idx as in spsk_grouped_linear (g->features unused, g->c_feat ignored)
- *   twin      : (b, n, cpad8) fp16 from spsk_make_twin (NULL iff cpad8 == 0)
- *   layer l   : input width kpad[l] (multiple of 16; kpad[0] >= cpad8 + 8*use_xyz, k order = [features(cpad8),
- *               x, y, z, 0...]), output width cpad[l] (multiple of 16; last layer: multiple of 128);
- *               cpad[l] == kpad[l+1]
- *   wtiles    : fp16 weight tiles of 128 couts x 64 k in the canonical K-major no-swizzle UMMA layout
- *               (byte(r,k) = (r/8)*1024 + (k/8)*128 + (r%8)*16 + (k%8)*2), zero padded, ordered
- *               layer -> cout chunk -> k chunk; layer l starts at tile tile_off[l]
- *   bias      : folded BN shift per layer at bias_off[l] (cpad[l] floats, zero padded)
+ * (1x1 conv + folded BN + ReLU) -> max over nsample   (replaces QueryAndGroup.forward's grouping + cat and the
+ * shared MLP + max_pool2d, pointnet2_utils.py:307-315, pointnet2_modules.py:204-211,431-436).
+ * fp16 operands / fp32 accumulation; `split` selects hi+lo fp16 operands (3 products, fp32-grade) for narrow chains.
+ *
+ *   layer l   : input width kpad[l] (multiple of 16), output width cpad[l] (multiple of 16; last layer: multiple
+ *               of 128), cpad[l] == kpad[l+1].  Plain mode: kpad[0] >= ceil8(c_feat) + 8*use_xyz with k order
+ *               [features (ceil8(c_feat)), x, y, z, 0...].  Split mode: kpad[0] == 16, k order [f0..f7, x, y, z, 0...]
+ *               (c_feat <= 8; xyz first when c_feat == 0), every width <= 64.
+ *   wtiles    : per layer (layers concatenated) the matrix W'[vk, cpad] (vk = kpad, or 3*kpad = [Wh; Wh; Wl] rows in
+ *               split mode) cut into tiles of (<=128 couts) x (<=64 k), ordered cout-chunk major then k, each tile
+ *               `ncols x kw` fp16 in the canonical K-major no-swizzle UMMA layout
+ *               byte(r, k) = (r/8)*(kw*16) + (k/8)*128 + (r%8)*16 + (k%8)*2;  zero padded
+ *   bias      : folded BN shift, layers concatenated, cpad[l] floats each (zero padded)
+ *   outputs   : out_cm[b, co_off + c, p] fp32 (the reference's new_features layout, (b, c_total, m)) and / or
+ *               out16[(b*m + p) * ld16 + co16 + c] fp16 point-major for c < n16 (columns cout_last..n16 get zeros)
  *   nsample must be a power of two <= 128. */
-SPSK_API int spsk_sa_mma_forward(const spsk_group_desc *g, int cpad8, const void *twin, int nlayers, const int *kpad,
-                        const int *cpad, const int *tile_off, const int *bias_off, const void *wtiles,
-                        const float *bias, int cout_last, float *out_pooled, int c_total, int co_off,
-                        spsk_stream_t stream);
+typedef struct spsk_sa_mma_desc {
+    int b, n, m, nsample;
+    const float *xyz;       /* (b,n,3) */
+    const float *new_xyz;   /* (b,m,3) */
+    const int *idx;         /* (b,m,nsample) */
+    int use_xyz;
+    int c_feat;
+    const void *twin;       /* (b,n,ldtwin) fp16 point-major features (plain mode), NULL if c_feat == 0 */
+    int ldtwin;             /* multiple of 8, >= ceil8(c_feat) */
+    const float *features;  /* (b,c_feat,n) fp32 (split mode) */
+    int split;
+    int nlayers;
+    int kpad[4], cpad[4];
+    const void *wtiles;
+    const float *bias;
+    int cout_last;
+    float *out_cm; int c_total, co_off;
+    void *out16; int ld16, co16, n16;
+    int o16lo;              /* > 0: out16 also receives the residuals fp16(y - fp16(y)) at column o16lo + co16 + c */
+} spsk_sa_mma_desc;
+
+/* Launch shape the library picks for a chain (only nlayers / kpad / cpad / split are read): dynamic shared memory,
+ * co-resident CTAs per SM, weight-ring depth, and whether the packed chain stays resident in shared memory.
+ * SPSK_ERR_UNSUPPORTED when the chain does not fit. */
+SPSK_API int spsk_sa_mma_config(const spsk_sa_mma_desc *d, int *smem_bytes, int *ctas_per_sm, int *nstages, int *resident);
+SPSK_API int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stream);
+/* Tuning aid: when `counters` (device memory, SPSK_SA_PROF_COUNTERS x u64, zeroed by the caller) is non-NULL every
+ * following spsk_sa_mma_forward adds the SM cycles its warp roles spent per wait / work category (order: mma total,
+ * mma wait acc-empty, mma wait weights, mma wait activations, producer wait stage, producer wait hidden-done, epilogue
+ * total, gather, wait hidden acc, hidden epilogue, wait pool acc, pool epilogue; summed over CTAs, epilogue = thread 0). */
+#define SPSK_SA_PROF_COUNTERS 12
+SPSK_API int spsk_sa_mma_set_profile(unsigned long long *counters);
+
+/* Point-wise layer on the tensor cores:  y[row, c] = relu?( bias[c] + sum_k x[row, k] * W[c, k] )  over point-major
+ * fp16 rows (replaces the aggregation / confidence / vote Conv1d + BN + ReLU stacks, pointnet2_modules.py:216-243,
+ * 447-458, 485-500).
+ *   x       : (rows, ldx) fp16, first k columns used (k multiple of 16; columns >= the true width must hold zeros)
+ *   wtiles  : W (n x k) cut into 128-cout x 64-k tiles, cout-chunk major then k, each tile a full 16 KB block in the
+ *             canonical K-major no-swizzle layout byte(r, kk) = (r/8)*1024 + (kk/8)*128 + (r%8)*16 + (kk%8)*2, zero
+ *             padded; tiles must cover ceil128(max(n, n16)) couts
+ *   bias    : ceil128(max(n, n16)) floats, zero padded
+ *   outputs (any subset): out_cm[(row/m) , co_off + c, row%m] fp32 channel-major (b, c_total, m);
+ *             out16[row*ld16 + c] fp16 for c < n16 (zeros above n); out_pm[row*ldpm + c] fp32 for c < n. */
+typedef struct spsk_pw_desc {
+    int rows, k, ldx, n, relu;
+    int split;  /* 1: fp32-grade arithmetic on hi + lo fp16 halves: x rows hold hi in columns [0, k) and lo = fp16(v - hi) in
+                   [xlo, xlo + k); wtiles pack W' = [Wh ; Wh ; Wl] (3k rows of K); y = xh.Wh + xl.Wh + xh.Wl */
+    int xlo;
+    const void *x;
+    const void *wtiles;
+    const float *bias;
+    float *out_cm; int m, c_total, co_off;
+    void *out16; int ld16, n16;
+    int o16lo;  /* > 0: out16 also receives the residuals fp16(y - fp16(y)) at columns [o16lo, o16lo + n16) */
+    float *out_pm; int ldpm;
+} spsk_pw_desc;
+SPSK_API int spsk_pw_mma_forward(const spsk_pw_desc *d, spsk_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -42,9 +42,10 @@ SIGNATURES = {
     "spsk_grouped_linear": [_p, _i, _p, _i, _p, _p, _i, _i, _i, _p, _p, _i, _i, _p],
     "spsk_pointwise_linear": [_i, _i, _p, _i, _p, _p, _i, _i, _p, _p],
     "spsk_make_twin": [_i, _i, _i, _i, _p, _p, _p],
-    "spsk_sa_mma_smem_bytes": [_i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)],
-    "spsk_sa_mma_forward": [_p, _i, _p, _i, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), _p, _p, _i, _p,
-                            _i, _i, _p],
+    "spsk_sa_mma_config": [_p, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)],
+    "spsk_sa_mma_forward": [_p, _p],
+    "spsk_sa_mma_set_profile": [_p],
+    "spsk_pw_mma_forward": [_p, _p],
 }
 _RESTYPE = {"spsk_last_error": C.c_char_p, "spsk_launch_count": C.c_ulonglong,
             "spsk_ball_query_grid_workspace_bytes": C.c_longlong}
@@ -57,6 +58,34 @@ class GroupDesc(C.Structure):
         ("b", _i), ("n", _i), ("m", _i), ("nsample", _i),
         ("c_feat", _i), ("use_xyz", _i),
         ("xyz", _p), ("new_xyz", _p), ("features", _p), ("idx", _p),
+    ]
+
+
+class SaMmaDesc(C.Structure):
+    """struct spsk_sa_mma_desc (include/spsk.h)."""
+
+    _fields_ = [
+        ("b", _i), ("n", _i), ("m", _i), ("nsample", _i),
+        ("xyz", _p), ("new_xyz", _p), ("idx", _p),
+        ("use_xyz", _i), ("c_feat", _i),
+        ("twin", _p), ("ldtwin", _i),
+        ("features", _p), ("split", _i),
+        ("nlayers", _i), ("kpad", _i * 4), ("cpad", _i * 4),
+        ("wtiles", _p), ("bias", _p), ("cout_last", _i),
+        ("out_cm", _p), ("c_total", _i), ("co_off", _i),
+        ("out16", _p), ("ld16", _i), ("co16", _i), ("n16", _i), ("o16lo", _i),
+    ]
+
+
+class PwDesc(C.Structure):
+    """struct spsk_pw_desc (include/spsk.h)."""
+
+    _fields_ = [
+        ("rows", _i), ("k", _i), ("ldx", _i), ("n", _i), ("relu", _i), ("split", _i), ("xlo", _i),
+        ("x", _p), ("wtiles", _p), ("bias", _p),
+        ("out_cm", _p), ("m", _i), ("c_total", _i), ("co_off", _i),
+        ("out16", _p), ("ld16", _i), ("n16", _i), ("o16lo", _i),
+        ("out_pm", _p), ("ldpm", _i),
     ]
 
 

@@ -36,6 +36,20 @@ void count_launch();
 
 static inline cudaStream_t as_stream(spsk_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: set it once per (kernel, device).
+struct SmemAttrOnce {
+    bool done[64] = {};
+    int ensure(const void *func, int bytes, const char *what) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+        if (done[dev]) return 0;
+        cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return cuda_fail(e, what);
+        done[dev] = true;
+        return 0;
+    }
+};
+
 // reference: src/cuda_utils.h:10-14 opt_n_threads -- the block size the REFERENCE would launch the FPS
 // kernels with; it decides the arg-max tie-break (see fps_rank below), not our launch shape.
 static inline int ref_block_threads(int n) {

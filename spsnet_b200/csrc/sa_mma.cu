@@ -6,155 +6,86 @@
 //     3 x [Conv2d 1x1 (no bias) -> BatchNorm2d(eval) -> ReLU] ; F.max_pool2d over nsample
 // The (B,3+C,npoint,nsample) grouped tensor and all conv/BN/ReLU intermediates stay on chip.
 //
-// Machine mapping (persistent CTAs, one per SM, 192 threads, TMEM 512 columns):
+// Machine mapping (persistent CTAs, 192 threads, 1-3 CTAs per SM depending on the chain's footprint):
 //   tile        = 128 grouped rows (= 128/nsample centres), looped over by each CTA
+//   job         = (layer, 128-wide cout chunk): one accumulator of <=128 TMEM columns; jobs of a tile run in
+//                 layer order through a ring of `nbuf` accumulators, so the MMAs of job j+1.. overlap the
+//                 epilogue of job j
 //   warps 0-3   : (a) gather: row r = thread r builds X0[r, :] = [features(idx) | xyz(idx) - centre | 0] as fp16
 //                     with 16-byte loads from the point-major fp16 feature twin and 16-byte smem stores;
-//                 (b) epilogue: TMEM -> registers (tcgen05.ld), + folded-BN bias, ReLU, -> fp16 operand of the
-//                     next layer in shared memory; last layer: max over nsample + bias + ReLU -> global
+//                 (b) hidden-layer epilogue: TMEM -> registers (tcgen05.ld), + folded-BN bias, ReLU, -> fp16 operand
+//                     of the next layer in shared memory, signalled per 64-wide K chunk so the next layer's MMAs
+//                     start before the whole activation is written;
+//                 (c) last layer: max over nsample + bias + ReLU -> global (fp32 channel-major and/or fp16 point-major)
 //   warp 4      : weight producer: 1-D bulk async copies (cp.async.bulk + mbarrier complete_tx) of host-packed
-//                 16 KB weight tiles through a ring of stages
+//                 weight tiles, either once (chain resident in shared memory) or through a ring of 16 KB stages
 //   warp 5      : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, fp16 operands, fp32 accumulate)
 //   hidden layers  (orientation A): D[row, cout]  = X[row, k] . W[cout, k]^T   M = 128 rows,  N = cout chunk
 //   last layer     (orientation B): D[cout, row]  = W[cout, k] . X[row, k]^T   M = 128 couts, N = 128 rows
-//                 so that the max over the nsample rows of a centre is a per-thread loop over TMEM columns;
-//                 4 accumulator buffers (4 x 128 columns) overlap the chunk epilogue with the next chunk's MMAs.
+//                 so that the max over the nsample rows of a centre is a per-thread loop over TMEM columns.
 //   All operands use the canonical K-major, no-swizzle UMMA layout (8-row x 16-byte core matrices):
 //       byte(r, k) = (r/8)*SBO + (k/8)*128 + (r%8)*16 + (k%8)*2          LBO = 128
 //
-// Numerics: operands are fp32 values rounded to fp16 (11-bit significand, same as TF32), products are
-// exact and accumulate in fp32; measured end-to-end error of a 3-layer scale is ~4e-4 of the output
-// range (DESIGN.md "precision"), inside the 1e-3 bar of BASELINE.json.  The exact-fp32 path is
-// linear_ffma.cu.
-#include "common.cuh"
-#include <cuda_fp16.h>
+// Numerics.  Default: operands are fp32 values rounded to fp16 (11-bit significand, same as TF32), products are
+// exact and accumulate in fp32; measured end-to-end error of a 3-layer scale is ~5e-4 of the output range.
+// `split` mode (narrow chains, every K <= 64, i.e. IA-SSD layer 0 where the error does not average out): every
+// operand is carried as hi + lo fp16 halves and each product is evaluated as Xh.Wh + Xl.Wh + Xh.Wl by
+// concatenating along K ([Xh | Xl | Xh] . [Wh ; Wh ; Wl]) -- fp32-grade results (~1e-6) for 3x MMA work that
+// these layers do not notice.  The exact-fp32 CUDA-core path is linear_ffma.cu.
+#include "mma_ptx.cuh"
+#include <stdlib.h>
 
 namespace spsk {
 
 constexpr int MM_ROWS = 128;          // grouped rows per tile
 constexpr int MM_THREADS = 192;       // 4 gather/epilogue warps + producer + mma
-constexpr int MM_WTILE_BYTES = 16384; // [128 cout][64 k] fp16
+constexpr int MM_STAGE_BYTES = 16384; // largest weight tile: [128 cout][64 k] fp16
 constexpr int MM_MAX_LAYERS = 4;
-constexpr int MM_MAX_STAGES = 6;
+constexpr int MM_MAX_STAGES = 8;
+constexpr int MM_HDR = 1024;          // barriers + TMEM slot
+constexpr int MM_MAX_XC = 16;         // 64-wide K chunks per activation buffer (K <= 1024)
 
-struct MmaLayer {
-    int kpad;      // input width, multiple of 16
+struct SaLayer {
+    int kpad;      // true input width, multiple of 16
     int cpad;      // output width: multiple of 16 (hidden) / 128 (last)
     int n_cc;      // ceil(cpad / 128)
-    int n_kc;      // ceil(kpad / 64)
-    int tile_off;  // first weight tile of this layer (units of 16 KB tiles)
-    int bias_off;  // offset into the bias array (floats)
+    int xw;        // activation buffer width in halfs: kpad (plain) or 2*kpad (split: [hi | lo])
+    int vk;        // K the MMAs run over: kpad (plain) or 3*kpad (split)
+    int n_kc;      // ceil(vk / 64)  weight tiles per cout chunk
+    int n_xc;      // ceil(xw / 64)  readiness chunks of the activation buffer
+    int w_off;     // byte offset of this layer's tiles in the packed weights
+    int bias_off;  // float offset into the bias array
 };
 
-struct MmaArgs {
+struct SaArgs {
     int nlayers;
-    MmaLayer L[MM_MAX_LAYERS];
+    SaLayer L[MM_MAX_LAYERS];
     int b, n, m, nsample, ns_log2;
-    int cpad8;       // feature channels in the twin (multiple of 8, 0 if none)
-    int use_xyz;
-    int k0pad;
+    int c_feat, cpad8, ldtwin, use_xyz, split;
     long long rows;  // b*m*nsample
     int ntiles;
-    int nstages;
-    int tmem_cols;   // 256 or 512 (power of two >= every accumulator this chain needs)
-    int nbuf;        // last-layer accumulator buffers of 128 columns: tmem_cols / 128
+    int nstages, resident, w_total, tmem_cols, nbuf, nbuf_log2;
+    int lstages;     // > 0: the last layer streams its weights through `lstages` extra 16 KB slots overlaid on the activation
+                     // buffer that is dead while it runs (the input of layer nlayers-2)
     int xa_bytes, xb_bytes;
-    const float *xyz, *new_xyz;
-    const __half *twin;   // (b, n, cpad8)
+    const float *xyz, *new_xyz, *feat32;
+    const __half *twin;   // (b, n, ldtwin)
     const int *idx;       // (b, m, nsample)
-    const __half *wtiles; // packed weight tiles
+    const uint8_t *wtiles;
     const float *bias;
-    float *out;           // (b, c_total, m)
+    float *out;           // (b, c_total, m) or null
     int c_total, co_off, cout_last;
+    __half *out16;        // (b*m, ld16) or null
+    int ld16, co16, n16, o16lo;
+    unsigned long long *prof;   // optional per-role wait/work cycle counters (spsk_sa_mma_set_profile), null = off
 };
 
-// ---- PTX wrappers ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// bounded wait: a protocol bug traps (the context dies, the box survives) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.b32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) return;
-    }
-    __trap();
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
+// byte offset of weight tile (cc, kc) inside a layer: chunks of 128 couts are contiguous (cc-major), inside a chunk
+// the tiles follow each other along K; a tile is ncols x kw fp16 in canonical layout with SBO = kw*16
+__device__ __forceinline__ int wtile_off(const SaLayer &Ly, int cc, int kc, int ncols) {
+    return Ly.w_off + (128 * cc * Ly.vk + ncols * 64 * kc) * 2;
 }
 
-// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
-// version=1 [46,48), layout_type=0 [61,64)   (cute/arch/mma_sm100_desc.hpp::SmemDescriptor)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
-           (1ull << 46);
-}
-// instruction descriptor kind::f16: D=f32 (bits 4-5 = 1), A=B=f16 (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
-__device__ __forceinline__ uint32_t umma_idesc(int m, int n) {
-    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t *>(&h);
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
 // 16 accumulator columns -> + bias -> ReLU -> fp16 -> two 16-byte stores into the next operand (K-major)
 __device__ __forceinline__ void store_hidden16(const float *v, const float *bias16, uint8_t *dst) {
     const float4 *b4 = reinterpret_cast<const float4 *>(bias16);
@@ -168,46 +99,117 @@ __device__ __forceinline__ void store_hidden16(const float *v, const float *bias
     *reinterpret_cast<uint4 *>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4 *>(dst + 128) = make_uint4(h[4], h[5], h[6], h[7]);
 }
+// hi/lo split of 8 fp32 values: hi = fp16(x), lo = fp16(x - hi)
+__device__ __forceinline__ void split8(const float *y, uint4 &hi, uint4 &lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 hh = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
+        const float2 hf = __half22float2(hh);
+        h[i] = *reinterpret_cast<const uint32_t *>(&hh);
+        l[i] = pack_h2(y[2 * i] - hf.x, y[2 * i + 1] - hf.y);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ void store_hidden16_split(const float *v, const float *bias16, uint8_t *dst_hi, uint8_t *dst_lo) {
+    float y[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) y[i] = fmaxf(v[i] + __ldg(bias16 + i), 0.f);
+    uint4 h0, l0, h1, l1;
+    split8(y, h0, l0);
+    split8(y + 8, h1, l1);
+    *reinterpret_cast<uint4 *>(dst_hi) = h0;
+    *reinterpret_cast<uint4 *>(dst_hi + 128) = h1;
+    *reinterpret_cast<uint4 *>(dst_lo) = l0;
+    *reinterpret_cast<uint4 *>(dst_lo + 128) = l1;
+}
 
 // Last-layer epilogue of one 128-cout chunk: thread = cout; max over each centre's NS consecutive columns,
-// + bias, ReLU, store to out[b, co_off + ch, p].  NS is a compile-time power of two, so the group
-// boundaries cost nothing; (scene, centre) of consecutive groups is advanced incrementally.
+// + bias, ReLU, store.  The output cursors advance incrementally with the centre.
+struct PoolOut {
+    float bv;
+    bool w32, w16;
+    float *outc;
+    __half *out16;
+    int ld16, o16lo;
+    long long q, qmax;
+    int m, p;
+    size_t scene_stride;
+    __device__ __forceinline__ void emit(float run) {
+        const float y = fmaxf(run + bv, 0.f);
+        if (q < qmax) {
+            if (w32) *outc = y;
+            if (w16) {
+                const __half h = __float2half_rn(y);
+                *out16 = h;
+                if (o16lo > 0) out16[o16lo] = __float2half_rn(y - __half2float(h));
+            }
+        }
+        ++q;
+        ++outc;
+        out16 += ld16;
+        if (++p == m) { p = 0; outc += scene_stride - (size_t)m; }
+    }
+};
+// NS = 16 / 32 (every shipped IA-SSD / SPSNet config): compile-time group boundaries
 template <int NS>
-__device__ __forceinline__ void pool_chunk(uint32_t taddr, float bv, bool ch_ok, float *outc, long long q0, long long qmax,
-                                           int m, size_t scene_stride, int p) {
-    // outc points at out[b(q0), co_off + ch, p(q0)]
-    long long q = q0;
+__device__ __forceinline__ void pool_chunk(uint32_t taddr, PoolOut &o) {
     float run = -3.0e38f;
-#pragma unroll
+#pragma unroll 1
     for (int c0 = 0; c0 < MM_ROWS; c0 += 32) {
         float v[32];
         tmem_ld32(taddr + (uint32_t)c0, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
             run = fmaxf(run, v[i]);
-            if (((c0 + i + 1) % NS) == 0) {
-                if (ch_ok && q < qmax) *outc = fmaxf(run + bv, 0.f);
-                run = -3.0e38f;
-                ++q;
-                ++outc;
-                if (++p == m) { p = 0; outc += scene_stride - (size_t)m; }
-            }
+            if (((i + 1) % NS) == 0) { o.emit(run); run = -3.0e38f; }
         }
     }
 }
-__device__ __forceinline__ uint32_t pack_h2_unused_(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t *>(&h);
+// any power of two <= 128
+__device__ __noinline__ void pool_chunk_any(uint32_t taddr, PoolOut &o, int ns) {
+    float run = -3.0e38f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < MM_ROWS; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            run = fmaxf(run, v[i]);
+            if (((c0 + i + 1) & (ns - 1)) == 0) { o.emit(run); run = -3.0e38f; }
+        }
+    }
 }
 
+// ---- optional role profiling: cycles spent per wait / work category, summed over CTAs ------------------------
+enum { PF_MMA_TOTAL = 0, PF_MMA_ACC_EMPTY, PF_MMA_W_FULL, PF_MMA_XR, PF_PROD_W_EMPTY, PF_PROD_HID, PF_EPI_TOTAL, PF_EPI_GATHER,
+       PF_EPI_WAIT_HID, PF_EPI_WORK_HID, PF_EPI_WAIT_POOL, PF_EPI_WORK_POOL, PF_COUNT };
+struct Prof {
+    unsigned long long acc[PF_COUNT];
+    bool on;
+    __device__ __forceinline__ void init(bool enable) {
+        on = enable;
+#pragma unroll
+        for (int i = 0; i < PF_COUNT; ++i) acc[i] = 0ull;
+    }
+    __device__ __forceinline__ long long now() const { return on ? clock64() : 0ll; }
+    __device__ __forceinline__ void add(int k, long long t0) { if (on) acc[k] += (unsigned long long)(clock64() - t0); }
+    __device__ __forceinline__ void flush(unsigned long long *dst) const {
+        if (!on) return;
+        for (int i = 0; i < PF_COUNT; ++i)
+            if (acc[i]) atomicAdd(dst + i, acc[i]);
+    }
+};
+
 // ---- the kernel -----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MM_THREADS, 2)
-sa_mma_kernel(const MmaArgs a) {
+__global__ void __launch_bounds__(MM_THREADS, 3)
+sa_mma_kernel(const __grid_constant__ SaArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    // carve: [barriers 256 B][XA][XB][W stages]
+    // carve: [header: barriers + tmem slot][XA][XB][weights]
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 192);
-    uint8_t *xa = smem + 256;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + MM_HDR - 16);
+    uint8_t *xa = smem + MM_HDR;
     uint8_t *xb = xa + a.xa_bytes;
     uint8_t *wst = xb + a.xb_bytes;
     const uint32_t bar0 = smem_u32(bars);
@@ -215,7 +217,10 @@ sa_mma_kernel(const MmaArgs a) {
     auto W_EMPTY = [&](int s) { return bar0 + 8u * (MM_MAX_STAGES + s); };
     auto ACC_FULL = [&](int i) { return bar0 + 8u * (2 * MM_MAX_STAGES + i); };
     auto ACC_EMPTY = [&](int i) { return bar0 + 8u * (2 * MM_MAX_STAGES + 4 + i); };
-    const uint32_t X_READY = bar0 + 8u * (2 * MM_MAX_STAGES + 8);
+    auto XR = [&](int buf, int c) { return bar0 + 8u * (2 * MM_MAX_STAGES + 8 + buf * MM_MAX_XC + c); };
+    auto WL_FULL = [&](int s) { return bar0 + 8u * (2 * MM_MAX_STAGES + 8 + 2 * MM_MAX_XC + s); };
+    auto WL_EMPTY = [&](int s) { return bar0 + 8u * (3 * MM_MAX_STAGES + 8 + 2 * MM_MAX_XC + s); };
+    const uint32_t HID_DONE = bar0 + 8u * (4 * MM_MAX_STAGES + 8 + 2 * MM_MAX_XC);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -224,213 +229,353 @@ sa_mma_kernel(const MmaArgs a) {
     if (tid == 0) {
         for (int s = 0; s < MM_MAX_STAGES; ++s) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), 1); }
         for (int i = 0; i < 4; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), 128); }
-        mbar_init(X_READY, 128);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int i = 0; i < 2 * MM_MAX_XC; ++i) mbar_init(XR(0, i), 128);
+        for (int s = 0; s < MM_MAX_STAGES; ++s) { mbar_init(WL_FULL(s), 1); mbar_init(WL_EMPTY(s), 1); }
+        mbar_init(HID_DONE, 1);
+        mbar_init_fence();
     }
-    if (warp == 5) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(a.tmem_cols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
+    if (warp == 5) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 4) {
-        // ================= weight producer =================
-        if ((tid & 31) == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-                for (int l = 0; l < nL; ++l) {
-                    const MmaLayer &Ly = a.L[l];
-                    for (int cc = 0; cc < Ly.n_cc; ++cc)
-                        for (int kc = 0; kc < Ly.n_kc; ++kc, ++it) {
-                            const int s = it % a.nstages;
-                            const uint32_t ph = (it / a.nstages) & 1u;
-                            mbar_wait(W_EMPTY(s), ph ^ 1u);
-                            mbar_expect_tx(W_FULL(s), MM_WTILE_BYTES);
-                            const __half *src = a.wtiles + (size_t)(Ly.tile_off + cc * Ly.n_kc + kc) * (MM_WTILE_BYTES / 2);
-                            bulk_g2s(smem_u32(wst + (size_t)s * MM_WTILE_BYTES), src, MM_WTILE_BYTES, W_FULL(s));
-                        }
+        // ================= weight producer (warp-uniform loops, one elected lane issues) =================
+        const bool leader = elect_one();
+        if (a.resident) {
+            // the whole packed chain becomes resident: shared-memory image == global image
+            if (leader) {
+                mbar_expect_tx(W_FULL(0), (uint32_t)a.w_total);
+                for (int off = 0; off < a.w_total; off += MM_STAGE_BYTES) {
+                    const int bytes = min(MM_STAGE_BYTES, a.w_total - off);
+                    bulk_g2s(smem_u32(wst + off), a.wtiles + off, (uint32_t)bytes, W_FULL(0));
                 }
             }
+        } else {
+            Prof pf;
+            pf.init(a.prof != nullptr && leader);
+            uint32_t tcount = 0;
+            int ws = 0, ls = 0;
+            uint32_t wph = 0u, lph = 0u;
+            uint8_t *lst = ((nL - 2) & 1) ? xb : xa;   // overlay slots of the last layer's ring (lstages > 0)
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++tcount) {
+                for (int l = 0; l < nL; ++l) {
+                    const SaLayer &Ly = a.L[l];
+                    const bool lring = a.lstages > 0 && l == nL - 1;
+                    if (lring) { const long long t0 = pf.now(); mbar_wait(HID_DONE, tcount & 1u); pf.add(PF_PROD_HID, t0); }   // the overlaid activation buffer is dead from here on
+                    for (int cc = 0; cc < Ly.n_cc; ++cc) {
+                        const int ncols = min(128, Ly.cpad - cc * 128);
+                        for (int kc = 0; kc < Ly.n_kc; ++kc) {
+                            const int kw = min(64, Ly.vk - kc * 64);
+                            const uint32_t bytes = (uint32_t)(ncols * kw * 2);
+                            const uint8_t *src = a.wtiles + wtile_off(Ly, cc, kc, ncols);
+                            uint32_t full, empty, dst, ph;
+                            if (!lring) {
+                                ph = wph;
+                                full = W_FULL(ws); empty = W_EMPTY(ws); dst = smem_u32(wst + (size_t)ws * MM_STAGE_BYTES);
+                                if (++ws == a.nstages) { ws = 0; wph ^= 1u; }
+                            } else {
+                                ph = lph;
+                                full = WL_FULL(ls); empty = WL_EMPTY(ls); dst = smem_u32(lst + (size_t)ls * MM_STAGE_BYTES);
+                                if (++ls == a.lstages) { ls = 0; lph ^= 1u; }
+                            }
+                            { const long long t0 = pf.now(); mbar_wait(empty, ph ^ 1u); pf.add(PF_PROD_W_EMPTY, t0); }
+                            if (leader) {
+                                mbar_expect_tx(full, bytes);
+                                bulk_g2s(dst, src, bytes, full);
+                            }
+                            __syncwarp();
+                        }
+                    }
+                }
+            }
+            pf.flush(a.prof);
         }
     } else if (warp == 5) {
-        // ================= MMA issuer =================
-        if ((tid & 31) == 0) {
-            uint32_t it = 0, xr = 0;
-            uint32_t af[4] = {0, 0, 0, 0};   // completed uses of ACC_FULL[i]
-            uint32_t bu[4] = {0, 0, 0, 0};   // orientation-B uses of accumulator buffer i
+        // ================= MMA issuer (warp-uniform loops, one elected lane issues) =================
+        {
+            const bool leader = elect_one();
+            Prof pf;
+            pf.init(a.prof != nullptr && leader);
+            const long long t_start = pf.now();
+            uint32_t job = 0;
+            int ws = 0, ls = 0;             // ring positions (hidden / last-layer ring) ...
+            uint32_t wph = 0u, lph = 0u;    // ... and their phase parities
+            uint32_t xph[2] = {0u, 0u};     // phase parity bit per readiness chunk of XA / XB
+            bool first = true;
+            uint8_t *lst = ((nL - 2) & 1) ? xb : xa;
+            const uint32_t nbmask = (uint32_t)a.nbuf - 1u;
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 for (int l = 0; l < nL; ++l) {
-                    const MmaLayer &Ly = a.L[l];
+                    const SaLayer &Ly = a.L[l];
                     const bool last = (l == nL - 1);
-                    const uint32_t xbase = smem_u32((l & 1) ? xb : xa);
-                    const uint32_t x_sbo = (uint32_t)Ly.kpad * 16u;
-                    mbar_wait(X_READY, xr & 1u);
-                    ++xr;
-                    tc_fence_after();
-                    for (int cc = 0; cc < Ly.n_cc; ++cc) {
+                    const bool lring = a.lstages > 0 && last;
+                    const int xbuf = l & 1;
+                    const uint32_t x_lo0 = umma_desc_lo(smem_u32(xbuf ? xb : xa), 128u);
+                    const uint32_t x_hi = umma_desc_hi((uint32_t)Ly.xw * 16u);
+                    const int nk2 = 2 * (Ly.kpad >> 4);   // split: x blocks [0, nk2) are [hi | lo]; v >= nk2 re-reads hi
+                    int xwait = 0;                        // readiness chunks of this layer's input already waited for
+                    for (int cc = 0; cc < Ly.n_cc; ++cc, ++job) {
                         const int ncols = min(128, Ly.cpad - cc * 128);  // couts in this chunk (multiple of 16)
-                        uint32_t d_tmem;
-                        uint32_t idesc;
-                        int buf = 0;
-                        if (!last) {
-                            d_tmem = tmem_base + (uint32_t)(cc * 128);
-                            idesc = umma_idesc(128, ncols);           // M = rows, N = couts
-                        } else {
-                            buf = cc & (a.nbuf - 1);
-                            if (bu[buf] > 0) { mbar_wait(ACC_EMPTY(buf), (bu[buf] - 1) & 1u); tc_fence_after(); }
-                            ++bu[buf];
-                            d_tmem = tmem_base + (uint32_t)(buf * 128);
-                            idesc = umma_idesc(128, MM_ROWS);         // M = couts (tile rows), N = rows
-                        }
-                        for (int kc = 0; kc < Ly.n_kc; ++kc, ++it) {
-                            const int s = it % a.nstages;
-                            const uint32_t ph = (it / a.nstages) & 1u;
-                            mbar_wait(W_FULL(s), ph);
-                            tc_fence_after();
-                            const uint32_t wbase = smem_u32(wst + (size_t)s * MM_WTILE_BYTES);
-                            const int nk16 = min(4, (Ly.kpad - kc * 64) / 16);
-                            for (int j = 0; j < nk16; ++j) {
-                                const uint64_t xd = umma_desc(xbase + (uint32_t)(kc * 4 + j) * 256u, 128u, x_sbo);
-                                const uint64_t wd = umma_desc(wbase + (uint32_t)j * 256u, 128u, 1024u);
-                                const uint32_t acc = (kc | j) ? 1u : 0u;
-                                if (!last) umma_f16(d_tmem, xd, wd, idesc, acc);
-                                else umma_f16(d_tmem, wd, xd, idesc, acc);
+                        const int buf = (int)(job & nbmask);
+                        const uint32_t use = job >> a.nbuf_log2;
+                        if (use > 0) { const long long t0 = pf.now(); mbar_wait(ACC_EMPTY(buf), (use - 1) & 1u); pf.add(PF_MMA_ACC_EMPTY, t0); tc_fence_after(); }
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
+                        const uint32_t idesc = last ? umma_idesc(128, MM_ROWS) : umma_idesc(128, ncols);
+                        for (int kc = 0; kc < Ly.n_kc; ++kc) {
+                            const int kw = min(64, Ly.vk - kc * 64);
+                            uint32_t wbase, wempty = 0u;
+                            if (a.resident) {
+                                if (first) { mbar_wait(W_FULL(0), 0u); first = false; }
+                                wbase = smem_u32(wst + wtile_off(Ly, cc, kc, ncols));
+                            } else if (lring) {
+                                { const long long t0 = pf.now(); mbar_wait(WL_FULL(ls), lph); pf.add(PF_MMA_W_FULL, t0); }
+                                wbase = smem_u32(lst + (size_t)ls * MM_STAGE_BYTES);
+                                wempty = WL_EMPTY(ls);
+                                if (++ls == a.lstages) { ls = 0; lph ^= 1u; }
+                            } else {
+                                { const long long t0 = pf.now(); mbar_wait(W_FULL(ws), wph); pf.add(PF_MMA_W_FULL, t0); }
+                                wbase = smem_u32(wst + (size_t)ws * MM_STAGE_BYTES);
+                                wempty = W_EMPTY(ws);
+                                if (++ws == a.nstages) { ws = 0; wph ^= 1u; }
                             }
-                            umma_commit(W_EMPTY(s));   // stage reusable once these MMAs retire
+                            const int nk16 = kw >> 4;
+                            if (cc == 0) {
+                                // the activation chunks this weight tile touches must have landed (epilogue of layer l-1 / gather)
+                                int need = (kc * 4 + nk16 - 1) >> 2;
+                                if (a.split) need = Ly.n_xc - 1;   // hi | lo | hi re-read: simply wait for the whole (narrow) operand
+                                while (xwait <= need) {
+                                    const long long t0 = pf.now();
+                                    mbar_wait(XR(xbuf, xwait), (xph[xbuf] >> xwait) & 1u);
+                                    pf.add(PF_MMA_XR, t0);
+                                    xph[xbuf] ^= (1u << xwait);
+                                    ++xwait;
+                                }
+                            }
+                            tc_fence_after();
+                            if (leader) {
+                                const uint32_t w_lo = umma_desc_lo(wbase, 128u);
+                                const uint32_t w_hi = umma_desc_hi((uint32_t)kw * 16u);
+                                const uint32_t x_lo = x_lo0 + (uint32_t)kc * 64u;   // 4 K blocks of 256 bytes (>>4: 16 each)
+                                if (nk16 == 4 && !a.split) {
+                                    if (!last) {
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j)
+                                            umma_f16_lohi(d_tmem, x_lo + 16u * j, x_hi, w_lo + 16u * j, w_hi, idesc, (kc | j) ? 1u : 0u);
+                                    } else {
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j)
+                                            umma_f16_lohi(d_tmem, w_lo + 16u * j, w_hi, x_lo + 16u * j, x_hi, idesc, (kc | j) ? 1u : 0u);
+                                    }
+                                } else {
+                                    for (int j = 0; j < nk16; ++j) {
+                                        const int v = kc * 4 + j;
+                                        const int xblk = (a.split && v >= nk2) ? v - nk2 : v;
+                                        const uint32_t xl = x_lo0 + 16u * (uint32_t)xblk, wl = w_lo + 16u * (uint32_t)j;
+                                        if (!last) umma_f16_lohi(d_tmem, xl, x_hi, wl, w_hi, idesc, v ? 1u : 0u);
+                                        else umma_f16_lohi(d_tmem, wl, w_hi, xl, x_hi, idesc, v ? 1u : 0u);
+                                    }
+                                }
+                                if (!a.resident) umma_commit(wempty);   // stage reusable once these MMAs retire
+                                if (kc == Ly.n_kc - 1) {
+                                    umma_commit(ACC_FULL(buf));
+                                    if (a.lstages > 0 && l == nL - 2 && cc == Ly.n_cc - 1) umma_commit(HID_DONE);   // its input buffer may now hold weight tiles
+                                }
+                            }
+                            __syncwarp();
                         }
-                        if (last) { umma_commit(ACC_FULL(buf)); ++af[buf]; }
                     }
-                    if (!last) { umma_commit(ACC_FULL(0)); ++af[0]; }
                 }
             }
-            (void)af;
+            pf.add(PF_MMA_TOTAL, t_start);
+            pf.flush(a.prof);
         }
     } else {
         // ================= gather + epilogue (threads 0..127; thread = row / TMEM lane) =================
-        uint32_t af[4] = {0, 0, 0, 0};
+        Prof pf;
+        pf.init(a.prof != nullptr && tid == 0);
+        const long long t_start = pf.now();
+        uint32_t job = 0;
         const uint32_t lane_field = (uint32_t)(warp * 32) << 16;
         const int r = tid;
-        const uint32_t row_off = (uint32_t)(r >> 3) * 0u;  // placeholder to keep the formula visible below
-        (void)row_off;
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-            // ---- gather X0 (into XA): [features | dxyz | 0]
+        const uint32_t row_off = (uint32_t)(r & 7) * 16u;
+        const int first_tile = blockIdx.x;
+        int jn = 0;   // neighbour index of this thread's row in the NEXT tile (prefetched one tile ahead)
+        if (first_tile < a.ntiles) {
+            const long long grow = (long long)first_tile * MM_ROWS + r;
+            if (grow < a.rows) jn = __ldg(a.idx + grow);
+        }
+        for (int tile = first_tile; tile < a.ntiles; tile += gridDim.x) {
+            // ---- gather X0 (into XA): [features | dxyz | 0]   (split: [hi(k0) | lo(k0)])
+            const long long t_g = pf.now();
             {
-                const MmaLayer &L0 = a.L[0];
-                const uint32_t sbo = (uint32_t)L0.kpad * 16u;
-                uint8_t *xrow = xa + (size_t)(r >> 3) * sbo + (size_t)(r & 7) * 16;
+                const SaLayer &L0 = a.L[0];
+                const uint32_t sbo = (uint32_t)L0.xw * 16u;
+                uint8_t *xrow = xa + (size_t)(r >> 3) * sbo + row_off;
                 const long long grow = (long long)tile * MM_ROWS + r;
                 const bool ok = grow < a.rows;
-                int j = 0;
+                const int j = jn;
+                {
+                    const long long gnext = grow + (long long)gridDim.x * MM_ROWS;
+                    if (gnext < a.rows) jn = __ldg(a.idx + gnext);
+                }
                 long long q = 0;
                 int bb = 0;
-                if (ok) {
-                    q = grow >> a.ns_log2;
-                    bb = (int)(q / a.m);
-                    j = __ldg(a.idx + grow);
+                if (ok) { q = grow >> a.ns_log2; bb = (int)(q / a.m); }
+                float dx = 0.f, dy = 0.f, dz = 0.f;
+                if (a.use_xyz && ok) {
+                    const float *p = a.xyz + ((size_t)bb * a.n + j) * 3;
+                    const float *ctr = a.new_xyz + (size_t)q * 3;
+                    dx = __fsub_rn(__ldg(p), __ldg(ctr));
+                    dy = __fsub_rn(__ldg(p + 1), __ldg(ctr + 1));
+                    dz = __fsub_rn(__ldg(p + 2), __ldg(ctr + 2));
                 }
-                const int nch = a.k0pad >> 3;
-                const int fch = a.cpad8 >> 3;
                 const uint4 zero = make_uint4(0, 0, 0, 0);
-                const uint4 *trow = ok && fch ? reinterpret_cast<const uint4 *>(a.twin + ((size_t)bb * a.n + j) * a.cpad8) : nullptr;
-                for (int c = 0; c < fch; ++c) {
-                    const uint4 v = ok ? __ldg(trow + c) : zero;
-                    *reinterpret_cast<uint4 *>(xrow + (size_t)c * 128) = v;
-                }
-                int c = fch;
-                if (a.use_xyz) {
-                    uint4 v = zero;
-                    if (ok) {
-                        const float *p = a.xyz + ((size_t)bb * a.n + j) * 3;
-                        const float *ctr = a.new_xyz + (size_t)q * 3;
-                        const float dx = __fsub_rn(__ldg(p), __ldg(ctr));
-                        const float dy = __fsub_rn(__ldg(p + 1), __ldg(ctr + 1));
-                        const float dz = __fsub_rn(__ldg(p + 2), __ldg(ctr + 2));
-                        v.x = pack_h2(dx, dy);
-                        v.y = pack_h2(dz, 0.f);
+                if (!a.split) {
+                    const int nch = L0.kpad >> 3;
+                    const int fch = a.cpad8 >> 3;
+                    const uint4 *trow = (ok && fch) ? reinterpret_cast<const uint4 *>(a.twin + ((size_t)bb * a.n + j) * a.ldtwin) : nullptr;
+                    int c = 0;
+                    for (; c + 8 <= fch; c += 8) {   // 8 independent 16-byte loads in flight
+                        uint4 t[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) t[u] = ok ? __ldg(trow + c + u) : zero;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) *reinterpret_cast<uint4 *>(xrow + (size_t)(c + u) * 128) = t[u];
                     }
-                    *reinterpret_cast<uint4 *>(xrow + (size_t)c * 128) = v;
-                    ++c;
+                    for (; c < fch; ++c) *reinterpret_cast<uint4 *>(xrow + (size_t)c * 128) = ok ? __ldg(trow + c) : zero;
+                    if (a.use_xyz) {
+                        *reinterpret_cast<uint4 *>(xrow + (size_t)c * 128) = make_uint4(pack_h2(dx, dy), pack_h2(dz, 0.f), 0u, 0u);
+                        ++c;
+                    }
+                    for (; c < nch; ++c) *reinterpret_cast<uint4 *>(xrow + (size_t)c * 128) = zero;
+                } else {
+                    // exact inputs: features from the fp32 channel-major tensor (c_feat <= 8), k order [f0..f7 | x y z 0..]
+                    float y[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) y[i] = 0.f;
+                    if (ok) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            if (c < a.c_feat) y[c] = __ldg(a.feat32 + ((size_t)bb * a.c_feat + c) * a.n + j);
+                    }
+                    if (a.c_feat) { y[8] = dx; y[9] = dy; y[10] = dz; }
+                    else { y[0] = dx; y[1] = dy; y[2] = dz; }
+                    const int nch = L0.kpad >> 3;   // 1 or 2 groups of 8
+                    uint8_t *xlo = xrow + (size_t)nch * 128;
+                    uint4 hi, lo;
+                    split8(y, hi, lo);
+                    *reinterpret_cast<uint4 *>(xrow) = hi;
+                    *reinterpret_cast<uint4 *>(xlo) = lo;
+                    if (nch > 1) {
+                        split8(y + 8, hi, lo);
+                        *reinterpret_cast<uint4 *>(xrow + 128) = hi;
+                        *reinterpret_cast<uint4 *>(xlo + 128) = lo;
+                    }
                 }
-                for (; c < nch; ++c) *reinterpret_cast<uint4 *>(xrow + (size_t)c * 128) = zero;
                 fence_proxy_async();
-                mbar_arrive(X_READY);
+                for (int c = 0; c < L0.n_xc; ++c) mbar_arrive(XR(0, c));
             }
-            // ---- hidden layers: D[row, cout] -> relu(D + bias) -> fp16 -> next X
+            pf.add(PF_EPI_GATHER, t_g);
+            // ---- hidden layers: D[row, cout] -> relu(D + bias) -> fp16 -> next X, chunk by chunk
             for (int l = 0; l < nL - 1; ++l) {
-                const MmaLayer &Ly = a.L[l];
-                uint8_t *xo = ((l + 1) & 1) ? xb : xa;
-                const uint32_t sbo = (uint32_t)a.L[l + 1].kpad * 16u;
-                uint8_t *xrow = xo + (size_t)(r >> 3) * sbo + (size_t)(r & 7) * 16;
-                mbar_wait(ACC_FULL(0), af[0] & 1u);
-                ++af[0];
-                tc_fence_after();
+                const SaLayer &Ly = a.L[l];
+                const SaLayer &Ln = a.L[l + 1];
+                const int obuf = (l + 1) & 1;
+                uint8_t *xo = obuf ? xb : xa;
+                const uint32_t sbo = (uint32_t)Ln.xw * 16u;
+                uint8_t *xrow = xo + (size_t)(r >> 3) * sbo + row_off;
                 const float *bias = a.bias + Ly.bias_off;
-                int c0 = 0;
-                for (; c0 + 32 <= Ly.cpad; c0 += 32) {
-                    float v[32];
-                    tmem_ld32(tmem_base + lane_field + (uint32_t)c0, v);
-                    store_hidden16(v, bias + c0, xrow + (size_t)(c0 >> 3) * 128);
-                    store_hidden16(v + 16, bias + c0 + 16, xrow + (size_t)((c0 >> 3) + 2) * 128);
+                for (int cc = 0; cc < Ly.n_cc; ++cc, ++job) {
+                    const int ncols = min(128, Ly.cpad - cc * 128);
+                    const int buf = (int)(job & ((uint32_t)a.nbuf - 1u));
+                    { const long long t0 = pf.now(); mbar_wait(ACC_FULL(buf), (job >> a.nbuf_log2) & 1u); pf.add(PF_EPI_WAIT_HID, t0); }
+                    tc_fence_after();
+                    const long long t_w = pf.now();
+                    const uint32_t taddr = tmem_base + lane_field + (uint32_t)(buf * 128);
+                    if (!a.split) {
+                        for (int h0 = 0; h0 < ncols; h0 += 64) {   // one 64-wide K chunk of the next operand at a time
+                            const int hend = min(ncols, h0 + 64);
+                            int c0 = h0;
+                            for (; c0 + 32 <= hend; c0 += 32) {
+                                float v[32];
+                                tmem_ld32(taddr + (uint32_t)c0, v);
+                                const int col = cc * 128 + c0;
+                                store_hidden16(v, bias + col, xrow + (size_t)(col >> 3) * 128);
+                                store_hidden16(v + 16, bias + col + 16, xrow + (size_t)((col >> 3) + 2) * 128);
+                            }
+                            if (c0 < hend) {
+                                float v[16];
+                                tmem_ld16(taddr + (uint32_t)c0, v);
+                                const int col = cc * 128 + c0;
+                                store_hidden16(v, bias + col, xrow + (size_t)(col >> 3) * 128);
+                            }
+                            fence_proxy_async();
+                            mbar_arrive(XR(obuf, (cc * 128 + h0) >> 6));
+                        }
+                    } else {
+                        uint8_t *xlo = xrow + (size_t)(Ln.kpad >> 3) * 128;
+                        for (int c0 = 0; c0 < ncols; c0 += 16) {
+                            float v[16];
+                            tmem_ld16(taddr + (uint32_t)c0, v);
+                            store_hidden16_split(v, bias + c0, xrow + (size_t)(c0 >> 3) * 128, xlo + (size_t)(c0 >> 3) * 128);
+                        }
+                        fence_proxy_async();
+                        for (int c = 0; c < Ln.n_xc; ++c) mbar_arrive(XR(obuf, c));
+                    }
+                    tc_fence_before();
+                    mbar_arrive(ACC_EMPTY(buf));
+                    pf.add(PF_EPI_WORK_HID, t_w);
                 }
-                if (c0 < Ly.cpad) {
-                    float v[16];
-                    tmem_ld16(tmem_base + lane_field + (uint32_t)c0, v);
-                    store_hidden16(v, bias + c0, xrow + (size_t)(c0 >> 3) * 128);
-                }
-                // zero the K padding of the next layer's operand (kpad_{l+1} == cpad_l by construction, so none)
-                tc_fence_before();
-                fence_proxy_async();
-                mbar_arrive(X_READY);
             }
             // ---- last layer: D[cout, row]; thread = cout; max over each centre's nsample columns
             {
-                const MmaLayer &Ly = a.L[nL - 1];
+                const SaLayer &Ly = a.L[nL - 1];
                 const float *bias = a.bias + Ly.bias_off;
                 const long long q0 = ((long long)tile * MM_ROWS) >> a.ns_log2;  // first centre of the tile
                 const long long qmax = (long long)a.b * a.m;
                 const int ns = a.nsample;
                 const long long bb0 = q0 / a.m;
                 const int p0 = (int)(q0 - bb0 * a.m);
-                for (int cc = 0; cc < Ly.n_cc; ++cc) {
-                    const int buf = cc & (a.nbuf - 1);
-                    mbar_wait(ACC_FULL(buf), af[buf] & 1u);
-                    ++af[buf];
+                const size_t sstride = (size_t)a.c_total * a.m;
+                for (int cc = 0; cc < Ly.n_cc; ++cc, ++job) {
+                    const int buf = (int)(job & ((uint32_t)a.nbuf - 1u));
+                    { const long long t0 = pf.now(); mbar_wait(ACC_FULL(buf), (job >> a.nbuf_log2) & 1u); pf.add(PF_EPI_WAIT_POOL, t0); }
                     tc_fence_after();
+                    const long long t_w = pf.now();
                     const int ch = cc * 128 + r;
-                    const bool ch_ok = ch < a.cout_last;
-                    const float bv = ch_ok ? __ldg(bias + ch) : 0.f;
-                    float *outc = a.out + ((size_t)bb0 * a.c_total + a.co_off + (ch_ok ? ch : 0)) * a.m + (size_t)p0;
-                    const size_t sstride = (size_t)a.c_total * a.m;
+                    const bool w32 = a.out != nullptr && ch < a.cout_last;
+                    const bool w16 = a.out16 != nullptr && ch < a.n16;
+                    const float bv = __ldg(bias + ch);   // bias is padded to cpad
+                    PoolOut o;
+                    o.bv = bv; o.w32 = w32; o.w16 = w16;
+                    o.outc = a.out + ((size_t)bb0 * a.c_total + a.co_off + (w32 ? ch : 0)) * a.m + (size_t)p0;
+                    o.out16 = a.out16 + (size_t)q0 * a.ld16 + a.co16 + (w16 ? ch : 0);
+                    o.ld16 = a.ld16; o.o16lo = a.o16lo; o.q = q0; o.qmax = qmax; o.m = a.m; o.p = p0; o.scene_stride = sstride;
                     const uint32_t taddr = tmem_base + lane_field + (uint32_t)(buf * 128);
-                    switch (ns) {
-                        case 1: pool_chunk<1>(taddr, bv, ch_ok, outc, q0, qmax, a.m, sstride, p0); break;
-                        case 2: pool_chunk<2>(taddr, bv, ch_ok, outc, q0, qmax, a.m, sstride, p0); break;
-                        case 4: pool_chunk<4>(taddr, bv, ch_ok, outc, q0, qmax, a.m, sstride, p0); break;
-                        case 8: pool_chunk<8>(taddr, bv, ch_ok, outc, q0, qmax, a.m, sstride, p0); break;
-                        case 16: pool_chunk<16>(taddr, bv, ch_ok, outc, q0, qmax, a.m, sstride, p0); break;
-                        case 32: pool_chunk<32>(taddr, bv, ch_ok, outc, q0, qmax, a.m, sstride, p0); break;
-                        case 64: pool_chunk<64>(taddr, bv, ch_ok, outc, q0, qmax, a.m, sstride, p0); break;
-                        default: pool_chunk<128>(taddr, bv, ch_ok, outc, q0, qmax, a.m, sstride, p0); break;
-                    }
+                    if (ns == 32) pool_chunk<32>(taddr, o);
+                    else if (ns == 16) pool_chunk<16>(taddr, o);
+                    else pool_chunk_any(taddr, o, ns);
                     tc_fence_before();
                     mbar_arrive(ACC_EMPTY(buf));
+                    pf.add(PF_EPI_WORK_POOL, t_w);
                 }
             }
         }
+        pf.add(PF_EPI_TOTAL, t_start);
+        pf.flush(a.prof);
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 5) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols));
+        tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
     }
 }
 
-// ---- feature twin: (b, c, n) f32 channel-major -> (b, n, cpad8) fp16 point-major (zero padded) -------------
+// ---- feature twin: (b, c, n) f32 channel-major -> (b, n, ld) fp16 point-major (zero padded) -------------
 __global__ void __launch_bounds__(256)
 make_twin_kernel(int c, int n, int cpad8, const float *__restrict__ in, __half *__restrict__ out) {
     __shared__ float tile[32][33];
@@ -448,6 +593,80 @@ make_twin_kernel(int c, int n, int cpad8, const float *__restrict__ in, __half *
     }
 }
 
+static unsigned long long *g_sa_prof = nullptr;
+
+// ---- host-side planning ---------------------------------------------------------------------------------
+struct SaPlan {
+    SaLayer L[MM_MAX_LAYERS];
+    int xa_bytes, xb_bytes, w_total, resident, nstages, lstages, ctas, tmem_cols, nbuf, smem;
+};
+
+static int sa_plan(const spsk_sa_mma_desc *d, SaPlan *P) {
+    const int nL = d->nlayers;
+    SPSK_REQUIRE(nL >= 1 && nL <= MM_MAX_LAYERS, SPSK_ERR_UNSUPPORTED, "sa_mma: nlayers=%d (1..%d)", nL, MM_MAX_LAYERS);
+    const int split = d->split ? 1 : 0;
+    int w_off = 0, b_off = 0;
+    P->xa_bytes = P->xb_bytes = 0;
+    for (int l = 0; l < nL; ++l) {
+        const bool last = l == nL - 1;
+        const int kpad = d->kpad[l], cpad = d->cpad[l];
+        SPSK_REQUIRE(kpad >= 16 && kpad % 16 == 0 && kpad <= 1024, SPSK_ERR_UNSUPPORTED, "sa_mma: layer %d kpad=%d", l, kpad);
+        SPSK_REQUIRE(cpad >= 16 && cpad % (last ? 128 : 16) == 0 && cpad <= (last ? 4096 : 1024), SPSK_ERR_UNSUPPORTED,
+                     "sa_mma: layer %d cpad=%d", l, cpad);
+        SPSK_REQUIRE(last || cpad == d->kpad[l + 1], SPSK_ERR_INVALID_ARG, "sa_mma: layer %d cpad != next kpad", l);
+        SPSK_REQUIRE(!split || (kpad <= 64 && (last || cpad <= 64)), SPSK_ERR_UNSUPPORTED, "sa_mma: split arithmetic needs every width <= 64");
+        SaLayer &Ly = P->L[l];
+        Ly.kpad = kpad; Ly.cpad = cpad;
+        Ly.n_cc = (cpad + 127) / 128;
+        Ly.xw = split ? 2 * kpad : kpad;
+        Ly.vk = split ? 3 * kpad : kpad;
+        Ly.n_kc = (Ly.vk + 63) / 64;
+        Ly.n_xc = (Ly.xw + 63) / 64;
+        Ly.w_off = w_off; Ly.bias_off = b_off;
+        w_off += Ly.vk * cpad * 2;
+        b_off += cpad;
+        const int xbytes = Ly.xw * MM_ROWS * 2;
+        if (l & 1) P->xb_bytes = max(P->xb_bytes, xbytes); else P->xa_bytes = max(P->xa_bytes, xbytes);
+    }
+    P->w_total = w_off;
+    const int xtot = MM_HDR + P->xa_bytes + P->xb_bytes;
+    const int sm_bytes = 228 * 1024;   // per SM; every resident CTA also reserves 1 KB
+    // CTAs per SM: as many (<= 3) as shared memory allows with the chain resident or >= 2 ring stages; the TMEM
+    // share (512 / ctas rounded down to a power of two) must hold at least one 128-column accumulator
+    auto fits = [&](int ctas, int *resident, int *nstages, int *smem) {
+        const int per = (sm_bytes / ctas - 1024) & ~127;
+        if (xtot + P->w_total <= per) { *resident = 1; *nstages = 1; *smem = xtot + P->w_total; return true; }
+        const int st = (per - xtot) / MM_STAGE_BYTES;
+        if (st < 2) return false;
+        *resident = 0; *nstages = st > MM_MAX_STAGES ? MM_MAX_STAGES : st; *smem = xtot + *nstages * MM_STAGE_BYTES;
+        return true;
+    };
+    int ctas = 0, cmax = 3;
+    if (const char *e = getenv("SPSK_SA_MAX_CTAS")) cmax = max(1, min(3, atoi(e)));   // tuning / A-B measurements
+    for (int c = cmax; c >= 1; --c) {
+        int res, st, sm;
+        if (!fits(c, &res, &st, &sm)) continue;
+        ctas = c; P->resident = res; P->nstages = st; P->smem = sm;
+        break;
+    }
+    SPSK_REQUIRE(ctas >= 1, SPSK_ERR_UNSUPPORTED, "sa_mma: activation tiles do not fit shared memory (layer widths too large)");
+    P->ctas = ctas;
+    // a starved ring (big activations leave < 4 stages): give the last layer -- most of the chain's weight bytes -- its own
+    // ring overlaid on the activation buffer that is dead while it runs
+    P->lstages = 0;
+    if (!P->resident && P->nstages < 4 && nL >= 2 && !getenv("SPSK_SA_NO_LRING")) {
+        const int other = ((nL - 2) & 1) ? P->xb_bytes : P->xa_bytes;
+        const int e = other / MM_STAGE_BYTES;
+        if (e >= 3) P->lstages = e > MM_MAX_STAGES ? MM_MAX_STAGES : e;
+    }
+    P->tmem_cols = ctas == 1 ? 512 : (ctas == 2 ? 256 : 128);
+    P->nbuf = P->tmem_cols / 128;
+    // shared-memory floor so that no more than `ctas` CTAs land on an SM (their TMEM allocations would not fit)
+    const int floor_bytes = (sm_bytes / (ctas + 1) - 1024 + 256) & ~127;
+    if (P->smem < floor_bytes) P->smem = floor_bytes;
+    return SPSK_OK;
+}
+
 }  // namespace spsk
 
 extern "C" int spsk_make_twin(int b, int c, int n, int cpad8, const float *features, void *twin, spsk_stream_t stream) {
@@ -462,105 +681,86 @@ extern "C" int spsk_make_twin(int b, int c, int n, int cpad8, const float *featu
     return SPSK_OK;
 }
 
-extern "C" int spsk_sa_mma_smem_bytes(int nlayers, const int *kpad, const int *cpad, int *nstages_out) {
-    // X ping-pong buffers + as many 16 KB weight stages as fit (2..6) + 256 B of barriers
-    using namespace spsk;
-    if (nlayers < 1 || nlayers > MM_MAX_LAYERS) return -1;
-    int xa = 0, xbv = 0;
-    for (int l = 0; l < nlayers; ++l) {
-        const int bytes = kpad[l] * MM_ROWS * 2;
-        if (l & 1) xbv = max(xbv, bytes); else xa = max(xa, bytes);
-    }
-    const int budget = 227 * 1024;
-    int stages = (budget - 256 - xa - xbv) / MM_WTILE_BYTES;
-    if (stages > MM_MAX_STAGES) stages = MM_MAX_STAGES;
-    if (stages < 2) return -1;
-    if (nstages_out) *nstages_out = stages;
-    int total = 256 + xa + xbv + stages * MM_WTILE_BYTES;
-    // TMEM: 256 columns per CTA when every hidden accumulator fits (two CTAs can then share an SM and overlap one
-    // tile's gather / epilogue with the other's MMAs); the shared-memory floors keep the CTA count per SM within
-    // the TMEM budget (3 x 76 KB and 2 x 120 KB both exceed 227 KB).
-    int hidden_max = 0;
-    for (int l = 0; l + 1 < nlayers; ++l) hidden_max = max(hidden_max, cpad[l]);
-    const bool two = hidden_max <= 256 && (256 + xa + xbv + 2 * MM_WTILE_BYTES) <= 112 * 1024;
-    if (two) {
-        stages = (112 * 1024 - 256 - xa - xbv) / MM_WTILE_BYTES;
-        if (stages > MM_MAX_STAGES) stages = MM_MAX_STAGES;
-        if (nstages_out) *nstages_out = stages;
-        total = 256 + xa + xbv + stages * MM_WTILE_BYTES;
-        if (total < 76 * 1024) total = 76 * 1024;
-        return -total;  // negative: "two CTAs per SM" variant (256 TMEM columns)
-    }
-    if (total < 120 * 1024) total = 120 * 1024;
-    return total;
+extern "C" int spsk_sa_mma_set_profile(unsigned long long *counters) {
+    spsk::g_sa_prof = counters;
+    return SPSK_OK;
 }
 
-extern "C" int spsk_sa_mma_forward(const spsk_group_desc *g, int cpad8, const void *twin, int nlayers, const int *kpad,
-                                   const int *cpad, const int *tile_off, const int *bias_off, const void *wtiles,
-                                   const float *bias, int cout_last, float *out_pooled, int c_total, int co_off,
-                                   spsk_stream_t stream) {
+extern "C" int spsk_sa_mma_config(const spsk_sa_mma_desc *d, int *smem_bytes, int *ctas_per_sm, int *nstages, int *resident) {
     using namespace spsk;
-    SPSK_REQUIRE(g && kpad && cpad && tile_off && bias_off && wtiles && bias && out_pooled, SPSK_ERR_INVALID_ARG, "sa_mma: null pointer");
-    SPSK_REQUIRE(nlayers >= 1 && nlayers <= MM_MAX_LAYERS, SPSK_ERR_UNSUPPORTED, "sa_mma: nlayers=%d (1..%d)", nlayers, MM_MAX_LAYERS);
-    SPSK_REQUIRE(g->nsample >= 1 && g->nsample <= MM_ROWS && (g->nsample & (g->nsample - 1)) == 0, SPSK_ERR_UNSUPPORTED,
-                 "sa_mma: nsample=%d must be a power of two <= %d", g->nsample, MM_ROWS);
-    SPSK_REQUIRE(g->idx && g->xyz && g->new_xyz && (cpad8 == 0 || twin), SPSK_ERR_INVALID_ARG, "sa_mma: null gather source");
-    SPSK_REQUIRE(cpad8 % 8 == 0 && cpad8 >= 0, SPSK_ERR_INVALID_ARG, "sa_mma: cpad8=%d", cpad8);
-    MmaArgs a{};
-    a.nlayers = nlayers;
-    for (int l = 0; l < nlayers; ++l) {
-        const bool last = l == nlayers - 1;
-        SPSK_REQUIRE(kpad[l] >= 16 && kpad[l] % 16 == 0 && kpad[l] <= 1024, SPSK_ERR_UNSUPPORTED, "sa_mma: layer %d kpad=%d", l, kpad[l]);
-        SPSK_REQUIRE(cpad[l] >= 16 && cpad[l] % (last ? 128 : 16) == 0 && cpad[l] <= (last ? 4096 : 512), SPSK_ERR_UNSUPPORTED,
-                     "sa_mma: layer %d cpad=%d", l, cpad[l]);
-        SPSK_REQUIRE(last || cpad[l] == kpad[l + 1], SPSK_ERR_INVALID_ARG, "sa_mma: layer %d cpad != next kpad", l);
-        a.L[l].kpad = kpad[l];
-        a.L[l].cpad = cpad[l];
-        a.L[l].n_cc = (cpad[l] + 127) / 128;
-        a.L[l].n_kc = (kpad[l] + 63) / 64;
-        a.L[l].tile_off = tile_off[l];
-        a.L[l].bias_off = bias_off[l];
-    }
-    a.b = g->b; a.n = g->n; a.m = g->m; a.nsample = g->nsample;
+    SPSK_REQUIRE(d, SPSK_ERR_INVALID_ARG, "sa_mma: null descriptor");
+    SaPlan P;
+    if (int rc = sa_plan(d, &P)) return rc;
+    if (smem_bytes) *smem_bytes = P.smem;
+    if (ctas_per_sm) *ctas_per_sm = P.ctas;
+    if (nstages) *nstages = P.nstages;
+    if (resident) *resident = P.resident;
+    return SPSK_OK;
+}
+
+extern "C" int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stream) {
+    using namespace spsk;
+    SPSK_REQUIRE(d, SPSK_ERR_INVALID_ARG, "sa_mma: null descriptor");
+    SPSK_REQUIRE(d->wtiles && d->bias && (d->out_cm || d->out16), SPSK_ERR_INVALID_ARG, "sa_mma: null weights / no output");
+    SPSK_REQUIRE(d->nsample >= 1 && d->nsample <= MM_ROWS && (d->nsample & (d->nsample - 1)) == 0, SPSK_ERR_UNSUPPORTED,
+                 "sa_mma: nsample=%d must be a power of two <= %d", d->nsample, MM_ROWS);
+    SPSK_REQUIRE(d->b >= 0 && d->n >= 1 && d->m >= 0 && d->c_feat >= 0, SPSK_ERR_INVALID_ARG, "sa_mma: bad sizes");
+    SPSK_REQUIRE(d->idx && d->xyz && d->new_xyz, SPSK_ERR_INVALID_ARG, "sa_mma: null gather source");
+    SaPlan P;
+    if (int rc = sa_plan(d, &P)) return rc;
+    SaArgs a{};
+    a.nlayers = d->nlayers;
+    for (int l = 0; l < d->nlayers; ++l) a.L[l] = P.L[l];
+    a.b = d->b; a.n = d->n; a.m = d->m; a.nsample = d->nsample;
     a.ns_log2 = 0;
-    while ((1 << a.ns_log2) < g->nsample) ++a.ns_log2;
-    a.cpad8 = cpad8;
-    a.use_xyz = g->use_xyz ? 1 : 0;
-    a.k0pad = kpad[0];
-    SPSK_REQUIRE(a.k0pad >= cpad8 + (a.use_xyz ? 8 : 0), SPSK_ERR_INVALID_ARG, "sa_mma: kpad[0]=%d too small for %d feature + xyz channels", a.k0pad, cpad8);
-    a.rows = (long long)g->b * g->m * g->nsample;
+    while ((1 << a.ns_log2) < d->nsample) ++a.ns_log2;
+    a.c_feat = d->c_feat;
+    a.use_xyz = d->use_xyz ? 1 : 0;
+    a.split = d->split ? 1 : 0;
+    if (a.split) {
+        SPSK_REQUIRE(d->c_feat <= 8 && (d->c_feat == 0 || d->features), SPSK_ERR_UNSUPPORTED, "sa_mma: split arithmetic takes <= 8 fp32 feature channels");
+        SPSK_REQUIRE(d->kpad[0] == 16, SPSK_ERR_INVALID_ARG, "sa_mma: split kpad[0]=%d must be 16 ([f0..f7 | x y z 0..])", d->kpad[0]);
+        a.feat32 = d->features;
+        a.cpad8 = d->c_feat ? 8 : 0;
+    } else {
+        a.cpad8 = (d->c_feat + 7) / 8 * 8;
+        SPSK_REQUIRE(d->c_feat == 0 || (d->twin && d->ldtwin >= a.cpad8 && d->ldtwin % 8 == 0 && (reinterpret_cast<uintptr_t>(d->twin) & 15) == 0),
+                     SPSK_ERR_INVALID_ARG, "sa_mma: twin must be a 16-byte aligned (b, n, ldtwin) fp16 tensor with ldtwin %% 8 == 0 and >= c_feat");
+        SPSK_REQUIRE(d->kpad[0] >= a.cpad8 + (a.use_xyz ? 8 : 0), SPSK_ERR_INVALID_ARG, "sa_mma: kpad[0]=%d too small for %d feature + xyz channels",
+                     d->kpad[0], a.cpad8);
+        a.twin = reinterpret_cast<const __half *>(d->twin);
+        a.ldtwin = d->ldtwin;
+    }
+    a.rows = (long long)d->b * d->m * d->nsample;
     if (a.rows == 0) return SPSK_OK;
     const long long ntiles = (a.rows + MM_ROWS - 1) / MM_ROWS;
     SPSK_REQUIRE(ntiles <= 0x7FFFFFFF, SPSK_ERR_UNSUPPORTED, "sa_mma: too many rows");
     a.ntiles = (int)ntiles;
-    int nstages = 0;
-    int smem = spsk_sa_mma_smem_bytes(nlayers, kpad, cpad, &nstages);
-    SPSK_REQUIRE(smem != -1, SPSK_ERR_UNSUPPORTED, "sa_mma: activation tiles do not fit shared memory (max layer width too large)");
-    const bool two_per_sm = smem < 0;
-    if (two_per_sm) smem = -smem;
-    a.nstages = nstages;
-    a.tmem_cols = two_per_sm ? 256 : 512;
-    a.nbuf = a.tmem_cols / 128;
-    a.xa_bytes = 0; a.xb_bytes = 0;
-    for (int l = 0; l < nlayers; ++l) {
-        const int bytes = kpad[l] * MM_ROWS * 2;
-        if (l & 1) a.xb_bytes = max(a.xb_bytes, bytes); else a.xa_bytes = max(a.xa_bytes, bytes);
-    }
-    a.xyz = g->xyz; a.new_xyz = g->new_xyz; a.twin = reinterpret_cast<const __half *>(twin); a.idx = g->idx;
-    a.wtiles = reinterpret_cast<const __half *>(wtiles); a.bias = bias;
-    a.out = out_pooled; a.c_total = c_total; a.co_off = co_off; a.cout_last = cout_last;
-    SPSK_REQUIRE(co_off >= 0 && co_off + cout_last <= c_total, SPSK_ERR_INVALID_ARG, "sa_mma: channel window outside c_total");
-    static int attr_set_for = 0;
-    if (smem > attr_set_for) {
-        cudaError_t e = cudaFuncSetAttribute(sa_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(sa_mma_kernel)");
-        attr_set_for = 227 * 1024;
-    }
-    // a few CTAs per SM slot (static tile striding): when another stream's kernels hold some SMs, late CTAs start
+    a.lstages = P.lstages;
+    a.nstages = P.nstages; a.resident = P.resident; a.w_total = P.w_total; a.tmem_cols = P.tmem_cols; a.nbuf = P.nbuf;
+    a.nbuf_log2 = P.nbuf == 4 ? 2 : (P.nbuf == 2 ? 1 : 0);
+    a.xa_bytes = P.xa_bytes; a.xb_bytes = P.xb_bytes;
+    a.xyz = d->xyz; a.new_xyz = d->new_xyz; a.idx = d->idx;
+    a.wtiles = reinterpret_cast<const uint8_t *>(d->wtiles); a.bias = d->bias;
+    SPSK_REQUIRE((reinterpret_cast<uintptr_t>(d->wtiles) & 15) == 0, SPSK_ERR_INVALID_ARG, "sa_mma: wtiles must be 16-byte aligned");
+    a.cout_last = d->cout_last;
+    SPSK_REQUIRE(d->cout_last >= 1 && d->cout_last <= d->cpad[d->nlayers - 1], SPSK_ERR_INVALID_ARG, "sa_mma: cout_last outside the last layer");
+    a.out = d->out_cm; a.c_total = d->c_total; a.co_off = d->co_off;
+    if (a.out) SPSK_REQUIRE(d->co_off >= 0 && d->co_off + d->cout_last <= d->c_total, SPSK_ERR_INVALID_ARG, "sa_mma: channel window outside c_total");
+    a.out16 = reinterpret_cast<__half *>(d->out16); a.ld16 = d->ld16; a.co16 = d->co16; a.n16 = d->n16; a.o16lo = d->o16lo;
+    if (a.out16 && d->o16lo)
+        SPSK_REQUIRE(d->o16lo > 0 && d->o16lo + d->co16 + d->n16 <= d->ld16, SPSK_ERR_INVALID_ARG, "sa_mma: residual columns outside ld16");
+    if (a.out16)
+        SPSK_REQUIRE(d->n16 >= d->cout_last && d->n16 <= d->cpad[d->nlayers - 1] && d->co16 >= 0 && d->co16 + d->n16 <= d->ld16, SPSK_ERR_INVALID_ARG,
+                     "sa_mma: fp16 output window [co16, co16 + n16) outside ld16 or wider than the last layer");
+    a.prof = g_sa_prof;
+    static SmemAttrOnce attr;
+    if (int rc = attr.ensure(reinterpret_cast<const void *>(sa_mma_kernel), 227 * 1024, "sa_mma_kernel")) return rc;
+    // two CTAs per SM slot (static tile striding): when another stream's kernels hold some SMs, late CTAs start
     // as soon as any SM frees up instead of doubling the kernel's duration
-    const int slots = SPSK_NUM_SMS * (two_per_sm ? 2 : 1) * 2;
+    const int slots = SPSK_NUM_SMS * P.ctas * 2;
     const int grid = a.ntiles < slots ? a.ntiles : slots;
-    sa_mma_kernel<<<grid, MM_THREADS, smem, as_stream(stream)>>>(a);
+    sa_mma_kernel<<<grid, MM_THREADS, P.smem, as_stream(stream)>>>(a);
     SPSK_LAUNCH_CHECK("sa_mma_kernel");
     return SPSK_OK;
 }

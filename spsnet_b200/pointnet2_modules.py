@@ -127,6 +127,65 @@ def _pool_code(pool_method: str) -> int:
     raise NotImplementedError
 
 
+def _ceil(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def _get_twin(features: torch.Tensor, mult: int = 8):
+    """Point-major fp16 twin of a channel-major (B, C, N) fp32 tensor, as (twin (B, N, ld), lo_off): the copy the
+    producing fused layer left on the tensor object when there is one (and the tensor was not modified since) -- that
+    copy also carries the fp16 residuals at column `lo_off` (> 0) -- else a fresh conversion (lo_off = 0)."""
+    B, Cc, N = features.shape
+    hit = getattr(features, "_spsk_twin", None)
+    if hit is not None:
+        tw, ver, lo = hit
+        width = lo if lo else tw.shape[2]
+        if ver == features._version and tw.shape[0] == B and tw.shape[1] == N and width >= _ceil(Cc, mult) and tw.device == features.device:
+            return tw, lo
+    return pu.make_twin(features.contiguous(), _ceil(Cc, mult)), 0
+
+
+def _set_twin(features: torch.Tensor, twin: torch.Tensor, lo_off: int = 0) -> None:
+    features._spsk_twin = (twin.view(features.shape[0], features.shape[2], -1), features._version, lo_off)
+
+
+class _PwCache:
+    """Packed tensor-core weights (pu.PwLayer) of a folded Conv1d stack, rebuilt when the folded chain changes;
+    kept per arithmetic (split = hi + lo fp16 inputs, fp32-grade; plain = fp16 inputs)."""
+
+    def __init__(self):
+        self._chain = None
+        self._layers = {}
+
+    def get(self, chain, split: bool):
+        if self._chain is not chain:
+            self._layers = {}
+            self._chain = chain
+        if split not in self._layers:
+            self._layers[split] = [pu.PwLayer(wt, bias, relu, split=split) for wt, bias, relu in chain]
+        return self._layers[split]
+
+
+def _pw_stack(layers, x16: torch.Tensor, xlo: int, B: int, M: int, final: str):
+    """Run a packed Conv1d stack on point-major fp16 rows (hi at column 0, residuals at column `xlo` for split layers).
+    Intermediate layers produce fp16 rows only; the last one produces, per `final`:
+      "cm+16" -> ((B, C, M) fp32 channel-major, (B*M, ld) fp16 rows, lo_off);   "pm" -> (B, M, C) fp32."""
+    split = layers[0].split
+    for i, layer in enumerate(layers):
+        if i < len(layers) - 1:
+            _, x16, _ = pu.pw_mma_forward(x16, layer, xlo=xlo, want16=not split, want16_lo=split)
+            xlo = layer.n16 if split else 0
+            continue
+        if final == "cm+16":
+            out_cm = torch.empty((B, layer.c_out, M), dtype=torch.float32, device=x16.device)
+            _, out16, _ = pu.pw_mma_forward(x16, layer, xlo=xlo, out_cm=out_cm, m=M, want16=not split, want16_lo=split)
+            return out_cm, out16, (layer.n16 if split else 0)
+        out_pm = torch.empty((B, M, layer.c_out), dtype=torch.float32, device=x16.device)
+        pu.pw_mma_forward(x16, layer, xlo=xlo, out_pm=out_pm)
+        return out_pm
+    raise RuntimeError("empty Conv1d stack")
+
+
 # ---------------------------------------------------------------------------------------------------
 # base: grouping + shared MLP + pooling over all scales
 # ---------------------------------------------------------------------------------------------------
@@ -181,7 +240,10 @@ class _PointnetSAModuleBase(nn.Module):
         return all(isinstance(g, (pu.QueryAndGroup, pu.QueryDilatedAndGroup)) for g in self.groupers)
 
     # -- fused inference path
-    def _msg_fused(self, xyz, new_xyz, features):
+    def _msg_fused(self, xyz, new_xyz, features, want16=False):
+        """All MSG scales.  Returns (out_cm, out16): the pooled features as the reference's (B, C_total, M) fp32 tensor,
+        or -- when `want16` and every scale runs on the tensor cores -- only as (B*M, 2*ceil16(C_total)) fp16 point-major
+        rows [values | residuals], the operand layout of the aggregation GEMM (the fp32 tensor is never materialised)."""
         xyz = xyz.contiguous()
         new_xyz = new_xyz.contiguous()
         if features is not None:
@@ -190,7 +252,6 @@ class _PointnetSAModuleBase(nn.Module):
         pool = _pool_code(self.pool_method)
         chains = [self._folded(f"mlps.{i}", mlp) for i, mlp in enumerate(self.mlps)]
         c_total = sum(ch[-1][0].shape[1] for ch in chains)
-        out = torch.zeros((B, c_total, M), dtype=torch.float32, device=xyz.device)
         if all(isinstance(g, pu.QueryAndGroup) for g in self.groupers):
             idxs = pu.ball_query_msg([g.radius for g in self.groupers], [g.nsample for g in self.groupers], xyz, new_xyz)
         else:
@@ -200,44 +261,86 @@ class _PointnetSAModuleBase(nn.Module):
                     idxs.append(pu.ball_query_dilated(g.radius_in, g.radius_out, g.nsample, xyz, new_xyz))
                 else:
                     idxs.append(pu.ball_query(g.radius, g.nsample, xyz, new_xyz))
+        c_feat = features.shape[1] if features is not None else 0
+        packs = [None] * len(chains)
+        if mlp_backend() == "mma" and pool == 1:
+            for si, (g, chain, idx) in enumerate(zip(self.groupers, chains, idxs)):
+                ns = idx.shape[2]
+                if ns <= 128 and (ns & (ns - 1)) == 0:
+                    pk = self._mma_chain(si, chain, c_feat, g.use_xyz)
+                    packs[si] = pk if pk.ok else None
+        out_cm = out16 = None
+        c16 = _ceil(c_total, 16)
+        if want16 and all(pk is not None for pk in packs):
+            # [hi (c16) | lo (c16)]: pooled features as fp16 values + fp16 residuals, so the aggregation GEMM stays fp32-grade
+            alloc = torch.empty if c16 == c_total else torch.zeros
+            out16 = alloc((B * M, 2 * c16), dtype=torch.float16, device=xyz.device)
+        else:
+            out_cm = torch.zeros((B, c_total, M), dtype=torch.float32, device=xyz.device)
         co = 0
-        use_mma = mlp_backend() == "mma" and pool == 1
         twin = None
         for si, (g, chain, idx) in enumerate(zip(self.groupers, chains, idxs)):
-            ns = idx.shape[2]
-            if use_mma and ns <= 128 and (ns & (ns - 1)) == 0:
-                c_feat = features.shape[1] if features is not None else 0
-                packed = self._mma_chain(si, chain, c_feat, g.use_xyz)
-                if packed.ok:
-                    if twin is None and c_feat:
-                        twin = pu.make_twin(features, packed.cpad8)
-                    pu.sa_mma_forward(xyz=xyz, new_xyz=new_xyz, twin=twin, idx=idx, use_xyz=g.use_xyz, chain=packed,
-                                      out_pooled=out, co_off=co)
-                    co += chain[-1][0].shape[1]
-                    continue
-            rows = None
-            for li, (wt, bias, relu) in enumerate(chain):
-                last = li == len(chain) - 1
-                rows = pu.grouped_linear(xyz=xyz, new_xyz=new_xyz, features=features, idx=idx, use_xyz=g.use_xyz,
-                                         in_rows=rows, wt=wt, bias=bias, relu=relu, pool=pool if last else 0,
-                                         out_pooled=out if last else None, co_off=co)
+            pk = packs[si]
+            if pk is not None:
+                if c_feat and not pk.split and twin is None:
+                    twin = _get_twin(features)[0]
+                pu.sa_mma_forward(xyz=xyz, new_xyz=new_xyz, idx=idx, chain=pk, twin=twin, features=features if pk.split else None,
+                                  out_pooled=out_cm, co_off=co, out16=out16, co16=co, o16lo=c16 if out16 is not None else 0)
+            else:
+                rows = None
+                for li, (wt, bias, relu) in enumerate(chain):
+                    last = li == len(chain) - 1
+                    rows = pu.grouped_linear(xyz=xyz, new_xyz=new_xyz, features=features, idx=idx, use_xyz=g.use_xyz,
+                                             in_rows=rows, wt=wt, bias=bias, relu=relu, pool=pool if last else 0,
+                                             out_pooled=out_cm if last else None, co_off=co)
             co += chain[-1][0].shape[1]
-        return out
+        return out_cm, out16
 
-    def _msg(self, xyz, new_xyz, features):
+    def _msg(self, xyz, new_xyz, features, want16=False):
         if _fused_ok(self, xyz, features, new_xyz) and self._fusable_groupers() and len(self.mlps) > 0 \
                 and all(len(m) > 0 for m in self.mlps):
-            return self._msg_fused(xyz, new_xyz, features)
-        return self._msg_composed(xyz, new_xyz, features)
+            return self._msg_fused(xyz, new_xyz, features, want16)
+        return self._msg_composed(xyz, new_xyz, features), None
+
+    def _pw_layers(self, name: str, seq: nn.Sequential, split: bool):
+        cache = self.__dict__.setdefault("_pw_cache", {})
+        if name not in cache:
+            cache[name] = _PwCache()
+        return cache[name].get(self._folded(name, seq), split)
 
     def _seq_1d(self, name: str, seq: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
-        """Conv1d/BN1d/ReLU stack: fused point-wise GEMMs at inference, torch modules otherwise."""
+        """Conv1d/BN1d/ReLU stack on a channel-major tensor: exact-fp32 point-wise GEMMs at inference (SPSK_MLP=ffma),
+        torch modules otherwise."""
         if not _fused_ok(self, x):
             return seq(x)
         x = x.contiguous()
         for wt, bias, relu in self._folded(name, seq):
             x = pu.pointwise_linear(x, wt, bias, relu)
         return x
+
+    def _aggregate(self, out_cm, out16, B, M):
+        """aggregation_layer over the pooled MSG features (reference :447-449).  Tensor-core path: fp16 rows (values +
+        residuals) in, (B, C, M) fp32 + its fp16 point-major twin out (the twin feeds the confidence GEMMs and the next
+        layer's gather); hi + lo arithmetic keeps this layer fp32-grade."""
+        if _fused_ok(self, out_cm) and mlp_backend() == "mma":
+            if out16 is not None:
+                xlo = out16.shape[1] // 2
+            else:
+                out16, xlo = pu.make_twin(out_cm, _ceil(out_cm.shape[1], 16)).view(B * M, -1), 0
+            layers = self._pw_layers("aggregation_layer", self.aggregation_layer, split=xlo > 0)
+            new_features, twin, lo = _pw_stack(layers, out16, xlo, B, M, "cm+16")
+            _set_twin(new_features, twin, lo)
+            return new_features
+        return self._seq_1d("aggregation_layer", self.aggregation_layer, out_cm)
+
+    def _confidence(self, new_features):
+        """confidence_layers -> (B, npoint, num_class) (reference :454-455, incl. the transpose)."""
+        if _fused_ok(self, new_features) and mlp_backend() == "mma":
+            B, _, M = new_features.shape
+            tw, lo = _get_twin(new_features, 16)
+            layers = self._pw_layers("confidence_layers", self.confidence_layers, split=lo > 0)
+            return _pw_stack(layers, tw.view(B * M, -1), lo, B, M, "pm")
+        return self._seq_1d("confidence_layers", self.confidence_layers, new_features).transpose(1, 2)
 
     # reference: pointnet2_modules.py:45-81
     def forward(self, xyz: torch.Tensor, features: torch.Tensor = None, new_xyz=None):
@@ -247,7 +350,7 @@ class _PointnetSAModuleBase(nn.Module):
                 new_xyz = pu.gather_rows(xyz.contiguous(), idx)
             else:
                 new_xyz = pu.gather_operation(xyz.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
-        return new_xyz, self._msg(xyz, new_xyz, features)
+        return new_xyz, self._msg(xyz, new_xyz, features)[0]
 
 
 class PointnetSAModuleMSG(_PointnetSAModuleBase):
@@ -286,6 +389,18 @@ def _gather_stds(stds, idx):
     """stds (B,1,N) -> (B,npoint) at idx (reference :305,310 `gather_operation(...).squeeze()`)."""
     B = stds.shape[0]
     return pu.gather_operation(stds.reshape(B, 1, -1).contiguous(), idx).reshape(B, -1)
+
+
+def _gather_features(features, idx, fused):
+    """SA layer without groupers: new_features = features[:, :, idx] (reference :451-452); the cached fp16 twin of the
+    source, if any, is gathered along (as 4-byte words) so that the next fused layer does not have to convert."""
+    features = features.contiguous()
+    out = pu.gather_operation(features, idx).contiguous()
+    hit = getattr(features, "_spsk_twin", None) if fused else None
+    if hit is not None and hit[1] == features._version and hit[0].shape[2] % 2 == 0 and mlp_backend() == "mma":
+        g = pu.gather_rows(hit[0].view(torch.float32), idx.contiguous())
+        _set_twin(out, g.view(torch.float16), hit[2])
+    return out
 
 
 def _sector_fps(xyz_tmp, npoint, key_fn, part_num=4):
@@ -458,14 +573,17 @@ class PointnetSAModuleMSG_WithSampling(_PointnetSAModuleBase):
             new_xyz = ctr_xyz
 
         if len(self.groupers) > 0:
-            new_features = self._msg(xyz, new_xyz, features)
+            B_, M_ = new_xyz.shape[0], new_xyz.shape[1]
+            out_cm, out16 = self._msg(xyz, new_xyz, features, want16=self.aggregation_layer is not None)
             if self.aggregation_layer is not None:
-                new_features = self._seq_1d("aggregation_layer", self.aggregation_layer, new_features)
+                new_features = self._aggregate(out_cm, out16, B_, M_)
+            else:
+                new_features = out_cm
         else:
-            new_features = pu.gather_operation(features.contiguous(), sampled_idx_list).contiguous()
+            new_features = _gather_features(features, sampled_idx_list, fused)
 
         if self.confidence_layers is not None:
-            cls_features = self._seq_1d("confidence_layers", self.confidence_layers, new_features).transpose(1, 2)
+            cls_features = self._confidence(new_features)
         else:
             cls_features = None
         return new_xyz, new_features, cls_features, sampled_idx_list, stds
@@ -504,16 +622,23 @@ class Vote_layer(nn.Module):
         if hasattr(self, "center_surface_futures"):
             features_select = torch.cat([self.center_surface_futures, features_select], dim=1)
 
-        if _fused_ok(self, features_select):
+        if _fused_ok(self, features_select) and mlp_backend() == "mma":
+            B_, _, M_ = features_select.shape
+            caches = self.__dict__.setdefault("_pw_cache", {"mlp_modules": _PwCache(), "ctr_reg": _PwCache()})
+            tw, lo = _get_twin(features_select.contiguous(), 16)
+            layers = caches["mlp_modules"].get(self._folded("mlp_modules", self.mlp_modules), lo > 0) + \
+                caches["ctr_reg"].get(self._folded("ctr_reg", nn.Sequential(self.ctr_reg)), lo > 0)
+            ctr_offsets = _pw_stack(layers, tw.view(B_ * M_, -1), lo, B_, M_, "pm")  # (B, npoint, 3 [+ extra])
+        elif _fused_ok(self, features_select):
             h = features_select.contiguous()
             for wt, bias, relu in self._folded("mlp_modules", self.mlp_modules):
                 h = pu.pointwise_linear(h, wt, bias, relu)
             for wt, bias, relu in self._folded("ctr_reg", nn.Sequential(self.ctr_reg)):
                 ctr_offsets = pu.pointwise_linear(h, wt, bias, relu)
+            ctr_offsets = ctr_offsets.transpose(1, 2)
         else:
-            ctr_offsets = self.ctr_reg(self.mlp_modules(features_select))
+            ctr_offsets = self.ctr_reg(self.mlp_modules(features_select)).transpose(1, 2)
 
-        ctr_offsets = ctr_offsets.transpose(1, 2)  # (B, npoint, 3 [+ extra])
         new_features = ctr_offsets[..., 3:]
         ctr_offsets = ctr_offsets[..., :3]
         if self.max_offset_limit is not None:
@@ -630,9 +755,11 @@ class PointnetSampling(_PointnetSAModuleBase):
         else:
             new_xyz = ctr_xyz
         if len(self.groupers) > 0:
-            new_features = self._msg(xyz, new_xyz, features)
+            out_cm, out16 = self._msg(xyz, new_xyz, features, want16=self.aggregation_layer is not None)
             if self.aggregation_layer is not None:
-                new_features = self._seq_1d("aggregation_layer", self.aggregation_layer, new_features)
+                new_features = self._aggregate(out_cm, out16, new_xyz.shape[0], new_xyz.shape[1])
+            else:
+                new_features = out_cm
         else:
-            new_features = pu.gather_operation(features.contiguous(), sampled_idx_list).contiguous()
+            new_features = _gather_features(features, sampled_idx_list, fused)
         return new_xyz, new_features, sampled_idx_list

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 from torch.autograd import Function
 
-from ._lib import GroupDesc, check, lib
+from ._lib import GroupDesc, PwDesc, SaMmaDesc, check, lib
 
 __all__ = [
     "farthest_point_sample", "furthest_point_sample", "furthest_point_sample_with_dist", "gather_operation",
@@ -429,59 +429,93 @@ def _ceil(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
-class MmaChain:
-    """A folded Conv/BN/ReLU chain packed for spsk_sa_mma_forward: fp16 weight tiles of 128 couts x 64 k in the
-    canonical K-major no-swizzle UMMA layout, zero padded; layer-0 input order is [features (cpad8), x, y, z, 0...]
-    (the reference's order is [x, y, z, features], pointnet2_utils.py:315 -- a pure row permutation of W0)."""
+def _canonical_tile(block: torch.Tensor) -> torch.Tensor:
+    """(rows, k) -> flat fp16 in the K-major no-swizzle UMMA layout: 8-row x 8-half core matrices, k-groups
+    contiguous inside an 8-row group:  half(r, k) = (r/8)*(kw*8) + (k/8)*64 + (r%8)*8 + (k%8)."""
+    rows, kw = block.shape
+    return block.reshape(rows // 8, 8, kw // 8, 8).permute(0, 2, 1, 3).contiguous().reshape(-1)
 
-    def __init__(self, chain, c_feat: int, use_xyz: bool):
+
+class MmaChain:
+    """A folded Conv/BN/ReLU chain packed for spsk_sa_mma_forward (layout: include/spsk.h).
+
+    plain mode : fp16 operands; layer-0 input order [features (ceil8(c_feat)), x, y, z, 0...] (the reference's order
+                 is [x, y, z, features], pointnet2_utils.py:315 -- a pure row permutation of W0)
+    split mode : chosen automatically for narrow chains (every width <= 64, c_feat <= 8: IA-SSD layer 0); weights
+                 become [Wh; Wh; Wl] so that [Xh | Xl | Xh] . W' = Xh.Wh + Xl.Wh + Xh.Wl  (fp32-grade)
+    """
+
+    def __init__(self, chain, c_feat: int, use_xyz: bool, split: bool | None = None):
         dev = chain[0][0].device
         self.nlayers = len(chain)
+        self.c_feat, self.use_xyz = c_feat, use_xyz
+        widths = [wt.shape[1] for wt, _, _ in chain]
+        can_split = c_feat <= 8 and all(_ceil(w, 16) <= 64 for w in widths[:-1]) and self.nlayers <= 4
+        self.split = can_split if split is None else (bool(split) and can_split)
         self.cpad8 = _ceil(c_feat, 8) if c_feat > 0 else 0
         k0 = self.cpad8 + (8 if use_xyz else 0)
-        kin = _ceil(max(k0, 16), 16)
-        self.kpad, self.cpad, self.tile_off, self.bias_off = [], [], [], []
+        self.ok = 1 <= self.nlayers <= 4 and all(relu for _, _, relu in chain) and k0 > 0
+        kin = 16 if self.split else _ceil(max(k0, 16), 16)
+        self.kpad, self.cpad = [], []
         tiles, biases = [], []
-        ntile = nbias = 0
-        self.ok = self.nlayers <= 4 and all(relu for _, _, relu in chain) and k0 > 0
         for l, (wt, bias, _relu) in enumerate(chain):
             cin, cout = wt.shape
             last = l == self.nlayers - 1
             cp = _ceil(cout, 128 if last else 16)
             W = torch.zeros((kin, cp), dtype=torch.float32, device=dev)
             if l == 0:
-                xr = 3 if use_xyz else 0
+                xr = 3 if use_xyz else 0  # reference row order: xyz first
+                fo = 0
+                xo = (8 if c_feat else 0) if self.split else self.cpad8
                 if c_feat:
-                    W[0:c_feat, :cout] = wt[xr:xr + c_feat]
+                    W[fo:fo + c_feat, :cout] = wt[xr:xr + c_feat]
                 if use_xyz:
-                    W[self.cpad8:self.cpad8 + 3, :cout] = wt[0:3]
+                    W[xo:xo + 3, :cout] = wt[0:3]
             else:
                 W[:cin, :cout] = wt
+            if self.split:
+                Wh = W.half()
+                Wl = (W - Wh.float()).half()
+                Wv = torch.cat([Wh, Wh, Wl], dim=0)
+            else:
+                Wv = W.half()
+            vk = Wv.shape[0]
+            for c0 in range(0, cp, 128):
+                ncols = min(128, cp - c0)
+                for k0_ in range(0, vk, 64):
+                    kw = min(64, vk - k0_)
+                    tiles.append(_canonical_tile(Wv[k0_:k0_ + kw, c0:c0 + ncols].t()))
             bv = torch.zeros(cp, dtype=torch.float32, device=dev)
             bv[:cout] = bias
-            n_cc, n_kc = (cp + 127) // 128, (kin + 63) // 64
-            Wt = torch.zeros((n_cc * 128, n_kc * 64), dtype=torch.float32, device=dev)
-            Wt[:cp, :kin] = W.t()
-            T = Wt.view(n_cc, 16, 8, n_kc, 8, 8).permute(0, 3, 1, 4, 2, 5).contiguous()  # (cc, kc, rg, kg, r, k)
-            tiles.append(T.reshape(-1).to(torch.float16))
             biases.append(bv)
             self.kpad.append(kin)
             self.cpad.append(cp)
-            self.tile_off.append(ntile)
-            self.bias_off.append(nbias)
-            ntile += n_cc * n_kc
-            nbias += cp
-            if kin > 1024 or (not last and cp > 512):
+            if kin > 1024 or (not last and cp > 1024):
                 self.ok = False
             kin = cp
             self.cout_last = cout
         self.wtiles = torch.cat(tiles).contiguous()
         self.bias = torch.cat(biases).contiguous()
-        self._c = {k: (C.c_int * self.nlayers)(*getattr(self, k)) for k in ("kpad", "cpad", "tile_off", "bias_off")}
+        self.ctas_per_sm = self.nstages = self.resident = self.smem = 0
         if self.ok:
-            ns = C.c_int(0)
-            # > 0: one CTA per SM (512 TMEM columns); < -1: two CTAs per SM (256 columns); -1: does not fit
-            self.ok = lib.spsk_sa_mma_smem_bytes(self.nlayers, self._c["kpad"], self._c["cpad"], C.byref(ns)) != -1
+            d = self._desc()
+            v = [C.c_int(0) for _ in range(4)]
+            self.ok = lib.spsk_sa_mma_config(C.byref(d), *[C.byref(x) for x in v]) == 0
+            self.smem, self.ctas_per_sm, self.nstages, self.resident = [int(x.value) for x in v]
+
+    def _desc(self) -> SaMmaDesc:
+        d = SaMmaDesc()
+        d.nlayers = self.nlayers
+        for l in range(self.nlayers):
+            d.kpad[l] = self.kpad[l]
+            d.cpad[l] = self.cpad[l]
+        d.split = 1 if self.split else 0
+        d.c_feat = self.c_feat
+        d.use_xyz = 1 if self.use_xyz else 0
+        d.cout_last = self.cout_last
+        d.wtiles = self.wtiles.data_ptr()
+        d.bias = self.bias.data_ptr()
+        return d
 
 
 def make_twin(features: torch.Tensor, cpad8: int) -> torch.Tensor:
@@ -494,16 +528,87 @@ def make_twin(features: torch.Tensor, cpad8: int) -> torch.Tensor:
     return twin
 
 
-def sa_mma_forward(*, xyz, new_xyz, twin, idx, use_xyz, chain: MmaChain, out_pooled, co_off):
+def sa_mma_forward(*, xyz, new_xyz, idx, chain: MmaChain, twin=None, features=None, out_pooled=None, co_off=0,
+                   out16=None, co16=0, n16=None, o16lo=0):
+    """One fused MSG scale (include/spsk.h: spsk_sa_mma_forward).  `twin` (B, N, ld) fp16 in plain mode, `features`
+    (B, C, N) fp32 in split mode; results go to out_pooled[:, co_off:co_off+cout, :] (fp32, (B, C_total, M)) and/or
+    out16[:, co16:co16+n16] (fp16, (B*M, ld16)); with o16lo > 0 the fp16 residuals go to out16[:, o16lo+co16 : ...]."""
     B, M, ns = idx.shape
-    g = GroupDesc()
-    g.b, g.n, g.m, g.nsample = B, xyz.shape[1], M, ns
-    g.c_feat = 0
-    g.use_xyz = 1 if use_xyz else 0
-    g.xyz, g.new_xyz, g.features, g.idx = xyz.data_ptr(), new_xyz.data_ptr(), None, idx.data_ptr()
+    d = chain._desc()
+    d.b, d.n, d.m, d.nsample = B, xyz.shape[1], M, ns
+    d.xyz, d.new_xyz, d.idx = xyz.data_ptr(), new_xyz.data_ptr(), idx.data_ptr()
+    if chain.c_feat:
+        if chain.split:
+            _chk(features, "features", torch.float32, 3)
+            d.features = features.data_ptr()
+        else:
+            if twin is None or twin.dtype != torch.float16 or not twin.is_contiguous() or twin.shape[2] < chain.cpad8:
+                raise RuntimeError("sa_mma_forward: twin must be a contiguous (B, N, >=ceil8(C)) fp16 tensor")
+            d.twin, d.ldtwin = twin.data_ptr(), twin.shape[2]
+    if out_pooled is not None:
+        d.out_cm, d.c_total, d.co_off = out_pooled.data_ptr(), out_pooled.shape[1], co_off
+    if out16 is not None:
+        d.out16, d.ld16, d.co16 = out16.data_ptr(), out16.shape[-1], co16
+        d.n16 = chain.cout_last if n16 is None else n16
+        d.o16lo = int(o16lo)
     with torch.cuda.device(idx.device):
-        check(lib.spsk_sa_mma_forward(C.byref(g), chain.cpad8, twin.data_ptr() if twin is not None else None, chain.nlayers,
-                                      chain._c["kpad"], chain._c["cpad"], chain._c["tile_off"], chain._c["bias_off"],
-                                      chain.wtiles.data_ptr(), chain.bias.data_ptr(), chain.cout_last,
-                                      out_pooled.data_ptr(), out_pooled.shape[1], co_off, _stream()), "sa_mma_forward")
-    return out_pooled
+        check(lib.spsk_sa_mma_forward(C.byref(d), _stream()), "sa_mma_forward")
+    return out_pooled if out_pooled is not None else out16
+
+
+class PwLayer:
+    """One folded Conv1d(k=1)[+BN][+ReLU] layer packed for spsk_pw_mma_forward: W (c_out x K) as 128-cout x 64-k
+    fp16 tiles (16 KB each, canonical K-major layout), zero padded to cover ceil128(max(c_out, n16)) couts.
+    split=True packs W' = [Wh ; Wh ; Wl] (K = 3 * ceil16(c_in)) for inputs carried as hi + lo fp16 halves."""
+
+    def __init__(self, wt: torch.Tensor, bias: torch.Tensor, relu: bool, split: bool = False):
+        dev = wt.device
+        self.c_in, self.c_out = wt.shape
+        self.relu = bool(relu)
+        self.split = bool(split)
+        self.k = _ceil(self.c_in, 16)
+        self.n16 = _ceil(self.c_out, 16)
+        ncov = _ceil(max(self.c_out, self.n16), 128)
+        W = torch.zeros((self.k, ncov), dtype=torch.float32, device=dev)
+        W[:self.c_in, :self.c_out] = wt
+        if self.split:
+            Wh = W.half()
+            Wv = torch.cat([Wh, Wh, (W - Wh.float()).half()], dim=0)
+        else:
+            Wv = W.half()
+        vk = Wv.shape[0]
+        n_cc, n_kc = ncov // 128, _ceil(vk, 64) // 64
+        Wt = torch.zeros((ncov, n_kc * 64), dtype=torch.float16, device=dev)
+        Wt[:, :vk] = Wv.t()
+        T = Wt.view(n_cc, 16, 8, n_kc, 8, 8).permute(0, 3, 1, 4, 2, 5).contiguous()  # (cc, kc, rg, kg, r, k)
+        self.wtiles = T.reshape(-1)
+        self.bias = torch.zeros(ncov, dtype=torch.float32, device=dev)
+        self.bias[:self.c_out] = bias
+
+
+def pw_mma_forward(x16: torch.Tensor, layer: PwLayer, *, xlo=0, out_cm=None, m=0, co_off=0, want16=False, want16_lo=False, out_pm=None):
+    """y = act(x16 @ W^T + b) on the tensor cores.  x16: (rows, ldx) fp16 point-major with zeros in columns >= c_in
+    (split layers: hi in [0, k), lo in [xlo, xlo + k)).  Returns (out_cm, out16, out_pm); out16 = (rows, ceil16(c_out))
+    fp16 when want16, or (rows, 2 * ceil16(c_out)) = [hi | lo] when want16_lo."""
+    if x16.dtype != torch.float16 or x16.dim() != 2 or not x16.is_contiguous() or not x16.is_cuda:
+        raise RuntimeError("pw_mma_forward: x16 must be a contiguous CUDA (rows, ldx) fp16 tensor")
+    rows, ldx = x16.shape
+    if ldx < layer.k or (layer.split and (xlo < layer.k or xlo + layer.k > ldx)):
+        raise RuntimeError(f"pw_mma_forward: input width {ldx} (lo at {xlo}) does not hold the padded c_in {layer.k}")
+    d = PwDesc()
+    d.rows, d.k, d.ldx, d.n, d.relu = rows, layer.k, ldx, layer.c_out, 1 if layer.relu else 0
+    d.split, d.xlo = (1, int(xlo)) if layer.split else (0, 0)
+    d.x, d.wtiles, d.bias = x16.data_ptr(), layer.wtiles.data_ptr(), layer.bias.data_ptr()
+    if out_cm is not None:
+        d.out_cm, d.m, d.c_total, d.co_off = out_cm.data_ptr(), m, out_cm.shape[1], co_off
+    out16 = None
+    if want16 or want16_lo:
+        ld16 = layer.n16 * (2 if want16_lo else 1)
+        out16 = torch.empty((rows, ld16), dtype=torch.float16, device=x16.device)
+        d.out16, d.ld16, d.n16 = out16.data_ptr(), ld16, layer.n16
+        d.o16lo = layer.n16 if want16_lo else 0
+    if out_pm is not None:
+        d.out_pm, d.ldpm = out_pm.data_ptr(), out_pm.shape[-1]
+    with torch.cuda.device(x16.device):
+        check(lib.spsk_pw_mma_forward(C.byref(d), _stream()), "pw_mma_forward")
+    return out_cm, out16, out_pm
