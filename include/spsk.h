@@ -243,8 +243,9 @@ SPSK_API int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stream
 /* Tuning aid: when `counters` (device memory, SPSK_SA_PROF_COUNTERS x u64, zeroed by the caller) is non-NULL every
  * following spsk_sa_mma_forward adds the SM cycles its warp roles spent per wait / work category (order: mma total,
  * mma wait acc-empty, mma wait weights, mma wait activations, producer wait stage, producer wait hidden-done, epilogue
- * total, gather, wait hidden acc, hidden epilogue, wait pool acc, pool epilogue; summed over CTAs, epilogue = thread 0). */
-#define SPSK_SA_PROF_COUNTERS 12
+ * total, gather, wait hidden acc, hidden epilogue, wait pool acc, pool epilogue, mma issue, mma commit; summed over CTAs,
+ * epilogue = thread 0). */
+#define SPSK_SA_PROF_COUNTERS 14
 SPSK_API int spsk_sa_mma_set_profile(unsigned long long *counters);
 
 /* Point-wise layer on the tensor cores:  y[row, c] = relu?( bias[c] + sum_k x[row, k] * W[c, k] )  over point-major

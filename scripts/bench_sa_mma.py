@@ -17,7 +17,7 @@ SHAPES = {
     "l5s1": (512, 256, 256, 16, 4.8, [256, 256, 512]), "l5s2": (512, 256, 256, 32, 6.4, [256, 512, 1024]),
 }
 NAMES = ["mma_total", "mma_wait_acc_empty", "mma_wait_w", "mma_wait_x", "prod_wait_stage", "prod_wait_hid", "epi_total", "epi_gather",
-         "epi_wait_hid", "epi_work_hid", "epi_wait_pool", "epi_work_pool"]
+         "epi_wait_hid", "epi_work_hid", "epi_wait_pool", "epi_work_pool", "mma_issue", "mma_commit"]
 
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
@@ -51,7 +51,7 @@ def main():
         print(f"{name}: {us:8.1f} us  rows={rows} tiles={rows//128} ctas/SM={pk.ctas_per_sm} res={pk.resident} stages={pk.nstages} split={pk.split} "
               f"{flops/us/1e6:7.1f} TFLOP/s  {us*1e3/(rows/128)*148*pk.ctas_per_sm/ max(1,pk.ctas_per_sm):.0f} ns/tile/SM-slot")
         if prof:
-            buf = torch.zeros(12, dtype=torch.int64, device="cuda")
+            buf = torch.zeros(14, dtype=torch.int64, device="cuda")
             lib.spsk_sa_mma_set_profile(buf.data_ptr())
             run(); torch.cuda.synchronize()
             lib.spsk_sa_mma_set_profile(None)

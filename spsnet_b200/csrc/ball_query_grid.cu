@@ -165,43 +165,44 @@ bq_grid_query_kernel(int n, int m, int words, BgScales sc, const float *__restri
         }
     }
     __syncwarp();
-    // read the bitmaps back in index order
-    const int wpl = (words + 31) / 32;   // words per lane (contiguous chunk)
+    // Read the bitmaps back in index order, one ROW of 32 consecutive words per step (lane = word: conflict-free shared
+    // memory reads; a per-lane contiguous chunk would be a 16-way bank conflict).  Hits are sparse, so most rows are
+    // skipped after one ballot, and the walk stops as soon as nsample indices are out.
+    const int rows = (words + 31) >> 5;
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
         const int ns = sc.nsample[s];
         int *out = sc.idx[s] + ((size_t)b * m + p) * ns;
-        uint32_t *w = bm + s * words;
-        const int w0 = (int)lane * wpl, w1 = min(w0 + wpl, words);
-        int cnt = 0;
-        for (int i = w0; i < w1; ++i) cnt += __popc(w[i]);
-        int incl = cnt;
+        const uint32_t *w = bm + s * words;
+        int base = 0;       // hits written so far (warp-uniform)
+        int first = -1;     // smallest hit index (warp-uniform once found)
+        for (int i = 0; i < rows && base < ns; ++i) {
+            const int wi = i * 32 + (int)lane;
+            uint32_t bits = wi < words ? w[wi] : 0u;
+            const uint32_t nz = __ballot_sync(0xFFFFFFFFu, bits != 0u);
+            if (nz == 0u) continue;
+            const int cnt = __popc(bits);
+            int incl = cnt;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if ((int)lane >= o) incl += v;
-        }
-        const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        int pos = incl - cnt;
-        int first_local = -1;
-        for (int i = w0; i < w1; ++i) {
-            uint32_t bits = w[i];
-            if (bits) {
-                w[i] = 0u;
-                while (bits) {
-                    const int bit = __ffs(bits) - 1;
-                    bits &= bits - 1u;
-                    const int id = i * 32 + bit;
-                    if (first_local < 0) first_local = id;
-                    if (pos < ns) out[pos] = id;
-                    ++pos;
-                }
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if ((int)lane >= o) incl += v;
             }
+            if (first < 0) {
+                const int l0 = __ffs(nz) - 1;
+                const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, bits, l0);
+                first = (i * 32 + l0) * 32 + (__ffs(b0) - 1);
+            }
+            int pos = base + incl - cnt;
+            while (bits && pos < ns) {
+                const int bit = __ffs(bits) - 1;
+                bits &= bits - 1u;
+                out[pos++] = wi * 32 + bit;
+            }
+            base += __shfl_sync(0xFFFFFFFFu, incl, 31);
         }
-        const uint32_t has = __ballot_sync(0xFFFFFFFFu, cnt > 0);
-        if (total > 0) {
-            const int first = __shfl_sync(0xFFFFFFFFu, first_local, __ffs(has) - 1);
-            for (int l = min(total, ns) + (int)lane; l < ns; l += 32) out[l] = first;   // first-hit padding
+        if (base > 0) {
+            for (int l = min(base, ns) + (int)lane; l < ns; l += 32) out[l] = first;   // first-hit padding
         } else {
             for (int l = (int)lane; l < ns; l += 32) out[l] = 0;
         }

@@ -21,10 +21,10 @@ namespace spsk {
 
 constexpr int PW_ROWS = 128;
 constexpr int PW_THREADS = 192;
-constexpr int PW_STAGES = 3;
 constexpr int PW_TILE_BYTES = 16384;                       // 128 rows x 64 k fp16
-constexpr int PW_SMEM = 256 + PW_STAGES * 2 * PW_TILE_BYTES;
-constexpr int PW_LAG = 2;                                  // chunks whose cp.async may still be in flight
+// <stages, lag>: ring depth and how many chunks of cp.async stay in flight behind the one being issued.
+// short K: <3, 2> (96 KB, two CTAs per SM);  long K (the 1536-wide aggregation, x3 in split mode): <6, 4> (192 KB)
+constexpr int pw_smem(int stages) { return 256 + stages * 2 * PW_TILE_BYTES; }
 
 struct PwArgs {
     int rows, k, ldx, n, npad, n_kc, relu;
@@ -38,7 +38,8 @@ struct PwArgs {
     float *out_pm; int ldpm;
 };
 
-__global__ void __launch_bounds__(PW_THREADS, 2)
+template <int PW_STAGES, int PW_LAG>
+__global__ void __launch_bounds__(PW_THREADS, PW_STAGES <= 3 ? 2 : 1)
 pw_mma_kernel(const PwArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
@@ -238,13 +239,19 @@ extern "C" int spsk_pw_mma_forward(const spsk_pw_desc *d, spsk_stream_t stream) 
                      SPSK_ERR_INVALID_ARG, "pw_mma: fp16 output needs ld16, n16 multiples of 8, n <= n16 <= ld16, 16-byte alignment");
     a.out_pm = d->out_pm; a.ldpm = d->ldpm;
     if (a.out_pm) SPSK_REQUIRE(d->ldpm >= d->n, SPSK_ERR_INVALID_ARG, "pw_mma: ldpm < n");
-    static SmemAttrOnce attr;
-    if (int rc = attr.ensure(reinterpret_cast<const void *>(pw_mma_kernel), PW_SMEM, "pw_mma_kernel")) return rc;
+    const bool deep = a.n_kc >= 12;
+    static SmemAttrOnce attr_s, attr_d;
+    if (deep) {
+        if (int rc = attr_d.ensure(reinterpret_cast<const void *>(pw_mma_kernel<6, 4>), pw_smem(6), "pw_mma_kernel<6,4>")) return rc;
+    } else {
+        if (int rc = attr_s.ensure(reinterpret_cast<const void *>(pw_mma_kernel<3, 2>), pw_smem(3), "pw_mma_kernel<3,2>")) return rc;
+    }
     // n16 may extend past npad (zero columns up to the consumer's K padding): cover them with column tiles
     const int ncover = a.out16 ? max(a.npad, a.n16) : a.npad;
     a.npad = (ncover + 15) / 16 * 16;
     dim3 grid((unsigned)((d->rows + PW_ROWS - 1) / PW_ROWS), (unsigned)((a.npad + 127) / 128));
-    pw_mma_kernel<<<grid, PW_THREADS, PW_SMEM, as_stream(stream)>>>(a);
+    if (deep) pw_mma_kernel<6, 4><<<grid, PW_THREADS, pw_smem(6), as_stream(stream)>>>(a);
+    else pw_mma_kernel<3, 2><<<grid, PW_THREADS, pw_smem(3), as_stream(stream)>>>(a);
     SPSK_LAUNCH_CHECK("pw_mma_kernel");
     return SPSK_OK;
 }

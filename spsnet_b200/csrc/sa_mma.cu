@@ -38,7 +38,7 @@
 namespace spsk {
 
 constexpr int MM_ROWS = 128;          // grouped rows per tile
-constexpr int MM_THREADS = 192;       // 4 gather/epilogue warps + producer + mma
+constexpr int MM_THREADS = 192;       // G = 1: 4 gather/epilogue warps + producer + mma;  G = 2: 8 + 2 = 320 threads
 constexpr int MM_STAGE_BYTES = 16384; // largest weight tile: [128 cout][64 k] fp16
 constexpr int MM_MAX_LAYERS = 4;
 constexpr int MM_MAX_STAGES = 8;
@@ -184,7 +184,7 @@ __device__ __noinline__ void pool_chunk_any(uint32_t taddr, PoolOut &o, int ns) 
 
 // ---- optional role profiling: cycles spent per wait / work category, summed over CTAs ------------------------
 enum { PF_MMA_TOTAL = 0, PF_MMA_ACC_EMPTY, PF_MMA_W_FULL, PF_MMA_XR, PF_PROD_W_EMPTY, PF_PROD_HID, PF_EPI_TOTAL, PF_EPI_GATHER,
-       PF_EPI_WAIT_HID, PF_EPI_WORK_HID, PF_EPI_WAIT_POOL, PF_EPI_WORK_POOL, PF_COUNT };
+       PF_EPI_WAIT_HID, PF_EPI_WORK_HID, PF_EPI_WAIT_POOL, PF_EPI_WORK_POOL, PF_MMA_ISSUE, PF_MMA_COMMIT, PF_COUNT };
 struct Prof {
     unsigned long long acc[PF_COUNT];
     bool on;
@@ -203,8 +203,13 @@ struct Prof {
 };
 
 // ---- the kernel -----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(MM_THREADS, 3)
+// G = epilogue warpgroups.  G = 1 (192 threads, up to 3 CTAs per SM) for chains whose concurrency comes from co-resident
+// CTAs; G = 2 (320 threads, one CTA per SM) for the wide chains: the two warpgroups take alternate jobs, so two
+// accumulators drain concurrently and every scheduler holds two epilogue warps to hide TMEM / shared-memory latency.
+template <int G>
+__global__ void __launch_bounds__(128 * G + 64, G == 1 ? 3 : 1)
 sa_mma_kernel(const __grid_constant__ SaArgs a) {
+    constexpr int W_PROD = 4 * G, W_MMA = 4 * G + 1;
     extern __shared__ __align__(128) uint8_t smem[];
     // carve: [header: barriers + tmem slot][XA][XB][weights]
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
@@ -234,13 +239,13 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
         mbar_init(HID_DONE, 1);
         mbar_init_fence();
     }
-    if (warp == 5) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
+    if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == W_PROD) {
         // ================= weight producer (warp-uniform loops, one elected lane issues) =================
         const bool leader = elect_one();
         if (a.resident) {
@@ -292,7 +297,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
             }
             pf.flush(a.prof);
         }
-    } else if (warp == 5) {
+    } else if (warp == W_MMA) {
         // ================= MMA issuer (warp-uniform loops, one elected lane issues) =================
         {
             const bool leader = elect_one();
@@ -355,6 +360,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                             }
                             tc_fence_after();
                             if (leader) {
+                                const long long t_i = pf.now();
                                 const uint32_t w_lo = umma_desc_lo(wbase, 128u);
                                 const uint32_t w_hi = umma_desc_hi((uint32_t)kw * 16u);
                                 const uint32_t x_lo = x_lo0 + (uint32_t)kc * 64u;   // 4 K blocks of 256 bytes (>>4: 16 each)
@@ -377,11 +383,14 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                                         else umma_f16_lohi(d_tmem, wl, w_hi, xl, x_hi, idesc, v ? 1u : 0u);
                                     }
                                 }
+                                pf.add(PF_MMA_ISSUE, t_i);
+                                const long long t_c = pf.now();
                                 if (!a.resident) umma_commit(wempty);   // stage reusable once these MMAs retire
                                 if (kc == Ly.n_kc - 1) {
                                     umma_commit(ACC_FULL(buf));
                                     if (a.lstages > 0 && l == nL - 2 && cc == Ly.n_cc - 1) umma_commit(HID_DONE);   // its input buffer may now hold weight tiles
                                 }
+                                pf.add(PF_MMA_COMMIT, t_c);
                             }
                             __syncwarp();
                         }
@@ -397,19 +406,28 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
         pf.init(a.prof != nullptr && tid == 0);
         const long long t_start = pf.now();
         uint32_t job = 0;
-        const uint32_t lane_field = (uint32_t)(warp * 32) << 16;
-        const int r = tid;
+        const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;   // a warp reads the TMEM lane quarter warp % 4
+        const int r = tid & 127;
+        const uint32_t grp = (uint32_t)(tid >> 7);                       // epilogue warpgroup: takes jobs with job % G == grp
         const uint32_t row_off = (uint32_t)(r & 7) * 16u;
         const int first_tile = blockIdx.x;
+        uint32_t prev_last_job = 0;   // G = 2: the previous tile's last job (its MMAs are the last readers of XA)
+        bool have_prev = false;
         int jn = 0;   // neighbour index of this thread's row in the NEXT tile (prefetched one tile ahead)
-        if (first_tile < a.ntiles) {
+        if (grp == 0 && first_tile < a.ntiles) {
             const long long grow = (long long)first_tile * MM_ROWS + r;
             if (grow < a.rows) jn = __ldg(a.idx + grow);
         }
         for (int tile = first_tile; tile < a.ntiles; tile += gridDim.x) {
-            // ---- gather X0 (into XA): [features | dxyz | 0]   (split: [hi(k0) | lo(k0)])
+            // ---- gather X0 (into XA): [features | dxyz | 0]   (split: [hi(k0) | lo(k0)])   -- warpgroup 0
             const long long t_g = pf.now();
-            {
+            if (G == 2 && grp == 0 && have_prev) {
+                // the other warpgroup may own the previous tile's last job: peek at its accumulator barrier so that every
+                // MMA reading the buffer this gather overwrites has retired (waits do not consume the phase)
+                const int pb = (int)(prev_last_job & ((uint32_t)a.nbuf - 1u));
+                mbar_wait(ACC_FULL(pb), (prev_last_job >> a.nbuf_log2) & 1u);
+            }
+            if (grp == 0) {
                 const SaLayer &L0 = a.L[0];
                 const uint32_t sbo = (uint32_t)L0.xw * 16u;
                 uint8_t *xrow = xa + (size_t)(r >> 3) * sbo + row_off;
@@ -488,6 +506,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                 uint8_t *xrow = xo + (size_t)(r >> 3) * sbo + row_off;
                 const float *bias = a.bias + Ly.bias_off;
                 for (int cc = 0; cc < Ly.n_cc; ++cc, ++job) {
+                    if (G == 2 && (job & 1u) != grp) continue;
                     const int ncols = min(128, Ly.cpad - cc * 128);
                     const int buf = (int)(job & ((uint32_t)a.nbuf - 1u));
                     { const long long t0 = pf.now(); mbar_wait(ACC_FULL(buf), (job >> a.nbuf_log2) & 1u); pf.add(PF_EPI_WAIT_HID, t0); }
@@ -540,6 +559,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                 const int p0 = (int)(q0 - bb0 * a.m);
                 const size_t sstride = (size_t)a.c_total * a.m;
                 for (int cc = 0; cc < Ly.n_cc; ++cc, ++job) {
+                    if (G == 2 && (job & 1u) != grp) continue;
                     const int buf = (int)(job & ((uint32_t)a.nbuf - 1u));
                     { const long long t0 = pf.now(); mbar_wait(ACC_FULL(buf), (job >> a.nbuf_log2) & 1u); pf.add(PF_EPI_WAIT_POOL, t0); }
                     tc_fence_after();
@@ -562,6 +582,8 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                     pf.add(PF_EPI_WORK_POOL, t_w);
                 }
             }
+            prev_last_job = job - 1u;
+            have_prev = true;
         }
         pf.add(PF_EPI_TOTAL, t_start);
         pf.flush(a.prof);
@@ -569,7 +591,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == W_MMA) {
         tc_fence_after();
         tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
     }
@@ -754,13 +776,19 @@ extern "C" int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stre
         SPSK_REQUIRE(d->n16 >= d->cout_last && d->n16 <= d->cpad[d->nlayers - 1] && d->co16 >= 0 && d->co16 + d->n16 <= d->ld16, SPSK_ERR_INVALID_ARG,
                      "sa_mma: fp16 output window [co16, co16 + n16) outside ld16 or wider than the last layer");
     a.prof = g_sa_prof;
-    static SmemAttrOnce attr;
-    if (int rc = attr.ensure(reinterpret_cast<const void *>(sa_mma_kernel), 227 * 1024, "sa_mma_kernel")) return rc;
     // two CTAs per SM slot (static tile striding): when another stream's kernels hold some SMs, late CTAs start
     // as soon as any SM frees up instead of doubling the kernel's duration
     const int slots = SPSK_NUM_SMS * P.ctas * 2;
     const int grid = a.ntiles < slots ? a.ntiles : slots;
-    sa_mma_kernel<<<grid, MM_THREADS, P.smem, as_stream(stream)>>>(a);
+    const bool two_groups = P.ctas == 1 && !getenv("SPSK_SA_ONE_GROUP");
+    static SmemAttrOnce attr1, attr2;
+    if (two_groups) {
+        if (int rc = attr2.ensure(reinterpret_cast<const void *>(sa_mma_kernel<2>), 227 * 1024, "sa_mma_kernel<2>")) return rc;
+        sa_mma_kernel<2><<<grid, 320, P.smem, as_stream(stream)>>>(a);
+    } else {
+        if (int rc = attr1.ensure(reinterpret_cast<const void *>(sa_mma_kernel<1>), 227 * 1024, "sa_mma_kernel<1>")) return rc;
+        sa_mma_kernel<1><<<grid, 192, P.smem, as_stream(stream)>>>(a);
+    }
     SPSK_LAUNCH_CHECK("sa_mma_kernel");
     return SPSK_OK;
 }
