@@ -63,6 +63,11 @@ SPSK_API int spsk_built_for_sm(void);
 SPSK_API int spsk_farthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx,
                                  spsk_stream_t stream);
 
+/* Tuning aid: with a non-NULL `counters` (6 x u64 device words, zeroed by the caller) the pruned D-FPS kernel adds, summed
+ * over scenes, warp 0's cycles in [query + bound, sub-bucket updates, warp arg-max, barrier wait, block arg-max] and the
+ * number of 32-point sub-buckets visited by all warps. */
+SPSK_API int spsk_fps_set_profile(unsigned long long *counters);
+
 /* F-FPS over a precomputed (b,n,n) distance matrix.  Replaces
  * furthest_point_sampling_with_dist_wrapper (src/sampling.cpp:46-56 -> src/sampling_gpu.cu:256-416).
  * Offsets are 64-bit here (the reference overflows int32 for b*n*n >= 2^31). */

@@ -24,6 +24,7 @@ SIGNATURES = {
     "spsk_built_for_sm": [],
     "spsk_launch_count": [],
     "spsk_farthest_point_sampling": [_i, _i, _i, _p, _p, _p, _p],
+    "spsk_fps_set_profile": [_p],
     "spsk_furthest_point_sampling_with_dist": [_i, _i, _i, _p, _p, _p, _p],
     "spsk_gather_points": [_i, _i, _i, _i, _p, _p, _p, _p],
     "spsk_gather_points_grad": [_i, _i, _i, _i, _p, _p, _p, _p],

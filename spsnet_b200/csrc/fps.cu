@@ -148,7 +148,8 @@ fps_kernel_1024(int n, int m, const float *__restrict__ src, float *__restrict__
 // minima / original indices in registers, orig->sorted position map (u16) in shared memory.
 template <int P>
 __global__ void __launch_bounds__(512, 1)
-fps_pruned_kernel(int n, int m, const float *__restrict__ src, float *__restrict__ temp, int *__restrict__ idx) {
+fps_pruned_kernel(int n, int m, const float *__restrict__ src, float *__restrict__ temp, int *__restrict__ idx,
+                  unsigned long long *__restrict__ prof) {
     constexpr int T = 512, W = 16, NP = T * P;
     constexpr uint32_t s_mask = 1023u, s_log2 = 10u;   // reference block size is 1024 for n >= 1024
     extern __shared__ float smem[];
@@ -263,10 +264,53 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ src, float *__restrict
         }
     }
 
-    int old = 0;
+    // Per iteration (the m-1 iterations are strictly sequential, so this loop is a latency chain):
+    //   1. every lane p < P bounds "its" sub-bucket against the new sample and the warp ballots the buckets to visit;
+    //   2. visited buckets only (a handful out of n/32 after the first few hundred samples) are updated through a
+    //      switch over the set bits -- the running minima live in registers, so the index must be static, and an
+    //      unrolled `if (mask >> p & 1)` ladder costs ~40 cycles per bucket even when nothing is visited;
+    //   3. warp arg-max over the P bucket summaries, one 16-byte slot per warp (value, ~rank, sorted position of the
+    //      bucket's best point), one barrier, arg-max over the 16 slots.  The winner's SORTED POSITION travels with the
+    //      slot, so the next iteration reads its coordinates directly (no index -> position lookup on the chain).
+    // Ties are rare: each arg-max first reduces the value alone and only falls back to the second (rank) reduction
+    // when the maximum is not unique.
+    __shared__ uint4 slots4[2][W];
+    uint32_t bpos = 0u;   // lane p: sorted position of sub-bucket p's best point
     if (tid == 0) idx[0] = 0;
+    int qpos = pos_of[0];   // first sample is point 0 (reference :113-115)
+    // optional profiling (spsk_fps_set_profile): cycles of warp 0 per phase + sub-buckets visited by all warps
+    const bool pf = prof != nullptr && tid == 0;
+    unsigned long long pc[6] = {0, 0, 0, 0, 0, 0};
+    unsigned long long visited = 0;
+
+#define SPSK_FPS_BUCKET(PP)                                                                                      \
+    case PP:                                                                                                     \
+        if (PP < P) {                                                                                            \
+            const int pos = (PP * W + warp) * 32 + lane;                                                         \
+            const float d = sqdist3(sx[pos], sy[pos], sz[pos], x1, y1, z1);                                      \
+            const float t = fminf(d, tmp[PP < P ? PP : 0]);                                                      \
+            tmp[PP < P ? PP : 0] = t;                                                                            \
+            const uint32_t oi = oidx[PP < P ? PP : 0];                                                           \
+            const bool valid = oi != 0xFFFFFFFFu;                                                                \
+            const uint32_t u = (valid && t > 0.f) ? __float_as_uint(t) : 0u;                                     \
+            const uint32_t mx = __reduce_max_sync(0xFFFFFFFFu, u);                                               \
+            const uint32_t eq = __ballot_sync(0xFFFFFFFFu, valid && u == mx);                                    \
+            uint32_t rr = 0u;                                                                                    \
+            int wl = 0;                                                                                          \
+            if (eq != 0u && (eq & (eq - 1u)) == 0u) {                                                            \
+                wl = __ffs(eq) - 1;                                                                              \
+                rr = __shfl_sync(0xFFFFFFFFu, ~fps_rank(oi, s_mask, s_log2), wl);                                \
+            } else if (eq != 0u) {                                                                               \
+                const uint32_t cand = ((eq >> lane) & 1u) ? ~fps_rank(oi, s_mask, s_log2) : 0u;                  \
+                rr = __reduce_max_sync(0xFFFFFFFFu, cand);                                                       \
+                wl = __ffs(__ballot_sync(0xFFFFFFFFu, cand == rr && ((eq >> lane) & 1u))) - 1;                   \
+            }                                                                                                    \
+            if (lane == PP) { bmax_bits = mx; brank = rr; bpos = (uint32_t)((PP * W + warp) * 32 + wl); }        \
+        }                                                                                                        \
+        break;
+
     for (int j = 1; j < m; ++j) {
-        const int qpos = pos_of[old];
+        long long t0 = pf ? clock64() : 0;
         const float x1 = sx[qpos], y1 = sy[qpos], z1 = sz[qpos];
         // box lower bound with the distance's own expression (monotone => rigorous in fp32)
         const float lx = fmaxf(fmaxf(__fsub_rn(bx0, x1), __fsub_rn(x1, bx1)), 0.f);
@@ -274,37 +318,63 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ src, float *__restrict
         const float lz = fmaxf(fmaxf(__fsub_rn(bz0, z1), __fsub_rn(z1, bz1)), 0.f);
         const float lb = __fmaf_rn(lz, lz, __fmaf_rn(lx, lx, __fmul_rn(ly, ly)));
         const bool act = (lane < P) && (lb < __uint_as_float(bmax_bits));
-        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, act);
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            if ((mask >> p) & 1u) {
-                const int pos = (p * W + warp) * 32 + lane;
-                const float d = sqdist3(sx[pos], sy[pos], sz[pos], x1, y1, z1);
-                const float t = fminf(d, tmp[p]);
-                tmp[p] = t;
-                const bool valid = oidx[p] != 0xFFFFFFFFu;
-                const uint32_t u = (valid && t > 0.f) ? __float_as_uint(t) : 0u;
-                const uint32_t mx = __reduce_max_sync(0xFFFFFFFFu, u);
-                const uint32_t cand = (valid && u == mx) ? ~fps_rank(oidx[p], s_mask, s_log2) : 0u;
-                const uint32_t rr = __reduce_max_sync(0xFFFFFFFFu, cand);
-                if (lane == p) { bmax_bits = mx; brank = rr; }
+        uint32_t mask = __ballot_sync(0xFFFFFFFFu, act);
+        if (pf) { const long long t1 = clock64(); pc[0] += t1 - t0; t0 = t1; }
+        if (prof != nullptr && lane == 0) visited += __popc(mask);
+        while (mask) {
+            const int pb = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            switch (pb) {
+                SPSK_FPS_BUCKET(0) SPSK_FPS_BUCKET(1) SPSK_FPS_BUCKET(2) SPSK_FPS_BUCKET(3) SPSK_FPS_BUCKET(4) SPSK_FPS_BUCKET(5)
+                SPSK_FPS_BUCKET(6) SPSK_FPS_BUCKET(7) SPSK_FPS_BUCKET(8) SPSK_FPS_BUCKET(9) SPSK_FPS_BUCKET(10) SPSK_FPS_BUCKET(11)
+                SPSK_FPS_BUCKET(12) SPSK_FPS_BUCKET(13) SPSK_FPS_BUCKET(14) SPSK_FPS_BUCKET(15) SPSK_FPS_BUCKET(16) SPSK_FPS_BUCKET(17)
+                SPSK_FPS_BUCKET(18) SPSK_FPS_BUCKET(19) SPSK_FPS_BUCKET(20) SPSK_FPS_BUCKET(21) SPSK_FPS_BUCKET(22) SPSK_FPS_BUCKET(23)
+                SPSK_FPS_BUCKET(24) SPSK_FPS_BUCKET(25) SPSK_FPS_BUCKET(26) SPSK_FPS_BUCKET(27) SPSK_FPS_BUCKET(28) SPSK_FPS_BUCKET(29)
+                SPSK_FPS_BUCKET(30) SPSK_FPS_BUCKET(31)
+                default: break;
             }
         }
-        // warp best over its P sub-buckets, then the block
+        if (pf) { const long long t1 = clock64(); pc[1] += t1 - t0; t0 = t1; }
+        // warp best over its P sub-buckets
         const uint32_t wv = (lane < P) ? bmax_bits : 0u;
         const uint32_t wm = __reduce_max_sync(0xFFFFFFFFu, wv);
-        const uint32_t wc = (lane < P && bmax_bits == wm) ? brank : 0u;
-        const uint32_t wr = __reduce_max_sync(0xFFFFFFFFu, wc);
-        uint2 *sl = slots[j & 1];
-        if (lane == 0) sl[warp] = make_uint2(wm, wr);
+        const uint32_t weq = __ballot_sync(0xFFFFFFFFu, lane < P && bmax_bits == wm);
+        int wl;
+        if ((weq & (weq - 1u)) == 0u) {
+            wl = __ffs(weq) - 1;
+        } else {
+            const uint32_t wc = ((weq >> lane) & 1u) ? brank : 0u;
+            const uint32_t wr2 = __reduce_max_sync(0xFFFFFFFFu, wc);
+            wl = __ffs(__ballot_sync(0xFFFFFFFFu, ((weq >> lane) & 1u) && brank == wr2)) - 1;
+        }
+        uint4 *sl = slots4[j & 1];
+        if ((int)lane == wl) sl[warp] = make_uint4(bmax_bits, brank, bpos, 0u);
+        if (pf) { const long long t1 = clock64(); pc[2] += t1 - t0; t0 = t1; }
         __syncthreads();
-        const uint2 v = (lane < W) ? sl[lane] : make_uint2(0u, 0u);
+        if (pf) { const long long t1 = clock64(); pc[3] += t1 - t0; t0 = t1; }
+        // block best over the W warp slots
+        const uint4 v = (lane < W) ? sl[lane] : make_uint4(0u, 0u, 0u, 0u);
         const uint32_t m2 = __reduce_max_sync(0xFFFFFFFFu, v.x);
-        const uint32_t c2 = (v.x == m2) ? v.y : 0u;
-        const uint32_t r2 = __reduce_max_sync(0xFFFFFFFFu, c2);
-        const uint32_t rank = ~r2;
-        old = (int)((__brev(rank) & s_mask) | ((rank & ((1u << (32u - s_log2)) - 1u)) << s_log2));
-        if (tid == 0) idx[j] = old;
+        const uint32_t beq = __ballot_sync(0xFFFFFFFFu, lane < W && v.x == m2);
+        int bl;
+        if ((beq & (beq - 1u)) == 0u) {
+            bl = __ffs(beq) - 1;
+        } else {
+            const uint32_t c2 = ((beq >> lane) & 1u) ? v.y : 0u;
+            const uint32_t r2 = __reduce_max_sync(0xFFFFFFFFu, c2);
+            bl = __ffs(__ballot_sync(0xFFFFFFFFu, ((beq >> lane) & 1u) && v.y == r2)) - 1;
+        }
+        qpos = (int)__shfl_sync(0xFFFFFFFFu, v.z, bl);
+        if (warp == 0) {   // the sample's original index, off the critical path: rank(k) = brev(k & s_mask) | (k >> s_log2)
+            const uint32_t rank = ~__shfl_sync(0xFFFFFFFFu, v.y, bl);
+            if (lane == 0) idx[j] = (int)((__brev(rank) & s_mask) | ((rank & ((1u << (32u - s_log2)) - 1u)) << s_log2));
+        }
+        if (pf) { const long long t1 = clock64(); pc[4] += t1 - t0; t0 = t1; }
+    }
+#undef SPSK_FPS_BUCKET
+    if (prof != nullptr) {
+        if (pf) for (int i = 0; i < 5; ++i) atomicAdd(prof + i, pc[i]);
+        if (lane == 0) atomicAdd(prof + 5, visited);
     }
     if (temp) {
 #pragma unroll
@@ -312,6 +382,8 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ src, float *__restrict
             if (oidx[p] != 0xFFFFFFFFu) temp[oidx[p]] = tmp[p];
     }
 }
+
+static unsigned long long *g_fps_prof = nullptr;
 
 template <int P>
 static int launch_fps_pruned(int b, int n, int m, const float *src, float *temp, int *idx, cudaStream_t st) {
@@ -321,7 +393,7 @@ static int launch_fps_pruned(int b, int n, int m, const float *src, float *temp,
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fps_pruned_kernel)");
     }
-    kern<<<b, 512, smem, st>>>(n, m, src, temp, idx);
+    kern<<<b, 512, smem, st>>>(n, m, src, temp, idx, g_fps_prof);
     SPSK_LAUNCH_CHECK("fps_pruned_kernel");
     return SPSK_OK;
 }
@@ -518,6 +590,11 @@ static int fps_dispatch(int b, int n, int m, const float *src, float *temp, int 
 }
 
 }  // namespace spsk
+
+extern "C" int spsk_fps_set_profile(unsigned long long *counters) {
+    spsk::g_fps_prof = counters;
+    return SPSK_OK;
+}
 
 extern "C" int spsk_farthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx,
                                             spsk_stream_t stream) {
