@@ -46,6 +46,25 @@ NCOLS = 5  # [batch_idx, x, y, z, intensity]
 L2_BYTES = 126 * 1024 * 1024
 WORKLOAD = ("IA-SSD KITTI cfg full SA stack (D-FPS 16384->4096->1024, ctr-aware top-k ->512->256, vote, "
             "MSG ball query + shared MLP), batch 16 x 16384 pts per GPU, eval")
+KIND = "kitti"
+
+# BASELINE.json configs: [1] = kitti (the headline, default), [2] = spsnet (stability-aware top-k), [3] = waymo
+WORKLOADS = {
+    "kitti": dict(batch=16, npts=16384, ncols=5, kind="kitti", cfg="kitti_iassd_cfg", bb="IASSD_Backbone", text=WORKLOAD),
+    "spsnet": dict(batch=16, npts=16384, ncols=5, kind="kitti", cfg="kitti_spsnet_cfg", bb="PAGNet_Backbone",
+                   text="SPSNet-IA KITTI cfg: stability-score (sss_aware) top-k sampling in SA layers 2,3 with per-point stds, "
+                        "otherwise the IA-SSD SA stack, batch 16 x 16384 pts per GPU, eval"),
+    "waymo": dict(batch=8, npts=65536, ncols=6, kind="waymo", cfg="waymo_iassd_cfg", bb="IASSD_Backbone",
+                  text="IA-SSD Waymo cfg full SA stack (D-FPS 65536->16384->4096, ctr-aware top-k ->2048->1024, vote, MSG ball "
+                       "query + shared MLP), batch 8 x 65536 pts per GPU, eval"),
+}
+_WL = WORKLOADS["kitti"]
+
+
+def set_workload(name: str):
+    global BATCH, NPTS, NCOLS, WORKLOAD, KIND, _WL
+    _WL = WORKLOADS[name]
+    BATCH, NPTS, NCOLS, WORKLOAD, KIND = _WL["batch"], _WL["npts"], _WL["ncols"], _WL["text"], _WL["kind"]
 
 
 def dist_env():
@@ -110,9 +129,18 @@ def build_net(seed=0):
     from spsnet_b200 import backbone as bb
 
     torch.manual_seed(seed)
-    net = bb.IASSD_Backbone(bb.kitti_iassd_cfg(), num_class=3, input_channels=4)
+    net = getattr(bb, _WL["bb"])(getattr(bb, _WL["cfg"])(), num_class=3, input_channels=NCOLS - 1)
     bb.randomize_bn_stats(net, seed=seed)
     return net.eval()
+
+
+def extra_inputs(device):
+    """Per-point stability `stds` for the SPSNet workload (generator output stand-in)."""
+    if _WL["bb"] != "PAGNet_Backbone":
+        return None
+    from spsnet_b200 import scenes
+
+    return {"stds": torch.from_numpy(scenes.make_stds(77, BATCH, NPTS)).to(device)}
 
 
 def make_pool(rank: int, n_batches: int):
@@ -121,7 +149,7 @@ def make_pool(rank: int, n_batches: int):
 
     pool = []
     for i in range(n_batches):
-        arr = scenes.to_points(scenes.make_batch(100000 * rank + i * BATCH, BATCH, NPTS, "kitti"))
+        arr = scenes.to_points(scenes.make_batch(100000 * rank + i * BATCH, BATCH, NPTS, KIND))
         pool.append(torch.from_numpy(arr).pin_memory())
     return pool
 
@@ -131,7 +159,7 @@ def cpu_baseline(net_cpu, sample_scenes: int):
     from oracle import oracle as O
     from spsnet_b200 import scenes
 
-    pts = scenes.make_batch(0, sample_scenes, NPTS, "kitti")
+    pts = scenes.make_batch(0, sample_scenes, NPTS, KIND)
     O.backbone_forward(net_cpu, pts[:1], dtype=torch.float32)  # warm (page in, build)
     t0 = time.perf_counter()
     O.backbone_forward(net_cpu, pts, dtype=torch.float32)
@@ -181,7 +209,9 @@ def profile_kernels(net, dev_points, steps: int):
     try:
         with torch.no_grad():
             for i in range(steps):
-                net({"batch_size": BATCH, "points": dev_points[i % len(dev_points)]})
+                d = {"batch_size": BATCH, "points": dev_points[i % len(dev_points)]}
+                d.update(extra_inputs("cuda") or {})
+                net(d)
         torch.cuda.synchronize()
     finally:
         for n in names:
@@ -284,11 +314,10 @@ def timed_region(pipe, inputs, steps, warmup, host: bool, world: int):
     wall = time.perf_counter() - t0
     if world > 1:
         dist.barrier()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    from spsnet_b200 import sharding
+
+    # the only communication of the path: SUM of scenes, MAX of the device-timed milliseconds (spsnet_b200/sharding.py)
+    _, ms = sharding.reduce_report(BATCH * steps, e0.elapsed_time(e1), device="cuda")
     return ms, wall
 
 
@@ -348,7 +377,9 @@ def load_reference_backbone(state_dict):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         mod = importlib.import_module("pcdet.models.backbones_3d.IASSD_backbone")
-    net = mod.IASSD_Backbone(bb.kitti_iassd_cfg(), num_class=3, input_channels=4)
+    if _WL["bb"] != "IASSD_Backbone":
+        raise RuntimeError("the reference arm runs IASSD_Backbone workloads (kitti, waymo)")
+    net = mod.IASSD_Backbone(getattr(bb, _WL["cfg"])(), num_class=3, input_channels=NCOLS - 1)
     net.load_state_dict(state_dict)
     return net.eval()
 
@@ -364,7 +395,9 @@ def main():
     ap.add_argument("--pool", type=int, default=0, help="distinct input batches (0 = enough to exceed L2)")
     ap.add_argument("--cpu-sample", type=int, default=8, help="scenes in the cpu_baseline sample (0 = skip)")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS), help="kitti = BASELINE.json configs[1] (headline)")
     args = ap.parse_args()
+    set_workload(args.workload)
     rank, world, local = dist_env()
     args.warmup = max(args.warmup, 3)
 
@@ -430,7 +463,7 @@ def main():
     from spsnet_b200.runtime import BackbonePipeline
 
     net = net.cuda()
-    pipe = BackbonePipeline(net, BATCH, NPTS, NCOLS, depth=args.depth, use_graph=not args.no_graph)
+    pipe = BackbonePipeline(net, BATCH, NPTS, NCOLS, depth=args.depth, use_graph=not args.no_graph, extra_inputs=extra_inputs("cuda"))
     pipe.prepare(dev_pool[0])
     sampler = ClockSampler(local)
     sampler.start()
@@ -475,7 +508,7 @@ def run_reference_cpu(args, rank, world):
     from spsnet_b200 import scenes
 
     sample = 2
-    pts = [scenes.make_batch(i * sample, sample, NPTS, "kitti") for i in range(2)]
+    pts = [scenes.make_batch(i * sample, sample, NPTS, KIND) for i in range(2)]
     for _ in range(min(args.warmup, 1)):
         O.backbone_forward(net, pts[0][:1], dtype=torch.float32)
     steps = min(args.steps, 5)

@@ -11,7 +11,8 @@ from spsnet_b200._lib import lib
 def main():
     prof = "--prof" in sys.argv
     for B, N, M, kind in [(16, 16384, 4096, "kitti"), (16, 4096, 1024, "kitti"), (8, 65536, 16384, "waymo"), (8, 16384, 4096, "waymo")]:
-        xyz = torch.from_numpy(np.ascontiguousarray(scenes.make_batch(5, B, max(N, 16384), kind)[:, :N, :3])).cuda().contiguous()
+        seed = 0 if "--bench-data" in sys.argv else 5
+        xyz = torch.from_numpy(np.ascontiguousarray(scenes.make_batch(seed, B, max(N, 16384), kind)[:, :N, :3])).cuda().contiguous()
         for _ in range(2): pu.furthest_point_sample(xyz, M)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

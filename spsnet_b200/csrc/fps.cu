@@ -146,25 +146,48 @@ fps_kernel_1024(int n, int m, const float *__restrict__ src, float *__restrict__
 // 512 threads, P points per lane (P*512 >= n), sub-bucket s = p*16 + warp (round-robin over warps so that
 // neighbouring sub-buckets are processed by different warps), sorted xyz in shared memory (SoA), running
 // minima / original indices in registers, orig->sorted position map (u16) in shared memory.
-template <int P>
+// CL = true: a thread-block CLUSTER per scene (n > 16384, e.g. Waymo's 65536 points): CTA r of the cluster owns the
+// contiguous index range [r*chunk, (r+1)*chunk), prunes and updates it exactly like the single-CTA kernel, and the
+// per-iteration arg-max is completed across the cluster through distributed shared memory: every warp stores its
+// (value, ~rank, x, y, z) record into the record table of EVERY CTA of the cluster (st.shared::cluster), one
+// barrier.cluster arrive/wait per iteration, then each warp reduces the csize*16 records locally.  The winner's
+// coordinates travel with the record, so no CTA ever reads another CTA's points.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_v4(const void *local_ptr, uint32_t cta, uint4 v) {
+    const uint32_t la = (uint32_t)__cvta_generic_to_shared(local_ptr);
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(cta));
+    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int P, bool CL, int LADDER>
 __global__ void __launch_bounds__(512, 1)
-fps_pruned_kernel(int n, int m, const float *__restrict__ src, float *__restrict__ temp, int *__restrict__ idx,
+fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__restrict__ temp, int *__restrict__ idx,
                   unsigned long long *__restrict__ prof) {
     constexpr int T = 512, W = 16, NP = T * P;
     constexpr uint32_t s_mask = 1023u, s_log2 = 10u;   // reference block size is 1024 for n >= 1024
     extern __shared__ float smem[];
-    __shared__ uint2 slots[2][32];
     __shared__ float red[6][W];
     float *sx = smem, *sy = smem + NP, *sz = smem + 2 * NP;
     uint32_t *keys = reinterpret_cast<uint32_t *>(smem);              // sort phase only (aliases sx)
     unsigned short *pos_of = reinterpret_cast<unsigned short *>(smem + 3 * NP);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const size_t scene = blockIdx.x;
-    const float *base = src + scene * (size_t)n * 3;
-    if (temp) temp += scene * (size_t)n;
+    const uint32_t crank = CL ? cluster_ctarank() : 0u, csize = CL ? cluster_nctarank() : 1u;
+    const size_t scene = CL ? blockIdx.x / csize : blockIdx.x;
+    const int chunk = CL ? (n_scene + (int)csize - 1) / (int)csize : n_scene;
+    const int gbase = (int)crank * chunk;                       // first scene index owned by this CTA
+    const int n = max(0, min(n_scene - gbase, chunk));          // points owned by this CTA (<= NP)
+    const float *scene_base = src + scene * (size_t)n_scene * 3;
+    const float *base = scene_base + (size_t)gbase * 3;
+    if (temp) temp += scene * (size_t)n_scene;   // indexed with scene indices
     idx += scene * (size_t)m;
 
-    // ---- scene bounding box
+    // ---- bounding box of the owned points (only scales the Morton cells: any box gives the same samples)
     float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
     for (int i = tid; i < n; i += T) {
 #pragma unroll
@@ -232,13 +255,13 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ src, float *__restrict
     for (int p = 0; p < P; ++p) {
         const int pos = (p * W + warp) * 32 + lane;
         const bool valid = oidx[p] != 0xFFFFFFFFu;
-        const uint32_t oi = valid ? (oidx[p] & 0x3FFFu) : 0u;
-        oidx[p] = valid ? oi : 0xFFFFFFFFu;
+        const uint32_t oi = valid ? (oidx[p] & 0x3FFFu) : 0u;   // index inside the owned range
+        oidx[p] = valid ? oi + (uint32_t)gbase : 0xFFFFFFFFu;   // index inside the scene (decides the tie-break rank)
         sx[pos] = valid ? __ldg(base + (size_t)oi * 3) : 0.f;
         sy[pos] = valid ? __ldg(base + (size_t)oi * 3 + 1) : 0.f;
         sz[pos] = valid ? __ldg(base + (size_t)oi * 3 + 2) : 0.f;
-        tmp[p] = valid ? (temp ? temp[oi] : 1e10f) : -1.f;
-        if (valid) pos_of[oi] = (unsigned short)pos;
+        tmp[p] = valid ? (temp ? temp[oidx[p]] : 1e10f) : -1.f;
+        if (!CL && valid) pos_of[oi] = (unsigned short)pos;
     }
     __syncthreads();
     // ---- sub-bucket boxes: lane p keeps the box / bmax / best-rank of slot p of this warp
@@ -274,12 +297,15 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ src, float *__restrict
     //      slot, so the next iteration reads its coordinates directly (no index -> position lookup on the chain).
     // Ties are rare: each arg-max first reduces the value alone and only falls back to the second (rank) reduction
     // when the maximum is not unique.
-    __shared__ uint4 slots4[2][W];
+    __shared__ uint2 slots2[2][W];            // single CTA: one (value, ~rank) slot per warp
+    __shared__ uint4 crec[CL ? 2 : 1][CL ? 8 * W : 1][2];   // cluster: [parity][cta * W + warp] = {value, ~rank, x, y | z, -, -, -}
     uint32_t bpos = 0u;   // lane p: sorted position of sub-bucket p's best point
-    if (tid == 0) idx[0] = 0;
-    int qpos = pos_of[0];   // first sample is point 0 (reference :113-115)
+    if (crank == 0 && tid == 0) idx[0] = 0;
+    int qpos = CL ? 0 : pos_of[0];   // first sample is point 0 (reference :113-115)
+    float qx = __ldg(scene_base), qy = __ldg(scene_base + 1), qz = __ldg(scene_base + 2);
+    if (CL) cluster_sync_all();      // every CTA of the cluster is resident before the first remote store
     // optional profiling (spsk_fps_set_profile): cycles of warp 0 per phase + sub-buckets visited by all warps
-    const bool pf = prof != nullptr && tid == 0;
+    const bool pf = prof != nullptr && tid == 0 && !CL;
     unsigned long long pc[6] = {0, 0, 0, 0, 0, 0};
     unsigned long long visited = 0;
 
@@ -294,24 +320,17 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ src, float *__restrict
             const bool valid = oi != 0xFFFFFFFFu;                                                                \
             const uint32_t u = (valid && t > 0.f) ? __float_as_uint(t) : 0u;                                     \
             const uint32_t mx = __reduce_max_sync(0xFFFFFFFFu, u);                                               \
-            const uint32_t eq = __ballot_sync(0xFFFFFFFFu, valid && u == mx);                                    \
-            uint32_t rr = 0u;                                                                                    \
-            int wl = 0;                                                                                          \
-            if (eq != 0u && (eq & (eq - 1u)) == 0u) {                                                            \
-                wl = __ffs(eq) - 1;                                                                              \
-                rr = __shfl_sync(0xFFFFFFFFu, ~fps_rank(oi, s_mask, s_log2), wl);                                \
-            } else if (eq != 0u) {                                                                               \
-                const uint32_t cand = ((eq >> lane) & 1u) ? ~fps_rank(oi, s_mask, s_log2) : 0u;                  \
-                rr = __reduce_max_sync(0xFFFFFFFFu, cand);                                                       \
-                wl = __ffs(__ballot_sync(0xFFFFFFFFu, cand == rr && ((eq >> lane) & 1u))) - 1;                   \
-            }                                                                                                    \
-            if (lane == PP) { bmax_bits = mx; brank = rr; bpos = (uint32_t)((PP * W + warp) * 32 + wl); }        \
+            const uint32_t cand = (valid && u == mx) ? ~fps_rank(oi, s_mask, s_log2) : 0u;                       \
+            const uint32_t rr = __reduce_max_sync(0xFFFFFFFFu, cand);                                            \
+            uint32_t bp = 0u;   /* cluster mode only: the best point's position travels with the summary */      \
+            if (CL) bp = __reduce_max_sync(0xFFFFFFFFu, (valid && cand == rr) ? (uint32_t)pos : 0u);             \
+            if (lane == PP) { bmax_bits = mx; brank = rr; bpos = bp; }                                           \
         }                                                                                                        \
         break;
 
     for (int j = 1; j < m; ++j) {
         long long t0 = pf ? clock64() : 0;
-        const float x1 = sx[qpos], y1 = sy[qpos], z1 = sz[qpos];
+        const float x1 = CL ? qx : sx[qpos], y1 = CL ? qy : sy[qpos], z1 = CL ? qz : sz[qpos];
         // box lower bound with the distance's own expression (monotone => rigorous in fp32)
         const float lx = fmaxf(fmaxf(__fsub_rn(bx0, x1), __fsub_rn(x1, bx1)), 0.f);
         const float ly = fmaxf(fmaxf(__fsub_rn(by0, y1), __fsub_rn(y1, by1)), 0.f);
@@ -321,55 +340,101 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ src, float *__restrict
         uint32_t mask = __ballot_sync(0xFFFFFFFFu, act);
         if (pf) { const long long t1 = clock64(); pc[0] += t1 - t0; t0 = t1; }
         if (prof != nullptr && lane == 0) visited += __popc(mask);
-        while (mask) {
-            const int pb = __ffs(mask) - 1;
-            mask &= mask - 1u;
-            switch (pb) {
-                SPSK_FPS_BUCKET(0) SPSK_FPS_BUCKET(1) SPSK_FPS_BUCKET(2) SPSK_FPS_BUCKET(3) SPSK_FPS_BUCKET(4) SPSK_FPS_BUCKET(5)
-                SPSK_FPS_BUCKET(6) SPSK_FPS_BUCKET(7) SPSK_FPS_BUCKET(8) SPSK_FPS_BUCKET(9) SPSK_FPS_BUCKET(10) SPSK_FPS_BUCKET(11)
-                SPSK_FPS_BUCKET(12) SPSK_FPS_BUCKET(13) SPSK_FPS_BUCKET(14) SPSK_FPS_BUCKET(15) SPSK_FPS_BUCKET(16) SPSK_FPS_BUCKET(17)
-                SPSK_FPS_BUCKET(18) SPSK_FPS_BUCKET(19) SPSK_FPS_BUCKET(20) SPSK_FPS_BUCKET(21) SPSK_FPS_BUCKET(22) SPSK_FPS_BUCKET(23)
-                SPSK_FPS_BUCKET(24) SPSK_FPS_BUCKET(25) SPSK_FPS_BUCKET(26) SPSK_FPS_BUCKET(27) SPSK_FPS_BUCKET(28) SPSK_FPS_BUCKET(29)
-                SPSK_FPS_BUCKET(30) SPSK_FPS_BUCKET(31)
-                default: break;
+#define SPSK_FPS_ALL_BUCKETS                                                                                              \
+    SPSK_FPS_BUCKET(0) SPSK_FPS_BUCKET(1) SPSK_FPS_BUCKET(2) SPSK_FPS_BUCKET(3) SPSK_FPS_BUCKET(4) SPSK_FPS_BUCKET(5)        \
+    SPSK_FPS_BUCKET(6) SPSK_FPS_BUCKET(7) SPSK_FPS_BUCKET(8) SPSK_FPS_BUCKET(9) SPSK_FPS_BUCKET(10) SPSK_FPS_BUCKET(11)      \
+    SPSK_FPS_BUCKET(12) SPSK_FPS_BUCKET(13) SPSK_FPS_BUCKET(14) SPSK_FPS_BUCKET(15) SPSK_FPS_BUCKET(16) SPSK_FPS_BUCKET(17)  \
+    SPSK_FPS_BUCKET(18) SPSK_FPS_BUCKET(19) SPSK_FPS_BUCKET(20) SPSK_FPS_BUCKET(21) SPSK_FPS_BUCKET(22) SPSK_FPS_BUCKET(23)  \
+    SPSK_FPS_BUCKET(24) SPSK_FPS_BUCKET(25) SPSK_FPS_BUCKET(26) SPSK_FPS_BUCKET(27) SPSK_FPS_BUCKET(28) SPSK_FPS_BUCKET(29)  \
+    SPSK_FPS_BUCKET(30) SPSK_FPS_BUCKET(31)
+        if (LADDER == 2) {
+            // two-level ladder: groups of 8 sub-buckets, then the bits of a non-empty group
+#pragma unroll
+            for (int g = 0; g < P; g += 8) {
+                if ((mask >> g) & 0xFFu) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int pb = g + q;
+                        if (pb < P && ((mask >> pb) & 1u)) {
+                            switch (pb) { SPSK_FPS_ALL_BUCKETS default: break; }
+                        }
+                    }
+                }
+            }
+        } else if (LADDER == 1) {
+            // few sub-buckets per warp: a straight ladder of bit tests (the switch below costs an indirect branch per visit)
+            if (mask) {
+#pragma unroll
+                for (int pb = 0; pb < P; ++pb) {
+                    if ((mask >> pb) & 1u) {
+                        switch (pb) { SPSK_FPS_ALL_BUCKETS default: break; }
+                    }
+                }
+            }
+        } else {
+            while (mask) {
+                const int pb = __ffs(mask) - 1;
+                mask &= mask - 1u;
+                switch (pb) { SPSK_FPS_ALL_BUCKETS default: break; }
             }
         }
+#undef SPSK_FPS_ALL_BUCKETS
         if (pf) { const long long t1 = clock64(); pc[1] += t1 - t0; t0 = t1; }
         // warp best over its P sub-buckets
         const uint32_t wv = (lane < P) ? bmax_bits : 0u;
         const uint32_t wm = __reduce_max_sync(0xFFFFFFFFu, wv);
-        const uint32_t weq = __ballot_sync(0xFFFFFFFFu, lane < P && bmax_bits == wm);
-        int wl;
-        if ((weq & (weq - 1u)) == 0u) {
-            wl = __ffs(weq) - 1;
+        const uint32_t wc = (lane < P && bmax_bits == wm) ? brank : 0u;
+        const uint32_t wr = __reduce_max_sync(0xFFFFFFFFu, wc);
+        // (value, ~rank) identifies one point, so exactly one lane matches: a max-reduction moves its position
+        uint32_t wpos = 0u;
+        if (CL) wpos = __reduce_max_sync(0xFFFFFFFFu, (lane < P && bmax_bits == wm && brank == wr) ? bpos : 0u);
+        if (!CL) {
+            uint2 *sl = slots2[j & 1];
+            if (lane == 0) sl[warp] = make_uint2(wm, wr);
+            if (pf) { const long long t1 = clock64(); pc[2] += t1 - t0; t0 = t1; }
+            __syncthreads();
+            if (pf) { const long long t1 = clock64(); pc[3] += t1 - t0; t0 = t1; }
+            // block best over the W warp slots
+            const uint2 v = (lane < W) ? sl[lane] : make_uint2(0u, 0u);
+            const uint32_t m2 = __reduce_max_sync(0xFFFFFFFFu, v.x);
+            const uint32_t r2 = __reduce_max_sync(0xFFFFFFFFu, (lane < W && v.x == m2) ? v.y : 0u);
+            // the sample's original index: rank(k) = brev(k & s_mask) | (k >> s_log2); its sorted position through the map
+            const uint32_t rank = ~r2;
+            const int old = (int)((__brev(rank) & s_mask) | ((rank & ((1u << (32u - s_log2)) - 1u)) << s_log2));
+            qpos = pos_of[old];
+            if (tid == 0) idx[j] = old;
+            if (pf) { const long long t1 = clock64(); pc[4] += t1 - t0; t0 = t1; }
         } else {
-            const uint32_t wc = ((weq >> lane) & 1u) ? brank : 0u;
-            const uint32_t wr2 = __reduce_max_sync(0xFFFFFFFFu, wc);
-            wl = __ffs(__ballot_sync(0xFFFFFFFFu, ((weq >> lane) & 1u) && brank == wr2)) - 1;
-        }
-        uint4 *sl = slots4[j & 1];
-        if ((int)lane == wl) sl[warp] = make_uint4(bmax_bits, brank, bpos, 0u);
-        if (pf) { const long long t1 = clock64(); pc[2] += t1 - t0; t0 = t1; }
-        __syncthreads();
-        if (pf) { const long long t1 = clock64(); pc[3] += t1 - t0; t0 = t1; }
-        // block best over the W warp slots
-        const uint4 v = (lane < W) ? sl[lane] : make_uint4(0u, 0u, 0u, 0u);
-        const uint32_t m2 = __reduce_max_sync(0xFFFFFFFFu, v.x);
-        const uint32_t beq = __ballot_sync(0xFFFFFFFFu, lane < W && v.x == m2);
-        int bl;
-        if ((beq & (beq - 1u)) == 0u) {
-            bl = __ffs(beq) - 1;
-        } else {
-            const uint32_t c2 = ((beq >> lane) & 1u) ? v.y : 0u;
+            // this warp's record -> the record table of every CTA of the cluster
+            const uint32_t rv = wm, rr = wr, rp = wpos;
+            const float rx = sx[rp], ry = sy[rp], rz = sz[rp];
+            uint4(*tab)[2] = crec[j & 1];
+            if (lane < csize) {
+                uint4 *dst = tab[crank * W + warp];
+                st_cluster_v4(dst, lane, make_uint4(rv, rr, __float_as_uint(rx), __float_as_uint(ry)));
+                st_cluster_v4(dst + 1, lane, make_uint4(__float_as_uint(rz), 0u, 0u, 0u));
+            }
+            cluster_sync_all();
+            // arg-max over the csize * W records (<= 4 per lane)
+            const int nrec = (int)csize * W;
+            uint32_t bv = 0u, br = 0u;
+            int bi = -1;
+            for (int i = lane; i < nrec; i += 32) {
+                const uint4 a = tab[i][0];
+                if (bi < 0 || a.x > bv || (a.x == bv && a.y > br)) { bv = a.x; br = a.y; bi = i; }
+            }
+            const uint32_t m2 = __reduce_max_sync(0xFFFFFFFFu, bi >= 0 ? bv : 0u);
+            const uint32_t c2 = (bi >= 0 && bv == m2) ? br : 0u;
             const uint32_t r2 = __reduce_max_sync(0xFFFFFFFFu, c2);
-            bl = __ffs(__ballot_sync(0xFFFFFFFFu, ((beq >> lane) & 1u) && v.y == r2)) - 1;
+            const int bl = __ffs(__ballot_sync(0xFFFFFFFFu, bi >= 0 && bv == m2 && br == r2)) - 1;
+            const int wi = __shfl_sync(0xFFFFFFFFu, bi, bl);
+            const uint4 w0 = tab[wi][0], w1 = tab[wi][1];
+            qx = __uint_as_float(w0.z); qy = __uint_as_float(w0.w); qz = __uint_as_float(w1.x);
+            if (crank == 0 && tid == 0) {
+                const uint32_t rank = ~w0.y;
+                idx[j] = (int)((__brev(rank) & s_mask) | ((rank & ((1u << (32u - s_log2)) - 1u)) << s_log2));
+            }
         }
-        qpos = (int)__shfl_sync(0xFFFFFFFFu, v.z, bl);
-        if (warp == 0) {   // the sample's original index, off the critical path: rank(k) = brev(k & s_mask) | (k >> s_log2)
-            const uint32_t rank = ~__shfl_sync(0xFFFFFFFFu, v.y, bl);
-            if (lane == 0) idx[j] = (int)((__brev(rank) & s_mask) | ((rank & ((1u << (32u - s_log2)) - 1u)) << s_log2));
-        }
-        if (pf) { const long long t1 = clock64(); pc[4] += t1 - t0; t0 = t1; }
     }
 #undef SPSK_FPS_BUCKET
     if (prof != nullptr) {
@@ -385,17 +450,45 @@ fps_pruned_kernel(int n, int m, const float *__restrict__ src, float *__restrict
 
 static unsigned long long *g_fps_prof = nullptr;
 
-template <int P>
-static int launch_fps_pruned(int b, int n, int m, const float *src, float *temp, int *idx, cudaStream_t st) {
-    const size_t smem = sizeof(float) * 3 * 512 * P + sizeof(unsigned short) * 512 * P;
-    auto kern = fps_pruned_kernel<P>;
-    if (smem + 4096 > 48 * 1024) {
+template <int P, bool CL, int LADDER>
+static int launch_fps_pruned_v(int b, int n, int m, int csize, const float *src, float *temp, int *idx, cudaStream_t st) {
+    const size_t smem = sizeof(float) * 3 * 512 * P + (CL ? 0 : sizeof(unsigned short) * 512 * P);   // xyz (+ index -> position map)
+    auto kern = fps_pruned_kernel<P, CL, LADDER>;
+    if (smem + 8192 > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fps_pruned_kernel)");
     }
-    kern<<<b, 512, smem, st>>>(n, m, src, temp, idx, g_fps_prof);
+    if (!CL) {
+        kern<<<b, 512, smem, st>>>(n, m, src, temp, idx, g_fps_prof);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(b * csize));
+        cfg.blockDim = dim3(512);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)csize;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, n, m, src, temp, idx, g_fps_prof);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(fps_pruned_kernel, cluster)");
+    }
     SPSK_LAUNCH_CHECK("fps_pruned_kernel");
     return SPSK_OK;
+}
+
+// bucket dispatch: ladder of bit tests for few sub-buckets per warp, switch over the set bits for many
+// (SPSK_FPS_DISPATCH=ladder|switch overrides, for A/B measurements)
+template <int P, bool CL>
+static int launch_fps_pruned(int b, int n, int m, int csize, const float *src, float *temp, int *idx, cudaStream_t st) {
+    int mode = 2;   // 1 = ladder, 2 = two-level ladder (fastest at every P on B200), 0 = switch over set bits
+    if (const char *e = getenv("SPSK_FPS_DISPATCH")) mode = e[0] == 'l' ? 1 : (e[0] == 'g' ? 2 : 0);
+    if (mode == 1) return launch_fps_pruned_v<P, CL, 1>(b, n, m, csize, src, temp, idx, st);
+    if (mode == 2) return launch_fps_pruned_v<P, CL, 2>(b, n, m, csize, src, temp, idx, st);
+    return launch_fps_pruned_v<P, CL, 0>(b, n, m, csize, src, temp, idx, st);
 }
 
 // Small scenes, n < 1024: the reference block has S = 2^floor(log2 n) < 1024 threads; T = blockDim.x =
@@ -564,19 +657,31 @@ static int fps_dispatch(int b, int n, int m, const float *src, float *temp, int 
     const int threads = S < 32 ? 32 : S;  // multiple of S, >= one warp; 1024 for n >= 1024
     const int per_thread = (n + threads - 1) / threads;
     const bool fits = per_thread <= 16;  // 16 x 1024 padded points of SoA xyz = 192 KB of shared memory
+    // n > 16384 (Waymo-shaped scenes): one 8-CTA cluster per scene, each CTA prunes its own slice, DSMEM arg-max
+    // cluster size: the fewest CTAs that hold the scene (16384 points each) -- least SM-time per scene, which is what a
+    // pipelined serving loop pays; SPSK_FPS_CLUSTER=8 trades SMs for latency
+    if (!DISTMAT && threads == 1024 && n > 16384 && n <= 8 * 16384 && !fps_dense_forced()) {
+        int cl = n <= 2 * 16384 ? 2 : (n <= 4 * 16384 ? 4 : 8);
+        if (const char *e = getenv("SPSK_FPS_CLUSTER")) { const int v = atoi(e); if ((v == 2 || v == 4 || v == 8) && v >= cl) cl = v; }
+        const int per_cta = (n + cl - 1) / cl;
+        if (per_cta <= 2048) return launch_fps_pruned<4, true>(b, n, m, cl, src, temp, idx, st);
+        if (per_cta <= 4096) return launch_fps_pruned<8, true>(b, n, m, cl, src, temp, idx, st);
+        if (per_cta <= 8192) return launch_fps_pruned<16, true>(b, n, m, cl, src, temp, idx, st);
+        return launch_fps_pruned<32, true>(b, n, m, cl, src, temp, idx, st);
+    }
     if (!fits) {
         SPSK_REQUIRE(temp != nullptr, SPSK_ERR_UNSUPPORTED,
-                     "fps: n=%d exceeds the on-chip variant (<=16384); pass a (b,n) `temp` scratch filled with 1e10", n);
+                     "fps: n=%d exceeds the on-chip variants (<=131072); pass a (b,n) `temp` scratch filled with 1e10", n);
         fps_generic_kernel<DISTMAT><<<b, threads, 0, st>>>(n, m, s_mask, s_log2, src, temp, idx);
         SPSK_LAUNCH_CHECK("fps_generic_kernel");
         return SPSK_OK;
     }
     if (!DISTMAT && threads == 1024 && n <= 16384 && !fps_dense_forced()) {
-        if (n <= 1024) return launch_fps_pruned<2>(b, n, m, src, temp, idx, st);
-        if (n <= 2048) return launch_fps_pruned<4>(b, n, m, src, temp, idx, st);
-        if (n <= 4096) return launch_fps_pruned<8>(b, n, m, src, temp, idx, st);
-        if (n <= 8192) return launch_fps_pruned<16>(b, n, m, src, temp, idx, st);
-        return launch_fps_pruned<32>(b, n, m, src, temp, idx, st);
+        if (n <= 1024) return launch_fps_pruned<2, false>(b, n, m, 1, src, temp, idx, st);
+        if (n <= 2048) return launch_fps_pruned<4, false>(b, n, m, 1, src, temp, idx, st);
+        if (n <= 4096) return launch_fps_pruned<8, false>(b, n, m, 1, src, temp, idx, st);
+        if (n <= 8192) return launch_fps_pruned<16, false>(b, n, m, 1, src, temp, idx, st);
+        return launch_fps_pruned<32, false>(b, n, m, 1, src, temp, idx, st);
     }
     if (threads == 1024) {
         if (per_thread <= 1) return launch_fps_1024<1, !DISTMAT, DISTMAT>(b, n, m, src, temp, idx, st);

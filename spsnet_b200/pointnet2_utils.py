@@ -4,7 +4,7 @@ Same public names, positional signatures, return dtypes and autograd behaviour
 (reference pointnet2_utils.py:36,65,101,133,181,225,256,287-384); every native call goes through the
 C-ABI of include/spsk.h (libspsk.so, hand-written sm_100a CUDA) on torch's current stream.  Differences,
 all deliberate: preconditions raise instead of `assert`/`exit(-1)`; kernels are stream-explicit; FPS
-keeps its running minima on chip (no `temp` tensor unless n > 16384).
+keeps its running minima on chip (no `temp` tensor unless n > 131072).
 """
 from __future__ import annotations
 
@@ -24,7 +24,7 @@ __all__ = [
     "score_topk", "gather_rows", "ball_query_msg",
 ]
 
-FPS_ONCHIP_MAX_N = 16384
+FPS_ONCHIP_MAX_N = 131072  # <= 16384: one CTA per scene; <= 131072: one 8-CTA cluster per scene; above: `temp` scratch in L2
 
 
 def _stream() -> int:

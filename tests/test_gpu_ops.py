@@ -50,12 +50,37 @@ def test_fps_ties_grid(oracle, ref_ops):
             np.testing.assert_array_equal(ref_ops.utils.furthest_point_sample(dev(xyz), m).cpu().numpy(), got)
 
 
-def test_fps_large_n_generic(oracle):
+@pytest.mark.parametrize("b,n,m,kind", [(2, 16385, 300, "kitti"), (2, 20000, 500, "waymo"), (2, 65536, 1500, "waymo"),
+                                        (1, 131072, 200, "waymo"), (3, 40001, 257, "waymo")])
+def test_fps_cluster_vs_oracle(oracle, ref_ops, b, n, m, kind):
+    """n > 16384: one 8-CTA cluster per scene with a DSMEM arg-max (Waymo-shaped scenes) -- same samples, bit-exact."""
     from spsnet_b200 import pointnet2_utils as pu
 
-    xyz = _xyz(1, 20000, seed=3, kind="waymo")
-    got = pu.furthest_point_sample(dev(xyz), 300).cpu().numpy()
-    np.testing.assert_array_equal(got, oracle.fps(xyz, 300))
+    xyz = _xyz(b, n, seed=n, kind=kind)
+    got = pu.furthest_point_sample(dev(xyz), m).cpu().numpy()
+    want = oracle.fps(xyz, m)
+    np.testing.assert_array_equal(got, want)
+    if ref_ops is not None and n <= 65536:
+        np.testing.assert_array_equal(ref_ops.utils.furthest_point_sample(dev(xyz), m).cpu().numpy(), want)
+
+
+def test_fps_cluster_ties(oracle):
+    """Lattice points spread over the 8 CTAs of a cluster: the tie-break key must hold across CTAs."""
+    from spsnet_b200 import pointnet2_utils as pu
+
+    rng = np.random.default_rng(9)
+    xyz = rng.integers(0, 7, (2, 40000, 3)).astype(np.float32)
+    got = pu.furthest_point_sample(dev(xyz), 400).cpu().numpy()
+    np.testing.assert_array_equal(got, oracle.fps(xyz, 400))
+
+
+def test_fps_large_n_generic(oracle):
+    """n > 131072: running minima in the caller-provided `temp` scratch (L2), same samples."""
+    from spsnet_b200 import pointnet2_utils as pu
+
+    xyz = _xyz(1, 140000, seed=3, kind="waymo")
+    got = pu.furthest_point_sample(dev(xyz), 120).cpu().numpy()
+    np.testing.assert_array_equal(got, oracle.fps(xyz, 120))
 
 
 @pytest.mark.parametrize("b,n,m", [(2, 64, 20), (2, 1000, 128), (1, 2048, 512)])
