@@ -195,10 +195,12 @@ def profile_kernels(net, dev_points, steps: int):
                 g = a[0]._obj
                 nl = int(g.nlayers)
                 a = (int(g.b) * int(g.m) * int(g.nsample), [int(g.kpad[i]) for i in range(nl)], [int(g.cpad[i]) for i in range(nl)],
-                     int(g.cout_last), int(g.split))
+                     int(g.cout_last), int(g.split), int(g.c_feat) + (3 if g.use_xyz else 0))
             elif name == "spsk_pw_mma_forward":
                 g = a[0]._obj
                 a = (int(g.rows), int(g.k), int(g.n))
+            elif name.startswith("spsk_ball_query_msg"):
+                a = tuple(a[:5]) + ([int(a[5][i]) for i in range(int(a[3]))],)
             records.append((name, a, e0, e1))
             return rc
         return inner
@@ -236,43 +238,89 @@ def profile_kernels(net, dev_points, steps: int):
     return table, steps
 
 
-def roofline_from_table(table, steps, peaks):
-    """Pick the dominant kernel by time share and state its roofline (algorithmic work / CUDA-event time)."""
-    total = sum(t["ms"] for t in table.values())
-    rows = []
-    for key, t in sorted(table.items(), key=lambda kv: -kv[1]["ms"]):
-        rows.append({"kernel": key, "ms_per_step": t["ms"] / steps, "launches_per_step": t["launches"] / steps,
-                     "share": t["ms"] / total})
-    top_key, top = max(table.items(), key=lambda kv: kv[1]["ms"])
-    avg_s = top["ms"] / top["launches"] / 1e3
-    a = top["args"]
-    hbm = peaks.get("hbm_gbs", 6650.0)
-    if top_key.startswith("spsk_farthest_point_sampling"):
+N_SMS = 148
+
+
+def _fps_sms(b, n):
+    return b * (1 if n <= 16384 else (2 if n <= 32768 else (4 if n <= 65536 else 8)))
+
+
+def _roof_entry(key, t, peaks, traffic):
+    """Roofline of one kernel class: ALGORITHMIC work per launch / mean CUDA-event duration."""
+    avg_s = t["ms"] / t["launches"] / 1e3
+    a = t["args"]
+    hbm = peaks.get("hbm_gbs", 6650.0)          # measured copy bandwidth, GB/s
+    tens = peaks.get("bf16_tflops", 1500.0)     # measured dense bf16 (burst: these kernels are timed alone), TFLOP/s
+    sms = N_SMS
+    e = {"kernel": key, "avg_us": avg_s * 1e6}
+    if key.startswith("spsk_farthest_point_sampling"):
         b, n, m = a[0], a[1], a[2]
-        alg_bytes = b * (n * 12 + m * 4)  # read xyz once + write idx (SURVEY.md 8d)
+        sms = _fps_sms(b, n)
+        alg_bytes = b * (n * 12 + m * 4)  # read xyz once + write idx
         pairs = b * n * (m - 1)
-        lane_peak = 148 * 128 * 1.965e9  # fp32 lane-ops/s at max clock
-        roof = {"kernel": top_key, "bound": "hbm", "achieved": alg_bytes / avg_s / 1e9, "peak": hbm, "unit": "GB/s",
-                "frac": alg_bytes / avg_s / 1e9 / hbm, "traffic": None,
-                "note": "FPS is latency-bound (m-1 sequential arg-max steps, one CTA per scene): neither HBM nor tensor "
-                        "roofline applies; see us_per_iter / lane_frac",
-                "us_per_iter": avg_s * 1e6 / max(m - 1, 1), "pair_evals_per_s": pairs / avg_s,
-                "lane_frac": pairs * 10 / avg_s / lane_peak, "sms_used": b}
-    elif top_key.startswith("spsk_grouped_linear") or top_key.startswith("spsk_pointwise_linear"):
-        # FFMA GEMM: flops = 2 * rows * cin * cout ; fp32 CUDA-core peak 74.4 TFLOP/s (SURVEY.md 8d)
-        if top_key.startswith("spsk_grouped_linear"):
+        lane_peak = N_SMS * 128 * 1.965e9  # fp32 lane-ops/s at max clock
+        e.update(bound="hbm", achieved=alg_bytes / avg_s / 1e9, peak=hbm, unit="GB/s",
+                 note="FPS is latency-bound (m-1 strictly sequential arg-max steps, one CTA or CTA-cluster per scene): neither "
+                      "the HBM nor the tensor roofline applies; see us_per_iter / cycles_per_iter / lane_frac",
+                 us_per_iter=avg_s * 1e6 / max(m - 1, 1), cycles_per_iter=avg_s * 1.965e9 / max(m - 1, 1),
+                 pair_evals_per_s=pairs / avg_s, lane_frac=pairs * 10 / avg_s / lane_peak)
+    elif key.startswith("spsk_sa_mma_forward"):
+        rows_n, kpad, cpad, cout_last, split, k0 = a
+        widths = [k0] + list(cpad[:-1]) + [cout_last]
+        flops = 2.0 * rows_n * sum(x * y for x, y in zip(widths[:-1], widths[1:]))
+        e.update(bound="tensor", achieved=flops / avg_s / 1e12, peak=tens, unit="TFLOP/s",
+                 note="fused gather + shared MLP + max-pool; algorithmic flops from the true layer widths (split-fp16 chains "
+                      "issue 3x these on the tensor cores); peak = measured dense bf16 cuBLAS throughput")
+    elif key.startswith("spsk_pw_mma_forward"):
+        rows_n, k, n = a
+        e.update(bound="tensor", achieved=2.0 * rows_n * k * n / avg_s / 1e12, peak=tens, unit="TFLOP/s",
+                 note="point-wise Conv1d GEMM (hi+lo fp16 operands: 3x these flops issued)")
+    elif key.startswith("spsk_grouped_linear") or key.startswith("spsk_pointwise_linear"):
+        if key.startswith("spsk_grouped_linear"):
             rows_n, cin, cout = a[0], a[3], a[6]
         else:
             rows_n, cin, cout = a[0] * a[1], a[3], a[6]
-        flops = 2.0 * rows_n * cin * cout
-        peak = 74.4
-        roof = {"kernel": top_key, "bound": "tensor", "achieved": flops / avg_s / 1e12, "peak": peak, "unit": "TFLOP/s",
-                "frac": flops / avg_s / 1e12 / peak, "traffic": None,
-                "note": "fp32 FFMA path: peak is the fp32 CUDA-core peak (148 SM x 128 lanes x 2 x 1.965 GHz), not the tensor peak"}
+        e.update(bound="tensor", achieved=2.0 * rows_n * cin * cout / avg_s / 1e12, peak=74.4, unit="TFLOP/s",
+                 note="exact-fp32 FFMA path: peak is the fp32 CUDA-core peak (148 SM x 128 lanes x 2 x 1.965 GHz)")
+    elif key.startswith("spsk_ball_query_msg"):
+        b, n, m = a[0], a[1], a[2]
+        nsum = sum(int(x) for x in a[5][:a[3]]) if len(a) > 5 else 48
+        alg_bytes = b * (n * 12 + m * 12 + m * nsum * 4)
+        e.update(bound="hbm", achieved=alg_bytes / avg_s / 1e9, peak=hbm, unit="GB/s",
+                 note="algorithmic bytes = xyz + centres + index lists; the kernel is fp32-issue / latency bound, not HBM bound")
     else:
-        roof = {"kernel": top_key, "bound": "hbm", "achieved": None, "peak": hbm, "unit": "GB/s", "frac": None, "traffic": None}
-    roof["peak_source"] = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
-    return roof, rows
+        e.update(bound="hbm", achieved=None, peak=hbm, unit="GB/s")
+    e["frac"] = (e["achieved"] / e["peak"]) if e.get("achieved") else None
+    e["sms_used"] = sms
+    e["sm_time_ms_per_step"] = None
+    tr = traffic.get(key.split("[")[0]) if traffic else None
+    e["traffic"] = tr
+    e["peak_source"] = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
+    return e
+
+
+def roofline_from_table(table, steps, peaks):
+    """Rooflines of the step's kernels.  Returned: (dominant, per-kernel rows, list of rooflines).  "Dominant" = largest
+    SM-time (duration x SMs held / 148): with several batches in flight the step is bound by SM-time, and the
+    latency-bound FPS (16 of 148 SMs) would otherwise hide the kernels that actually fill the GPU."""
+    total = sum(t["ms"] for t in table.values())
+    traffic = {}
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text())
+        except Exception:
+            traffic = {}
+    rows, roofs = [], []
+    for key, t in sorted(table.items(), key=lambda kv: -kv[1]["ms"]):
+        rows.append({"kernel": key, "ms_per_step": t["ms"] / steps, "launches_per_step": t["launches"] / steps,
+                     "share": t["ms"] / total})
+        if t["ms"] / total >= 0.01:
+            e = _roof_entry(key, t, peaks, traffic)
+            e["sm_time_ms_per_step"] = t["ms"] / steps * e["sms_used"] / N_SMS
+            roofs.append(e)
+    roofs.sort(key=lambda e: -e["sm_time_ms_per_step"])
+    return roofs[0], rows, roofs
 
 
 def load_peaks():
@@ -479,8 +527,9 @@ def main():
 
     if rank == 0 and not args.no_profile:
         table, psteps = profile_kernels(net, dev_pool, steps=min(args.steps, 5))
-        roof, rows = roofline_from_table(table, psteps, peaks)
+        roof, rows, roofs = roofline_from_table(table, psteps, peaks)
         line["roofline"] = roof
+        line["rooflines"] = roofs[:8]
         line["kernels"] = rows[:12]
         line["eager_ms_per_step_sum_of_kernels"] = sum(r["ms_per_step"] for r in rows)
     if rank == 0 and world == 1 and args.cpu_sample > 0:
