@@ -56,7 +56,7 @@ def main():
             run(); torch.cuda.synchronize()
             lib.spsk_sa_mma_set_profile(None)
             v = buf.cpu().numpy().astype(np.float64)
-            ncta = min(rows // 128, 148 * pk.ctas_per_sm * 2)
+            ncta = min(rows // 256, 148) if pk.pair else min(rows // 128, 148 * pk.ctas_per_sm * 2)
             print("   per-CTA kcycles: " + "  ".join(f"{n}={x/ncta/1e3:.1f}" for n, x in zip(NAMES, v)))
 
 if __name__ == "__main__":

@@ -32,175 +32,10 @@
 // operand is carried as hi + lo fp16 halves and each product is evaluated as Xh.Wh + Xl.Wh + Xh.Wl by
 // concatenating along K ([Xh | Xl | Xh] . [Wh ; Wh ; Wl]) -- fp32-grade results (~1e-6) for 3x MMA work that
 // these layers do not notice.  The exact-fp32 CUDA-core path is linear_ffma.cu.
-#include "mma_ptx.cuh"
+#include "sa_mma_common.cuh"
 #include <stdlib.h>
 
 namespace spsk {
-
-constexpr int MM_ROWS = 128;          // grouped rows per tile
-constexpr int MM_THREADS = 192;       // G = 1: 4 gather/epilogue warps + producer + mma;  G = 2: 8 + 2 = 320 threads
-constexpr int MM_STAGE_BYTES = 16384; // largest weight tile: [128 cout][64 k] fp16
-constexpr int MM_MAX_LAYERS = 4;
-constexpr int MM_MAX_STAGES = 8;
-constexpr int MM_HDR = 1024;          // barriers + TMEM slot
-constexpr int MM_MAX_XC = 16;         // 64-wide K chunks per activation buffer (K <= 1024)
-
-struct SaLayer {
-    int kpad;      // true input width, multiple of 16
-    int cpad;      // output width: multiple of 16 (hidden) / 128 (last)
-    int n_cc;      // ceil(cpad / 128)
-    int xw;        // activation buffer width in halfs: kpad (plain) or 2*kpad (split: [hi | lo])
-    int vk;        // K the MMAs run over: kpad (plain) or 3*kpad (split)
-    int n_kc;      // ceil(vk / 64)  weight tiles per cout chunk
-    int n_xc;      // ceil(xw / 64)  readiness chunks of the activation buffer
-    int w_off;     // byte offset of this layer's tiles in the packed weights
-    int bias_off;  // float offset into the bias array
-};
-
-struct SaArgs {
-    int nlayers;
-    SaLayer L[MM_MAX_LAYERS];
-    int b, n, m, nsample, ns_log2;
-    int c_feat, cpad8, ldtwin, use_xyz, split;
-    long long rows;  // b*m*nsample
-    int ntiles;
-    int nstages, resident, w_total, tmem_cols, nbuf, nbuf_log2;
-    int lstages;     // > 0: the last layer streams its weights through `lstages` extra 16 KB slots overlaid on the activation
-                     // buffer that is dead while it runs (the input of layer nlayers-2)
-    int xa_bytes, xb_bytes;
-    const float *xyz, *new_xyz, *feat32;
-    const __half *twin;   // (b, n, ldtwin)
-    const int *idx;       // (b, m, nsample)
-    const uint8_t *wtiles;
-    const float *bias;
-    float *out;           // (b, c_total, m) or null
-    int c_total, co_off, cout_last;
-    __half *out16;        // (b*m, ld16) or null
-    int ld16, co16, n16, o16lo;
-    unsigned long long *prof;   // optional per-role wait/work cycle counters (spsk_sa_mma_set_profile), null = off
-};
-
-// byte offset of weight tile (cc, kc) inside a layer: chunks of 128 couts are contiguous (cc-major), inside a chunk
-// the tiles follow each other along K; a tile is ncols x kw fp16 in canonical layout with SBO = kw*16
-__device__ __forceinline__ int wtile_off(const SaLayer &Ly, int cc, int kc, int ncols) {
-    return Ly.w_off + (128 * cc * Ly.vk + ncols * 64 * kc) * 2;
-}
-
-// 16 accumulator columns -> + bias -> ReLU -> fp16 -> two 16-byte stores into the next operand (K-major)
-__device__ __forceinline__ void store_hidden16(const float *v, const float *bias16, uint8_t *dst) {
-    const float4 *b4 = reinterpret_cast<const float4 *>(bias16);
-    uint32_t h[8];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float4 bb = __ldg(b4 + i);
-        h[2 * i] = pack_h2(fmaxf(v[4 * i] + bb.x, 0.f), fmaxf(v[4 * i + 1] + bb.y, 0.f));
-        h[2 * i + 1] = pack_h2(fmaxf(v[4 * i + 2] + bb.z, 0.f), fmaxf(v[4 * i + 3] + bb.w, 0.f));
-    }
-    *reinterpret_cast<uint4 *>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4 *>(dst + 128) = make_uint4(h[4], h[5], h[6], h[7]);
-}
-// hi/lo split of 8 fp32 values: hi = fp16(x), lo = fp16(x - hi)
-__device__ __forceinline__ void split8(const float *y, uint4 &hi, uint4 &lo) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const __half2 hh = __floats2half2_rn(y[2 * i], y[2 * i + 1]);
-        const float2 hf = __half22float2(hh);
-        h[i] = *reinterpret_cast<const uint32_t *>(&hh);
-        l[i] = pack_h2(y[2 * i] - hf.x, y[2 * i + 1] - hf.y);
-    }
-    hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
-__device__ __forceinline__ void store_hidden16_split(const float *v, const float *bias16, uint8_t *dst_hi, uint8_t *dst_lo) {
-    float y[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) y[i] = fmaxf(v[i] + __ldg(bias16 + i), 0.f);
-    uint4 h0, l0, h1, l1;
-    split8(y, h0, l0);
-    split8(y + 8, h1, l1);
-    *reinterpret_cast<uint4 *>(dst_hi) = h0;
-    *reinterpret_cast<uint4 *>(dst_hi + 128) = h1;
-    *reinterpret_cast<uint4 *>(dst_lo) = l0;
-    *reinterpret_cast<uint4 *>(dst_lo + 128) = l1;
-}
-
-// Last-layer epilogue of one 128-cout chunk: thread = cout; max over each centre's NS consecutive columns,
-// + bias, ReLU, store.  The output cursors advance incrementally with the centre.
-struct PoolOut {
-    float bv;
-    bool w32, w16;
-    float *outc;
-    __half *out16;
-    int ld16, o16lo;
-    long long q, qmax;
-    int m, p;
-    size_t scene_stride;
-    __device__ __forceinline__ void emit(float run) {
-        const float y = fmaxf(run + bv, 0.f);
-        if (q < qmax) {
-            if (w32) *outc = y;
-            if (w16) {
-                const __half h = __float2half_rn(y);
-                *out16 = h;
-                if (o16lo > 0) out16[o16lo] = __float2half_rn(y - __half2float(h));
-            }
-        }
-        ++q;
-        ++outc;
-        out16 += ld16;
-        if (++p == m) { p = 0; outc += scene_stride - (size_t)m; }
-    }
-};
-// NS = 16 / 32 (every shipped IA-SSD / SPSNet config): compile-time group boundaries
-template <int NS>
-__device__ __forceinline__ void pool_chunk(uint32_t taddr, PoolOut &o) {
-    float run = -3.0e38f;
-#pragma unroll 1
-    for (int c0 = 0; c0 < MM_ROWS; c0 += 32) {
-        float v[32];
-        tmem_ld32(taddr + (uint32_t)c0, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            run = fmaxf(run, v[i]);
-            if (((i + 1) % NS) == 0) { o.emit(run); run = -3.0e38f; }
-        }
-    }
-}
-// any power of two <= 128
-__device__ __noinline__ void pool_chunk_any(uint32_t taddr, PoolOut &o, int ns) {
-    float run = -3.0e38f;
-#pragma unroll 1
-    for (int c0 = 0; c0 < MM_ROWS; c0 += 16) {
-        float v[16];
-        tmem_ld16(taddr + (uint32_t)c0, v);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            run = fmaxf(run, v[i]);
-            if (((c0 + i + 1) & (ns - 1)) == 0) { o.emit(run); run = -3.0e38f; }
-        }
-    }
-}
-
-// ---- optional role profiling: cycles spent per wait / work category, summed over CTAs ------------------------
-enum { PF_MMA_TOTAL = 0, PF_MMA_ACC_EMPTY, PF_MMA_W_FULL, PF_MMA_XR, PF_PROD_W_EMPTY, PF_PROD_HID, PF_EPI_TOTAL, PF_EPI_GATHER,
-       PF_EPI_WAIT_HID, PF_EPI_WORK_HID, PF_EPI_WAIT_POOL, PF_EPI_WORK_POOL, PF_MMA_ISSUE, PF_MMA_COMMIT, PF_COUNT };
-struct Prof {
-    unsigned long long acc[PF_COUNT];
-    bool on;
-    __device__ __forceinline__ void init(bool enable) {
-        on = enable;
-#pragma unroll
-        for (int i = 0; i < PF_COUNT; ++i) acc[i] = 0ull;
-    }
-    __device__ __forceinline__ long long now() const { return on ? clock64() : 0ll; }
-    __device__ __forceinline__ void add(int k, long long t0) { if (on) acc[k] += (unsigned long long)(clock64() - t0); }
-    __device__ __forceinline__ void flush(unsigned long long *dst) const {
-        if (!on) return;
-        for (int i = 0; i < PF_COUNT; ++i)
-            if (acc[i]) atomicAdd(dst + i, acc[i]);
-    }
-};
 
 // ---- the kernel -----------------------------------------------------------------------------------
 // G = epilogue warpgroups.  G = 1 (192 threads, up to 3 CTAs per SM) for chains whose concurrency comes from co-resident
@@ -623,8 +458,11 @@ struct SaPlan {
     int xa_bytes, xb_bytes, w_total, resident, nstages, lstages, ctas, tmem_cols, nbuf, smem;
 };
 
+constexpr int PR_HDR_BYTES = 2048;   // header of the pair kernel (sa_mma_pair.cu)
+
 static int sa_plan(const spsk_sa_mma_desc *d, SaPlan *P) {
     const int nL = d->nlayers;
+    const bool pair = d->pair != 0;
     SPSK_REQUIRE(nL >= 1 && nL <= MM_MAX_LAYERS, SPSK_ERR_UNSUPPORTED, "sa_mma: nlayers=%d (1..%d)", nL, MM_MAX_LAYERS);
     const int split = d->split ? 1 : 0;
     int w_off = 0, b_off = 0;
@@ -637,9 +475,10 @@ static int sa_plan(const spsk_sa_mma_desc *d, SaPlan *P) {
                      "sa_mma: layer %d cpad=%d", l, cpad);
         SPSK_REQUIRE(last || cpad == d->kpad[l + 1], SPSK_ERR_INVALID_ARG, "sa_mma: layer %d cpad != next kpad", l);
         SPSK_REQUIRE(!split || (kpad <= 64 && (last || cpad <= 64)), SPSK_ERR_UNSUPPORTED, "sa_mma: split arithmetic needs every width <= 64");
+        SPSK_REQUIRE(!pair || (!split && (!last || cpad % 256 == 0)), SPSK_ERR_UNSUPPORTED, "sa_mma: pair kernel needs plain arithmetic and a last cpad multiple of 256");
         SaLayer &Ly = P->L[l];
         Ly.kpad = kpad; Ly.cpad = cpad;
-        Ly.n_cc = (cpad + 127) / 128;
+        Ly.n_cc = pair ? (cpad + 255) / 256 : (cpad + 127) / 128;
         Ly.xw = split ? 2 * kpad : kpad;
         Ly.vk = split ? 3 * kpad : kpad;
         Ly.n_kc = (Ly.vk + 63) / 64;
@@ -651,7 +490,7 @@ static int sa_plan(const spsk_sa_mma_desc *d, SaPlan *P) {
         if (l & 1) P->xb_bytes = max(P->xb_bytes, xbytes); else P->xa_bytes = max(P->xa_bytes, xbytes);
     }
     P->w_total = w_off;
-    const int xtot = MM_HDR + P->xa_bytes + P->xb_bytes;
+    const int xtot = (pair ? PR_HDR_BYTES : MM_HDR) + P->xa_bytes + P->xb_bytes;
     const int sm_bytes = 228 * 1024;   // per SM; every resident CTA also reserves 1 KB
     // CTAs per SM: as many (<= 3) as shared memory allows with the chain resident or >= 2 ring stages; the TMEM
     // share (512 / ctas rounded down to a power of two) must hold at least one 128-column accumulator
@@ -663,7 +502,7 @@ static int sa_plan(const spsk_sa_mma_desc *d, SaPlan *P) {
         *resident = 0; *nstages = st > MM_MAX_STAGES ? MM_MAX_STAGES : st; *smem = xtot + *nstages * MM_STAGE_BYTES;
         return true;
     };
-    int ctas = 0, cmax = 3;
+    int ctas = 0, cmax = pair ? 1 : 3;
     if (const char *e = getenv("SPSK_SA_MAX_CTAS")) cmax = max(1, min(3, atoi(e)));   // tuning / A-B measurements
     for (int c = cmax; c >= 1; --c) {
         int res, st, sm;
@@ -676,6 +515,11 @@ static int sa_plan(const spsk_sa_mma_desc *d, SaPlan *P) {
     // a starved ring (big activations leave < 4 stages): give the last layer -- most of the chain's weight bytes -- its own
     // ring overlaid on the activation buffer that is dead while it runs
     P->lstages = 0;
+    if (pair && P->resident) {   // the pair kernel always streams: turn the resident plan into a ring
+        P->resident = 0;
+        P->nstages = min(MM_MAX_STAGES, max(2, (P->smem - xtot) / MM_STAGE_BYTES));
+        P->smem = xtot + P->nstages * MM_STAGE_BYTES;
+    }
     if (!P->resident && P->nstages < 4 && nL >= 2 && !getenv("SPSK_SA_NO_LRING")) {
         const int other = ((nL - 2) & 1) ? P->xb_bytes : P->xa_bytes;
         const int e = other / MM_STAGE_BYTES;
@@ -690,6 +534,8 @@ static int sa_plan(const spsk_sa_mma_desc *d, SaPlan *P) {
 }
 
 }  // namespace spsk
+
+int spsk_sa_mma_pair_launch(const spsk::SaArgs &a, int smem_bytes, cudaStream_t st);   // sa_mma_pair.cu
 
 extern "C" int spsk_make_twin(int b, int c, int n, int cpad8, const float *features, void *twin, spsk_stream_t stream) {
     using namespace spsk;
@@ -776,6 +622,11 @@ extern "C" int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stre
         SPSK_REQUIRE(d->n16 >= d->cout_last && d->n16 <= d->cpad[d->nlayers - 1] && d->co16 >= 0 && d->co16 + d->n16 <= d->ld16, SPSK_ERR_INVALID_ARG,
                      "sa_mma: fp16 output window [co16, co16 + n16) outside ld16 or wider than the last layer");
     a.prof = g_sa_prof;
+    a.prof = g_sa_prof;
+    if (d->pair) {
+        a.ntiles = (int)((a.rows + 255) / 256);   // 256-row tiles, one per CTA pair
+        return spsk_sa_mma_pair_launch(a, P.smem, as_stream(stream));
+    }
     // two CTAs per SM slot (static tile striding): when another stream's kernels hold some SMs, late CTAs start
     // as soon as any SM frees up instead of doubling the kernel's duration
     const int slots = SPSK_NUM_SMS * P.ctas * 2;

@@ -9,6 +9,7 @@ keeps its running minima on chip (no `temp` tensor unless n > 131072).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Tuple
 
 import torch
@@ -445,13 +446,20 @@ class MmaChain:
                  become [Wh; Wh; Wl] so that [Xh | Xl | Xh] . W' = Xh.Wh + Xl.Wh + Xh.Wl  (fp32-grade)
     """
 
-    def __init__(self, chain, c_feat: int, use_xyz: bool, split: bool | None = None):
+    def __init__(self, chain, c_feat: int, use_xyz: bool, split: bool | None = None, pair: bool | None = None):
         dev = chain[0][0].device
         self.nlayers = len(chain)
         self.c_feat, self.use_xyz = c_feat, use_xyz
         widths = [wt.shape[1] for wt, _, _ in chain]
         can_split = c_feat <= 8 and all(_ceil(w, 16) <= 64 for w in widths[:-1]) and self.nlayers <= 4
         self.split = can_split if split is None else (bool(split) and can_split)
+        # CTA-pair kernel (tcgen05 cta_group::2, sa_mma_pair.cu) for wide chains: opt-in (SPSK_SA_PAIR=1 or pair=True).
+        # Measured on B200 (round 1): correct, 4x fewer MMA issues per row, but with the activations of 128 rows per CTA
+        # still filling shared memory the 2-stage weight ring plus the cross-CTA forwarding hops make it 25-45 % slower
+        # than the single-CTA kernel (layer 5 scale 2: 388 vs 288 us) -- see DESIGN.md section 4.3.
+        can_pair = (not self.split) and len(widths) >= 2
+        want_pair = can_pair and os.environ.get("SPSK_SA_PAIR", "0") == "1" and (max(widths) >= 512 or widths[-1] >= 256)
+        self.pair = want_pair if pair is None else (bool(pair) and can_pair)
         self.cpad8 = _ceil(c_feat, 8) if c_feat > 0 else 0
         k0 = self.cpad8 + (8 if use_xyz else 0)
         self.ok = 1 <= self.nlayers <= 4 and all(relu for _, _, relu in chain) and k0 > 0
@@ -461,7 +469,7 @@ class MmaChain:
         for l, (wt, bias, _relu) in enumerate(chain):
             cin, cout = wt.shape
             last = l == self.nlayers - 1
-            cp = _ceil(cout, 128 if last else 16)
+            cp = _ceil(cout, (256 if self.pair else 128) if last else 16)
             W = torch.zeros((kin, cp), dtype=torch.float32, device=dev)
             if l == 0:
                 xr = 3 if use_xyz else 0  # reference row order: xyz first
@@ -480,11 +488,22 @@ class MmaChain:
             else:
                 Wv = W.half()
             vk = Wv.shape[0]
-            for c0 in range(0, cp, 128):
-                ncols = min(128, cp - c0)
-                for k0_ in range(0, vk, 64):
-                    kw = min(64, vk - k0_)
-                    tiles.append(_canonical_tile(Wv[k0_:k0_ + kw, c0:c0 + ncols].t()))
+            if self.pair:
+                # 256-wide cout chunks; inside a chunk the rows of pair rank 0 then rank 1 (half of the chunk each; the last
+                # layer's chunks are always 256 wide: 128 couts per CTA), each as tiles of <= 64 k
+                for c0 in range(0, cp, 256):
+                    cw = min(256, cp - c0)
+                    for rk in range(2):
+                        r0 = c0 + rk * (cw // 2)
+                        for k0_ in range(0, vk, 64):
+                            kw = min(64, vk - k0_)
+                            tiles.append(_canonical_tile(Wv[k0_:k0_ + kw, r0:r0 + cw // 2].t()))
+            else:
+                for c0 in range(0, cp, 128):
+                    ncols = min(128, cp - c0)
+                    for k0_ in range(0, vk, 64):
+                        kw = min(64, vk - k0_)
+                        tiles.append(_canonical_tile(Wv[k0_:k0_ + kw, c0:c0 + ncols].t()))
             bv = torch.zeros(cp, dtype=torch.float32, device=dev)
             bv[:cout] = bias
             biases.append(bv)
@@ -510,6 +529,7 @@ class MmaChain:
             d.kpad[l] = self.kpad[l]
             d.cpad[l] = self.cpad[l]
         d.split = 1 if self.split else 0
+        d.pair = 1 if self.pair else 0
         d.c_feat = self.c_feat
         d.use_xyz = 1 if self.use_xyz else 0
         d.cout_last = self.cout_last

@@ -147,6 +147,35 @@ def test_pw_mma_split_is_fp32_grade(rows, c_in, c_out, relu):
     assert torch.all(out16[:, c_out:n16] == 0) and torch.all(out16[:, n16 + c_out:] == 0)
 
 
+@pytest.mark.parametrize("name", ["l2s2", "l5s1", "l5s2", "l1s2"])
+def test_mma_pair_kernel_matches_single(name):
+    """The CTA-pair kernel (tcgen05 cta_group::2, 256-row tiles; opt-in) reproduces the single-CTA kernel: same operands,
+    same fp32 accumulation per output, so the pooled results agree to fp32 summation-order noise."""
+    from spsnet_b200 import pointnet2_utils as pu
+
+    c_feat, ns, radius, widths = SCALES[name]
+    B, N, M = 3, 1500, 333
+    rng = np.random.default_rng(21)
+    xyz = torch.from_numpy(np.ascontiguousarray(scenes.make_batch(5, B, N)[:, :, :3])).cuda()
+    feats = torch.from_numpy(rng.standard_normal((B, c_feat, N)).astype(np.float32)).cuda()
+    sel = torch.from_numpy(np.stack([rng.choice(N, M, replace=False) for _ in range(B)]).astype(np.int32)).cuda()
+    new_xyz = pu.gather_rows(xyz, sel)
+    idx = pu.ball_query(radius, ns, xyz, new_xyz)
+    chain = _chain(c_feat, widths, seed=3)
+    outs = []
+    for pair in (False, True):
+        pk = pu.MmaChain(chain, c_feat, True, pair=pair)
+        assert pk.ok and pk.pair == pair
+        twin = pu.make_twin(feats, pk.cpad8)
+        out = torch.full((B, widths[-1], M), -7.0, device="cuda")
+        pu.sa_mma_forward(xyz=xyz, new_xyz=new_xyz, idx=idx, chain=pk, twin=twin, out_pooled=out)
+        torch.cuda.synchronize()
+        outs.append(out.cpu().numpy())
+    e = rel_err(outs[1], outs[0])
+    print(f"[mma pair] {name}: pair vs single rel diff {e:.2e}")
+    assert e <= 2e-6
+
+
 def test_make_twin():
     from spsnet_b200 import pointnet2_utils as pu
 
