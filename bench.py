@@ -54,6 +54,9 @@ WORKLOADS = {
     "spsnet": dict(batch=16, npts=16384, ncols=5, kind="kitti", cfg="kitti_spsnet_cfg", bb="PAGNet_Backbone",
                    text="SPSNet-IA KITTI cfg: stability-score (sss_aware) top-k sampling in SA layers 2,3 with per-point stds, "
                         "otherwise the IA-SSD SA stack, batch 16 x 16384 pts per GPU, eval"),
+    "spsnet_e2e": dict(batch=16, npts=16384, ncols=5, kind="kitti", cfg="kitti_spsnet_cfg", bb="SPSNetIA",
+                       text="SPSNet-IA end to end on the path: stability generator (SA layer with M = N = 16384 centres + logvar "
+                            "head -> stds) feeding the PAGNet backbone with stability-score top-k, batch 16 x 16384 pts per GPU, eval"),
     "waymo": dict(batch=8, npts=65536, ncols=6, kind="waymo", cfg="waymo_iassd_cfg", bb="IASSD_Backbone",
                   text="IA-SSD Waymo cfg full SA stack (D-FPS 65536->16384->4096, ctr-aware top-k ->2048->1024, vote, MSG ball "
                        "query + shared MLP), batch 8 x 65536 pts per GPU, eval"),
@@ -129,7 +132,13 @@ def build_net(seed=0):
     from spsnet_b200 import backbone as bb
 
     torch.manual_seed(seed)
-    net = getattr(bb, _WL["bb"])(getattr(bb, _WL["cfg"])(), num_class=3, input_channels=NCOLS - 1)
+    if _WL["bb"] == "SPSNetIA":
+        from spsnet_b200 import stability as st
+
+        net = st.SPSNetIAFrontEnd(st.Generate_center(st.sf_unc_cfg()),
+                                  bb.PAGNet_Backbone(getattr(bb, _WL["cfg"])(), num_class=3, input_channels=NCOLS - 1))
+    else:
+        net = getattr(bb, _WL["bb"])(getattr(bb, _WL["cfg"])(), num_class=3, input_channels=NCOLS - 1)
     bb.randomize_bn_stats(net, seed=seed)
     return net.eval()
 

@@ -222,6 +222,58 @@ def test_backbone_vs_reference_backbone(ref_ops):
             h.remove()
 
 
+def test_stability_generator_vs_reference(ref_ops):
+    """SPSNet stability generator (eval branch): stds = sum exp(0.5 * fc2(SA(points))) against the reference's own
+    PointnetSampling module + CUDA ops with the same weights (identity sampling: every point is a centre)."""
+    if ref_ops is None:
+        pytest.skip("oracle/_ref (rebuilt reference) not present")
+    from spsnet_b200 import backbone as bb
+    from spsnet_b200 import stability as st
+
+    B, N = 2, 3000
+    cfg = st.sf_unc_cfg()
+    cfg["SA_CONFIG"]["NPOINT_LIST"] = [[N]]
+    torch.manual_seed(5)
+    gen = st.Generate_center(cfg)
+    bb.randomize_bn_stats(gen, seed=5)
+    gen = gen.cuda().eval()
+    sa = cfg["SA_CONFIG"]
+    ref_sa = ref_ops.modules.PointnetSampling(
+        npoint_list=sa["NPOINT_LIST"][0], sample_range_list=sa["SAMPLE_RANGE_LIST"][0], sample_type_list=sa["SAMPLE_METHOD_LIST"][0],
+        radii=sa["RADIUS_LIST"][0], nsamples=sa["NSAMPLE_LIST"][0], mlps=[[1] + list(m) for m in sa["MLPS"][0]], use_xyz=True,
+        dilated_group=False, aggregation_mlp=list(sa["AGGREGATION_MLPS"][0])).cuda().eval()
+    mine = gen.feature_extract.SA_modules[0]
+    assert list(ref_sa.state_dict().keys()) == list(mine.state_dict().keys())
+    ref_sa.load_state_dict(mine.state_dict())
+    pts = scenes.make_batch(70, B, N)
+    points = dev(scenes.to_points(pts))
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            out = gen({"batch_size": B, "points": points.clone()})
+            xyz = dev(np.ascontiguousarray(pts[:, :, :3]))
+            feats = dev(np.ascontiguousarray(pts[:, :, 3:].transpose(0, 2, 1)))
+            r_xyz, r_feat, r_idx = ref_sa(xyz, feats, None)
+            logvar = gen.feature_encoder.fc2(r_feat.permute(0, 2, 1).contiguous())
+            want = torch.sum(torch.exp(0.5 * logvar), dim=-1)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    assert out["stds"].shape == (B, N)
+    np.testing.assert_array_equal(out["encoder_xyz"][1].cpu().numpy(), r_xyz.cpu().numpy())
+    assert_close(out["soc_feature"].cpu().numpy(), r_feat.permute(0, 2, 1).cpu().numpy(), what="generator soc_feature")
+    e = rel_err(out["stds"].cpu().numpy(), want.cpu().numpy())
+    print(f"[stability] stds rel err vs reference composition {e:.2e}")
+    assert e <= 1e-3
+    # the stds drive SPSNet-IA's stability-aware sampling end to end
+    net = make_backbone(small_sa_cfg((512, 128, 64, 32)), seed=2, cls=bb.PAGNet_Backbone)
+    net.model_cfg.SA_CONFIG["SAMPLE_METHOD_LIST"][2] = ["sss_aware"]
+    with torch.no_grad():
+        res = net.cuda()({"batch_size": B, "points": points.clone(), "stds": out["stds"]})
+    assert res["centers_features"].shape[0] == B * 32
+
+
 def test_fp_module(oracle):
     from spsnet_b200 import backbone as bb
     from spsnet_b200 import pointnet2_modules as pm

@@ -152,3 +152,19 @@ def test_bench_reference_cpu_line():
         assert k in line
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_stability_generator_state_dict_layout():
+    """Generator checkpoints (reference stability_generate/model.py) address feature_extract.SA_modules.*,
+    feature_encoder.fc{1,2}.* and obj_encoder.*: same key layout here."""
+    from spsnet_b200 import stability as st
+
+    gen = st.Generate_center(st.sf_unc_cfg())
+    keys = list(gen.state_dict().keys())
+    assert "feature_extract.SA_modules.0.mlps.0.0.weight" in keys and "feature_extract.SA_modules.0.mlps.1.7.running_var" in keys
+    assert "feature_extract.SA_modules.0.aggregation_layer.0.weight" in keys
+    for k in ("feature_encoder.fc1.weight", "feature_encoder.fc2.bias", "obj_encoder.fc1.weight", "obj_encoder.fc_ce2.weight", "global_step"):
+        assert k in keys
+    assert gen.feature_encoder.fc2.weight.shape == (8, 64) and gen.obj_encoder.fc1.weight.shape == (64, 72)
+    with __import__("pytest").raises(NotImplementedError):
+        gen.train()({"batch_size": 1, "points": None})
