@@ -238,6 +238,9 @@ typedef struct spsk_sa_mma_desc {
     float *out_cm; int c_total, co_off;
     void *out16; int ld16, co16, n16;
     int o16lo;              /* > 0: out16 also receives the residuals fp16(y - fp16(y)) at column o16lo + co16 + c */
+    int l0_fused;           /* 1 (split chains, >= 2 layers, cpad[0] <= 32): layer 0 is evaluated in fp32 by the gather threads;
+                               wtiles then carries, after the last layer's tiles, W0 as [16][cpad[0]] fp32 (same row order as
+                               the split k order) followed by cpad[0] fp32 biases */
     int pair;               /* 1: CTA-pair kernel (tcgen05 cta_group::2, 256-row tiles) for wide chains: plain mode only, last cpad a
                                multiple of 256, and wtiles in the PAIR packing: per layer, 256-wide cout chunks; inside a chunk
                                the rows of pair rank 0 then rank 1 (hidden layers: half of the chunk each; last layer: 128

@@ -74,7 +74,7 @@ class SaMmaDesc(C.Structure):
         ("nlayers", _i), ("kpad", _i * 4), ("cpad", _i * 4),
         ("wtiles", _p), ("bias", _p), ("cout_last", _i),
         ("out_cm", _p), ("c_total", _i), ("co_off", _i),
-        ("out16", _p), ("ld16", _i), ("co16", _i), ("n16", _i), ("o16lo", _i), ("pair", _i),
+        ("out16", _p), ("ld16", _i), ("co16", _i), ("n16", _i), ("o16lo", _i), ("l0_fused", _i), ("pair", _i),
     ]
 
 

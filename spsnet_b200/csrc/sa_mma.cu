@@ -134,7 +134,65 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
         }
     } else if (warp == W_MMA) {
         // ================= MMA issuer (warp-uniform loops, one elected lane issues) =================
-        {
+        if (a.narrow) {
+            // Narrow chains (weights resident, one job per layer): every descriptor is tile-invariant, so they are built ONCE
+            // into registers (loops over layers fully unrolled -> static indexing) and the per-job path is just: wait for the
+            // accumulator, wait for the activation chunks, issue, commit.  The general loop below spends ~2 k cycles of
+            // address arithmetic and parameter loads per job, which is the critical path of these latency-bound chains.
+            const bool leader = elect_one();
+            uint32_t x_lo[MM_MAX_LAYERS], x_hi[MM_MAX_LAYERS], w_lo[MM_MAX_LAYERS], idesc[MM_MAX_LAYERS], tstride[MM_MAX_LAYERS];
+            int nv[MM_MAX_LAYERS], nk2[MM_MAX_LAYERS], nxc[MM_MAX_LAYERS], vkl[MM_MAX_LAYERS];
+#pragma unroll
+            for (int l = 0; l < MM_MAX_LAYERS; ++l) {
+                const SaLayer &Ly = a.L[l < nL ? l : 0];
+                const bool last = (l == nL - 1);
+                x_lo[l] = umma_desc_lo(smem_u32((l & 1) ? xb : xa), 128u);
+                x_hi[l] = umma_desc_hi((uint32_t)Ly.xw * 16u);
+                w_lo[l] = umma_desc_lo(smem_u32(wst + Ly.w_off), 128u);
+                tstride[l] = (uint32_t)(Ly.cpad * 64 * 2) >> 4;            // one full 64-k tile of this layer, in descriptor units
+                idesc[l] = last ? umma_idesc(128, MM_ROWS) : umma_idesc(128, Ly.cpad);
+                nv[l] = Ly.vk >> 4;
+                nk2[l] = a.split ? 2 * (Ly.kpad >> 4) : 0x7FFFFFFF;
+                nxc[l] = Ly.n_xc;
+                vkl[l] = Ly.vk;
+            }
+            mbar_wait(W_FULL(0), 0u);   // the resident weights have landed
+            uint32_t job = 0;
+            uint32_t xph[2] = {0u, 0u};
+            const uint32_t nbmask = (uint32_t)a.nbuf - 1u;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+#pragma unroll
+                for (int l = 0; l < MM_MAX_LAYERS; ++l) {
+                    if (l < nL && l >= a.l0_fused) {
+                        const bool last = (l == nL - 1);
+                        const int buf = (int)(job & nbmask);
+                        const uint32_t use = job >> a.nbuf_log2;
+                        if (use > 0) mbar_wait(ACC_EMPTY(buf), (use - 1) & 1u);
+                        for (int c = 0; c < nxc[l]; ++c) {
+                            mbar_wait(XR(l & 1, c), (xph[l & 1] >> c) & 1u);
+                            xph[l & 1] ^= (1u << c);
+                        }
+                        tc_fence_after();
+                        if (leader) {
+                            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
+                            for (int v = 0; v < nv[l]; ++v) {
+                                const int xblk = v >= nk2[l] ? v - nk2[l] : v;
+                                const int kc = v >> 2, jj = v & 3;
+                                const uint32_t kw = (uint32_t)min(64, vkl[l] - kc * 64);
+                                const uint32_t wl = w_lo[l] + (uint32_t)kc * tstride[l] + 16u * (uint32_t)jj;
+                                const uint32_t wh = umma_desc_hi(kw * 16u);
+                                const uint32_t xl = x_lo[l] + 16u * (uint32_t)xblk;
+                                if (!last) umma_f16_lohi(d_tmem, xl, x_hi[l], wl, wh, idesc[l], v ? 1u : 0u);
+                                else umma_f16_lohi(d_tmem, wl, wh, xl, x_hi[l], idesc[l], v ? 1u : 0u);
+                            }
+                            umma_commit(ACC_FULL(buf));
+                        }
+                        __syncwarp();
+                        ++job;
+                    }
+                }
+            }
+        } else {
             const bool leader = elect_one();
             Prof pf;
             pf.init(a.prof != nullptr && leader);
@@ -147,7 +205,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
             uint8_t *lst = ((nL - 2) & 1) ? xb : xa;
             const uint32_t nbmask = (uint32_t)a.nbuf - 1u;
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-                for (int l = 0; l < nL; ++l) {
+                for (int l = a.l0_fused; l < nL; ++l) {
                     const SaLayer &Ly = a.L[l];
                     const bool last = (l == nL - 1);
                     const bool lring = a.lstages > 0 && last;
@@ -248,6 +306,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
         const int first_tile = blockIdx.x;
         uint32_t prev_last_job = 0;   // G = 2: the previous tile's last job (its MMAs are the last readers of XA)
         bool have_prev = false;
+        if (a.l0_fused) mbar_wait(W_FULL(0), 0u);   // layer 0's fp32 weights live in the resident weight image
         int jn = 0;   // neighbour index of this thread's row in the NEXT tile (prefetched one tile ahead)
         if (grp == 0 && first_tile < a.ntiles) {
             const long long grow = (long long)first_tile * MM_ROWS + r;
@@ -315,6 +374,50 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                     }
                     if (a.c_feat) { y[8] = dx; y[9] = dy; y[10] = dz; }
                     else { y[0] = dx; y[1] = dy; y[2] = dz; }
+                    if (a.l0_fused) {
+                        // layer 0 right here, in fp32 on the CUDA cores (<= 11 real inputs x <= 32 outputs per row): saves one
+                        // MMA job + TMEM round trip + hand-off per tile; the result goes straight into layer 1's [hi | lo] operand
+                        const float *w0 = reinterpret_cast<const float *>(wst + a.l0_off);
+                        const int c0n = L0.cpad;   // 16 or 32
+                        float h[32];
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4) {
+                            const float4 bv = c < c0n ? *reinterpret_cast<const float4 *>(w0 + 16 * c0n + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            h[c] = bv.x; h[c + 1] = bv.y; h[c + 2] = bv.z; h[c + 3] = bv.w;
+                        }
+                        const int xo = a.c_feat ? 8 : 0;
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) {
+                            if (k < a.c_feat || (k >= xo && k < xo + 3)) {   // warp-uniform: rows that are not padding
+                                const float yk = y[k];
+#pragma unroll
+                                for (int c = 0; c < 32; c += 4) {
+                                    if (c < c0n) {
+                                        const float4 wv = *reinterpret_cast<const float4 *>(w0 + k * c0n + c);
+                                        h[c] = fmaf(yk, wv.x, h[c]); h[c + 1] = fmaf(yk, wv.y, h[c + 1]);
+                                        h[c + 2] = fmaf(yk, wv.z, h[c + 2]); h[c + 3] = fmaf(yk, wv.w, h[c + 3]);
+                                    }
+                                }
+                            }
+                        }
+                        const SaLayer &L1 = a.L[1];
+                        uint8_t *x1 = xb + (size_t)(r >> 3) * ((uint32_t)L1.xw * 16u) + row_off;
+                        uint8_t *x1lo = x1 + (size_t)(L1.kpad >> 3) * 128;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            if (8 * g < c0n) {
+                                float t8[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) t8[i] = fmaxf(h[8 * g + i], 0.f);
+                                uint4 hi, lo;
+                                split8(t8, hi, lo);
+                                *reinterpret_cast<uint4 *>(x1 + (size_t)g * 128) = hi;
+                                *reinterpret_cast<uint4 *>(x1lo + (size_t)g * 128) = lo;
+                            }
+                        }
+                        fence_proxy_async();
+                        for (int c = 0; c < L1.n_xc; ++c) mbar_arrive(XR(1, c));
+                    } else {
                     const int nch = L0.kpad >> 3;   // 1 or 2 groups of 8
                     uint8_t *xlo = xrow + (size_t)nch * 128;
                     uint4 hi, lo;
@@ -326,13 +429,16 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                         *reinterpret_cast<uint4 *>(xrow + 128) = hi;
                         *reinterpret_cast<uint4 *>(xlo + 128) = lo;
                     }
+                    }
                 }
-                fence_proxy_async();
-                for (int c = 0; c < L0.n_xc; ++c) mbar_arrive(XR(0, c));
+                if (!a.l0_fused) {
+                    fence_proxy_async();
+                    for (int c = 0; c < L0.n_xc; ++c) mbar_arrive(XR(0, c));
+                }
             }
             pf.add(PF_EPI_GATHER, t_g);
             // ---- hidden layers: D[row, cout] -> relu(D + bias) -> fp16 -> next X, chunk by chunk
-            for (int l = 0; l < nL - 1; ++l) {
+            for (int l = a.l0_fused; l < nL - 1; ++l) {
                 const SaLayer &Ly = a.L[l];
                 const SaLayer &Ln = a.L[l + 1];
                 const int obuf = (l + 1) & 1;
@@ -370,7 +476,14 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                         }
                     } else {
                         uint8_t *xlo = xrow + (size_t)(Ln.kpad >> 3) * 128;
-                        for (int c0 = 0; c0 < ncols; c0 += 16) {
+                        int c0 = 0;
+                        for (; c0 + 32 <= ncols; c0 += 32) {
+                            float v[32];
+                            tmem_ld32(taddr + (uint32_t)c0, v);
+                            store_hidden16_split(v, bias + c0, xrow + (size_t)(c0 >> 3) * 128, xlo + (size_t)(c0 >> 3) * 128);
+                            store_hidden16_split(v + 16, bias + c0 + 16, xrow + (size_t)((c0 >> 3) + 2) * 128, xlo + (size_t)((c0 >> 3) + 2) * 128);
+                        }
+                        if (c0 < ncols) {
                             float v[16];
                             tmem_ld16(taddr + (uint32_t)c0, v);
                             store_hidden16_split(v, bias + c0, xrow + (size_t)(c0 >> 3) * 128, xlo + (size_t)(c0 >> 3) * 128);
@@ -455,7 +568,7 @@ static unsigned long long *g_sa_prof = nullptr;
 // ---- host-side planning ---------------------------------------------------------------------------------
 struct SaPlan {
     SaLayer L[MM_MAX_LAYERS];
-    int xa_bytes, xb_bytes, w_total, resident, nstages, lstages, ctas, tmem_cols, nbuf, smem;
+    int xa_bytes, xb_bytes, w_total, l0_off, resident, nstages, lstages, ctas, tmem_cols, nbuf, smem;
 };
 
 constexpr int PR_HDR_BYTES = 2048;   // header of the pair kernel (sa_mma_pair.cu)
@@ -490,6 +603,13 @@ static int sa_plan(const spsk_sa_mma_desc *d, SaPlan *P) {
         if (l & 1) P->xb_bytes = max(P->xb_bytes, xbytes); else P->xa_bytes = max(P->xa_bytes, xbytes);
     }
     P->w_total = w_off;
+    P->l0_off = 0;
+    if (d->l0_fused) {
+        SPSK_REQUIRE(split && nL >= 2 && d->cpad[0] <= 32 && !pair, SPSK_ERR_UNSUPPORTED, "sa_mma: layer-0 fusion needs a split chain of >= 2 layers with cpad[0] <= 32");
+        P->l0_off = w_off;
+        P->w_total = w_off + (16 * d->cpad[0] + d->cpad[0]) * 4;
+        P->w_total = (P->w_total + 15) & ~15;
+    }
     const int xtot = (pair ? PR_HDR_BYTES : MM_HDR) + P->xa_bytes + P->xb_bytes;
     const int sm_bytes = 228 * 1024;   // per SM; every resident CTA also reserves 1 KB
     // CTAs per SM: as many (<= 3) as shared memory allows with the chain resident or >= 2 ring stages; the TMEM
@@ -605,6 +725,12 @@ extern "C" int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stre
     SPSK_REQUIRE(ntiles <= 0x7FFFFFFF, SPSK_ERR_UNSUPPORTED, "sa_mma: too many rows");
     a.ntiles = (int)ntiles;
     a.lstages = P.lstages;
+    a.l0_fused = d->l0_fused ? 1 : 0;
+    a.l0_off = P.l0_off;
+    SPSK_REQUIRE(!a.l0_fused || P.resident, SPSK_ERR_UNSUPPORTED, "sa_mma: layer-0 fusion needs the chain resident in shared memory");
+    a.narrow = P.resident && !getenv("SPSK_SA_NO_NARROW");
+    for (int l = 0; l < d->nlayers; ++l)
+        if (P.L[l].n_cc != 1) a.narrow = 0;
     a.nstages = P.nstages; a.resident = P.resident; a.w_total = P.w_total; a.tmem_cols = P.tmem_cols; a.nbuf = P.nbuf;
     a.nbuf_log2 = P.nbuf == 4 ? 2 : (P.nbuf == 2 ? 1 : 0);
     a.xa_bytes = P.xa_bytes; a.xb_bytes = P.xb_bytes;

@@ -33,6 +33,9 @@ struct SaArgs {
     long long rows;  // b*m*nsample
     int ntiles;
     int nstages, resident, w_total, tmem_cols, nbuf, nbuf_log2;
+    int l0_fused, l0_off;   // split chains: layer 0 (K <= 11 real inputs) is evaluated in fp32 by the gather threads from the
+                            // [16][cpad0] fp32 weights + bias appended to the resident weights at byte l0_off; the MMA chain starts at layer 1
+    int narrow;      // resident chain with one job per layer: the MMA warp runs the register-resident fast loop
     int lstages;     // > 0: the last layer streams its weights through `lstages` extra 16 KB slots overlaid on the activation
                      // buffer that is dead while it runs (the input of layer nlayers-2)
     int xa_bytes, xb_bytes;
@@ -81,9 +84,14 @@ __device__ __forceinline__ void split8(const float *y, uint4 &hi, uint4 &lo) {
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 __device__ __forceinline__ void store_hidden16_split(const float *v, const float *bias16, uint8_t *dst_hi, uint8_t *dst_lo) {
+    const float4 *b4 = reinterpret_cast<const float4 *>(bias16);
     float y[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) y[i] = fmaxf(v[i] + __ldg(bias16 + i), 0.f);
+    for (int i = 0; i < 4; ++i) {
+        const float4 bb = __ldg(b4 + i);
+        y[4 * i] = fmaxf(v[4 * i] + bb.x, 0.f); y[4 * i + 1] = fmaxf(v[4 * i + 1] + bb.y, 0.f);
+        y[4 * i + 2] = fmaxf(v[4 * i + 2] + bb.z, 0.f); y[4 * i + 3] = fmaxf(v[4 * i + 3] + bb.w, 0.f);
+    }
     uint4 h0, l0, h1, l1;
     split8(y, h0, l0);
     split8(y + 8, h1, l1);

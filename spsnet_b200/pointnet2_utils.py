@@ -513,6 +513,24 @@ class MmaChain:
                 self.ok = False
             kin = cp
             self.cout_last = cout
+        # split chains: layer 0 (<= 11 real inputs) CAN be evaluated in fp32 by the gather threads (include/spsk.h: l0_fused; its
+        # fp32 weights [16][cpad0] + bias ride behind the fp16 tiles).  Opt-in (SPSK_SA_L0_FUSED=1): measured on B200 it is
+        # 8-12 % SLOWER than running layer 0 as one more tensor-core job -- the gather/epilogue warps' instruction issue, not
+        # the hand-off latency, bounds these chains, and the fusion adds ~300 instructions per row to exactly those warps.
+        self.l0_fused = bool(self.split and self.nlayers >= 2 and self.cpad[0] <= 32 and os.environ.get("SPSK_SA_L0_FUSED", "0") == "1")
+        if self.l0_fused:
+            wt0, b0, _ = chain[0]
+            cp0 = self.cpad[0]
+            W0 = torch.zeros((16, cp0), dtype=torch.float32, device=dev)
+            xr = 3 if use_xyz else 0
+            if c_feat:
+                W0[0:c_feat, :wt0.shape[1]] = wt0[xr:xr + c_feat]
+            if use_xyz:
+                xo = 8 if c_feat else 0
+                W0[xo:xo + 3, :wt0.shape[1]] = wt0[0:3]
+            bb0 = torch.zeros(cp0, dtype=torch.float32, device=dev)
+            bb0[:wt0.shape[1]] = b0
+            tiles.append(torch.cat([W0.reshape(-1), bb0]).contiguous().view(torch.float16))
         self.wtiles = torch.cat(tiles).contiguous()
         self.bias = torch.cat(biases).contiguous()
         self.ctas_per_sm = self.nstages = self.resident = self.smem = 0
@@ -530,6 +548,7 @@ class MmaChain:
             d.cpad[l] = self.cpad[l]
         d.split = 1 if self.split else 0
         d.pair = 1 if self.pair else 0
+        d.l0_fused = 1 if self.l0_fused else 0
         d.c_feat = self.c_feat
         d.use_xyz = 1 if self.use_xyz else 0
         d.cout_last = self.cout_last
