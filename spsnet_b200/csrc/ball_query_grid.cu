@@ -135,77 +135,102 @@ bq_grid_query_kernel(int n, int m, int words, BgScales sc, const float *__restri
     const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5;
     const uint32_t lane = lane_id();
-    const int p = blockIdx.x * BG_WARPS + warp;
     uint32_t *bm = bitmaps + (size_t)warp * NS * words;
+    // The bitmaps are zeroed ONCE per warp; afterwards every centre clears exactly the rows it touched while reading
+    // them back, so the per-centre cost follows the number of hits, not n / 32.
     for (int i = lane; i < NS * words; i += 32) bm[i] = 0u;
     __syncwarp();
-    if (p >= m) return;
     const GridParams gp = params[b];
     const int *cs = cell_start + (size_t)b * (BG_MAXC + 1);
     const float4 *pts = sorted + (size_t)b * n;
-    const float *c = new_xyz + ((size_t)b * m + p) * 3;
-    const float qx = __ldg(c), qy = __ldg(c + 1), qz = __ldg(c + 2);
-    // the centre may lie outside the scene box (vote centres): unclamped cell coordinate, clamped ranges
-    const int ccx = (int)floorf((qx - gp.minx) * gp.inv_c), ccy = (int)floorf((qy - gp.miny) * gp.inv_c);
-    const int xlo = max(ccx - 1, 0), xhi = min(ccx + 1, gp.gx - 1);
-    if (xlo <= xhi) {
-        for (int cy = max(ccy - 1, 0); cy <= min(ccy + 1, gp.gy - 1); ++cy) {
-            const int beg = __ldg(cs + cy * gp.gx + xlo), end = __ldg(cs + cy * gp.gx + xhi + 1);
-            for (int k0 = beg; k0 < end; k0 += 32) {
-                const int k = k0 + (int)lane;
-                if (k < end) {
-                    const float4 v = __ldg(pts + k);
-                    const float d2 = sqdist3(qx, qy, qz, v.x, v.y, v.z);
-                    const uint32_t oi = (uint32_t)__float_as_int(v.w);
+    for (int p = blockIdx.x * BG_WARPS + warp; p < m; p += gridDim.x * BG_WARPS) {
+        const float *c = new_xyz + ((size_t)b * m + p) * 3;
+        const float qx = __ldg(c), qy = __ldg(c + 1), qz = __ldg(c + 2);
+        // rows (32 words = 1024 point ids) that received a hit, per scale: 64 rows cover n <= 65536
+        uint32_t tlo[NS], thi[NS];
 #pragma unroll
-                    for (int s = 0; s < NS; ++s)
-                        if (d2 < sc.r2[s]) atomicOr(&bm[s * words + (oi >> 5)], 1u << (oi & 31u));
+        for (int s = 0; s < NS; ++s) { tlo[s] = 0u; thi[s] = 0u; }
+        // the centre may lie outside the scene box (vote centres): unclamped cell coordinate, clamped ranges
+        const int ccx = (int)floorf((qx - gp.minx) * gp.inv_c), ccy = (int)floorf((qy - gp.miny) * gp.inv_c);
+        const int xlo = max(ccx - 1, 0), xhi = min(ccx + 1, gp.gx - 1);
+        if (xlo <= xhi) {
+            for (int cy = max(ccy - 1, 0); cy <= min(ccy + 1, gp.gy - 1); ++cy) {
+                const int beg = __ldg(cs + cy * gp.gx + xlo), end = __ldg(cs + cy * gp.gx + xhi + 1);
+                for (int k0 = beg; k0 < end; k0 += 32) {
+                    const int k = k0 + (int)lane;
+                    float d2 = 3.0e38f;
+                    uint32_t oi = 0u;
+                    if (k < end) {
+                        const float4 v = __ldg(pts + k);
+                        d2 = sqdist3(qx, qy, qz, v.x, v.y, v.z);
+                        oi = (uint32_t)__float_as_int(v.w);
+                    }
+                    const uint32_t row = oi >> 10;
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) {
+                        const bool hit = d2 < sc.r2[s];
+                        if (hit) atomicOr(&bm[s * words + (oi >> 5)], 1u << (oi & 31u));
+                        tlo[s] |= (hit && row < 32u) ? (1u << row) : 0u;
+                        thi[s] |= (hit && row >= 32u) ? (1u << (row - 32u)) : 0u;
+                    }
                 }
             }
         }
-    }
-    __syncwarp();
-    // Read the bitmaps back in index order, one ROW of 32 consecutive words per step (lane = word: conflict-free shared
-    // memory reads; a per-lane contiguous chunk would be a 16-way bank conflict).  Hits are sparse, so most rows are
-    // skipped after one ballot, and the walk stops as soon as nsample indices are out.
-    const int rows = (words + 31) >> 5;
 #pragma unroll
-    for (int s = 0; s < NS; ++s) {
-        const int ns = sc.nsample[s];
-        int *out = sc.idx[s] + ((size_t)b * m + p) * ns;
-        const uint32_t *w = bm + s * words;
-        int base = 0;       // hits written so far (warp-uniform)
-        int first = -1;     // smallest hit index (warp-uniform once found)
-        for (int i = 0; i < rows && base < ns; ++i) {
-            const int wi = i * 32 + (int)lane;
-            uint32_t bits = wi < words ? w[wi] : 0u;
-            const uint32_t nz = __ballot_sync(0xFFFFFFFFu, bits != 0u);
-            if (nz == 0u) continue;
-            const int cnt = __popc(bits);
-            int incl = cnt;
+        for (int s = 0; s < NS; ++s) {
+            tlo[s] = __reduce_or_sync(0xFFFFFFFFu, tlo[s]);
+            thi[s] = __reduce_or_sync(0xFFFFFFFFu, thi[s]);
+        }
+        __syncwarp();
+        // Read the touched rows back in index order (lane = word: conflict-free shared memory reads), clearing them on the
+        // way; all rows are cleared even after nsample indices are out.
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if ((int)lane >= o) incl += v;
+        for (int s = 0; s < NS; ++s) {
+            const int ns = sc.nsample[s];
+            int *out = sc.idx[s] + ((size_t)b * m + p) * ns;
+            uint32_t *w = bm + s * words;
+            int base = 0;       // hits written so far (warp-uniform)
+            int first = -1;     // smallest hit index (warp-uniform once found)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t rows = half ? thi[s] : tlo[s];
+                while (rows) {
+                    const int i = (__ffs(rows) - 1) + 32 * half;
+                    rows &= rows - 1u;
+                    const int wi = i * 32 + (int)lane;
+                    uint32_t bits = 0u;
+                    if (wi < words) { bits = w[wi]; w[wi] = 0u; }
+                    if (base >= ns) continue;   // row only needed clearing
+                    const uint32_t nz = __ballot_sync(0xFFFFFFFFu, bits != 0u);
+                    if (nz == 0u) continue;
+                    const int cnt = __popc(bits);
+                    int incl = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                        if ((int)lane >= o) incl += v;
+                    }
+                    if (first < 0) {
+                        const int l0 = __ffs(nz) - 1;
+                        const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, bits, l0);
+                        first = (i * 32 + l0) * 32 + (__ffs(b0) - 1);
+                    }
+                    int pos = base + incl - cnt;
+                    while (bits && pos < ns) {
+                        const int bit = __ffs(bits) - 1;
+                        bits &= bits - 1u;
+                        out[pos++] = wi * 32 + bit;
+                    }
+                    base += __shfl_sync(0xFFFFFFFFu, incl, 31);
+                }
             }
-            if (first < 0) {
-                const int l0 = __ffs(nz) - 1;
-                const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, bits, l0);
-                first = (i * 32 + l0) * 32 + (__ffs(b0) - 1);
+            if (base > 0) {
+                for (int l = min(base, ns) + (int)lane; l < ns; l += 32) out[l] = first;   // first-hit padding
+            } else {
+                for (int l = (int)lane; l < ns; l += 32) out[l] = 0;
             }
-            int pos = base + incl - cnt;
-            while (bits && pos < ns) {
-                const int bit = __ffs(bits) - 1;
-                bits &= bits - 1u;
-                out[pos++] = wi * 32 + bit;
-            }
-            base += __shfl_sync(0xFFFFFFFFu, incl, 31);
         }
-        if (base > 0) {
-            for (int l = min(base, ns) + (int)lane; l < ns; l += 32) out[l] = first;   // first-hit padding
-        } else {
-            for (int l = (int)lane; l < ns; l += 32) out[l] = 0;
-        }
+        __syncwarp();
     }
 }
 
@@ -247,7 +272,10 @@ extern "C" int spsk_ball_query_msg_grid(int b, int n, int m, int nscales, const 
     const int words = (n + 31) / 32;
     const size_t smem = sizeof(uint32_t) * (size_t)BG_WARPS * nscales * words;
     SPSK_REQUIRE(smem <= 200 * 1024, SPSK_ERR_UNSUPPORTED, "ball_query_msg_grid: bitmap of %zu B does not fit shared memory", smem);
-    dim3 grid((m + BG_WARPS - 1) / BG_WARPS, b);
+    // each warp walks several centres (the bitmap is zeroed once per warp): ~4 waves of CTAs over the GPU
+    const int want = (m + BG_WARPS - 1) / BG_WARPS;
+    const int per_scene = max(1, min(want, (SPSK_NUM_SMS * 6 * 4 + b - 1) / b));
+    dim3 grid(per_scene, b);
 #define SPSK_BG_LAUNCH(NSV)                                                                                          \
     do {                                                                                                             \
         if (smem > 48 * 1024) {                                                                                      \
