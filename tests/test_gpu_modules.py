@@ -124,6 +124,50 @@ def test_sa_module_vs_reference_modules(ref_ops, kind, n):
         assert e <= tol, f"{kind} cls vs reference: relative error {e:.3e} > {tol:.1e}"
 
 
+@pytest.mark.parametrize("stype,n,npoint", [("F-FPS", 1024, 256), ("FS", 1024, 128), ("ds_FPS", 2048, 512), ("ry_FPS", 2048, 512),
+                                             ("Rand", 1000, 200), ("S-FPS", 16384, 4096), ("S-FPS", 2048, 512), ("D-FPS", 3000, 777)])
+def test_every_sampler_vs_reference_modules(ref_ops, stype, n, npoint):
+    """Every sampler string the reference dispatches on (pointnet2_modules.py:284-419) through the
+    drop-in module vs the reference module + its CUDA ops: sampled indices and new_xyz bit-exact (S-FPS incl. its
+    `< 3500 unique` fallback at the small size), features within 1e-3."""
+    if ref_ops is None:
+        pytest.skip("oracle/_ref (rebuilt reference) not present")
+    from spsnet_b200 import backbone as bb
+    from spsnet_b200 import pointnet2_modules as pm
+
+    B, cin = 2, 8
+    kw = dict(npoint_list=[npoint], sample_range_list=[-1], sample_type_list=[stype], radii=[0.8, 1.6], nsamples=[16, 32],
+              mlps=[[cin, 16, 32], [cin, 16, 32]], aggregation_mlp=[32], confidence_mlp=None, num_class=3,
+              ss_radii=[0.2], ss_nsamples=[16])
+    torch.manual_seed(3)
+    mine = pm.PointnetSAModuleMSG_WithSampling(**copy.deepcopy(kw))
+    bb.randomize_bn_stats(mine, seed=3)
+    mine = mine.cuda().eval()
+    ref = ref_ops.modules.PointnetSAModuleMSG_WithSampling(**copy.deepcopy(kw)).cuda().eval()
+    ref.load_state_dict(mine.state_dict())
+    rng = np.random.default_rng(12)
+    xyz = dev(np.ascontiguousarray(scenes.make_batch(33, B, n)[:, :, :3]))
+    feats = dev(rng.standard_normal((B, cin, n)).astype(np.float32))
+    stds = dev(scenes.make_stds(5, B, n)) if stype == "S-FPS" else None
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            kws = {"stds": stds.view(B, 1, n)} if stds is not None else {}
+            torch.manual_seed(99)   # 'Rand' draws torch.randperm on the device
+            want = ref(xyz, feats, None, **kws)
+            torch.manual_seed(99)
+            got = mine(xyz, feats, None, **kws)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    np.testing.assert_array_equal(got[3].cpu().numpy(), want[3].cpu().numpy())
+    np.testing.assert_array_equal(got[0].cpu().numpy(), want[0].cpu().numpy())
+    assert_close(got[1].cpu().numpy(), want[1].cpu().numpy(), what=f"{stype} new_features vs reference")
+    if stds is not None:
+        np.testing.assert_array_equal(got[4].cpu().numpy().reshape(B, -1), want[4].cpu().numpy().reshape(B, -1))
+
+
 def test_training_path_matches_fused(oracle):
     """The autograd composition (used when training) and the fused inference path agree in eval mode."""
     m, cin = _sa_module("l1", seed=2)
