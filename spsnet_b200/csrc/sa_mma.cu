@@ -49,7 +49,8 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
     // carve: [header: barriers + tmem slot][XA][XB][weights]
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + MM_HDR - 16);
-    uint8_t *xa = smem + MM_HDR;
+    uint4 *sched = reinterpret_cast<uint4 *>(smem + MM_HDR);               // a.sched_n entries (streaming chains)
+    uint8_t *xa = smem + MM_HDR + ((a.sched_n * 16 + 127) & ~127);
     uint8_t *xb = xa + a.xa_bytes;
     uint8_t *wst = xb + a.xb_bytes;
     const uint32_t bar0 = smem_u32(bars);
@@ -65,6 +66,11 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int nL = a.nlayers;
+    // The last layer's cout chunks are independent jobs: every CTA walks them from a different starting chunk, so that
+    // at any moment the CTAs stream DIFFERENT weight tiles (148 SMs requesting the same 16 KB in lock-step serialise on
+    // the L2 slices holding those lines).
+    const int rot_last = a.rot_last ? (int)(blockIdx.x % (unsigned)a.L[nL - 1].n_cc) : 0;
+    auto chunk_of = [&](int l, int cci, int n_cc) { int c = cci + (l == nL - 1 ? rot_last : 0); return c >= n_cc ? c - n_cc : c; };
 
     if (tid == 0) {
         for (int s = 0; s < MM_MAX_STAGES; ++s) { mbar_init(W_FULL(s), 1); mbar_init(W_EMPTY(s), 1); }
@@ -104,7 +110,8 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                     const SaLayer &Ly = a.L[l];
                     const bool lring = a.lstages > 0 && l == nL - 1;
                     if (lring) { const long long t0 = pf.now(); mbar_wait(HID_DONE, tcount & 1u); pf.add(PF_PROD_HID, t0); }   // the overlaid activation buffer is dead from here on
-                    for (int cc = 0; cc < Ly.n_cc; ++cc) {
+                    for (int cci = 0; cci < Ly.n_cc; ++cci) {
+                        const int cc = chunk_of(l, cci, Ly.n_cc);
                         const int ncols = min(128, Ly.cpad - cc * 128);
                         for (int kc = 0; kc < Ly.n_kc; ++kc) {
                             const int kw = min(64, Ly.vk - kc * 64);
@@ -192,6 +199,115 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                     }
                 }
             }
+        } else if (a.sched_n > 0) {
+            // Streaming chains: the per-tile schedule (one entry per weight tile) is identical for every tile, so it is
+            // tabulated once in shared memory and the issue loop does no address arithmetic or parameter loads: per entry
+            // one 16-byte read, the waits, <= 4 MMAs, the commits.  (The general loop below executes ~120 instructions
+            // per weight tile on ONE warp -- ~2x the duration of the four 128x128x16 MMAs it issues.)
+            //   .x = activation descriptor lo of the tile's first K block   .y = instruction descriptor
+            //   .z = activation desc hi | weight desc hi << 16
+            //   .w = nk16[0:3) first_kc[3] last_kc[4] cc0[5] need_chunk[6:11) lring[11] hid_done[12] last_layer[13] xbuf[14] layer_start[15]
+            const bool leader = elect_one();
+            if ((tid & 31) == 0) {
+                int e = 0;
+                for (int l = 0; l < nL; ++l) {
+                    const SaLayer &Ly = a.L[l];
+                    const bool last = (l == nL - 1);
+                    const uint32_t x_lo0 = umma_desc_lo(smem_u32((l & 1) ? xb : xa), 128u);
+                    const uint32_t x_hi = umma_desc_hi((uint32_t)Ly.xw * 16u);
+                    for (int cci = 0; cci < Ly.n_cc; ++cci) {
+                        const int cc = chunk_of(l, cci, Ly.n_cc);
+                        const int ncols = min(128, Ly.cpad - cc * 128);
+                        for (int kc = 0; kc < Ly.n_kc; ++kc, ++e) {
+                            const int kw = min(64, Ly.vk - kc * 64);
+                            const int nk16 = kw >> 4;
+                            uint32_t f = (uint32_t)nk16;
+                            if (kc == 0) f |= 1u << 3;
+                            if (kc == Ly.n_kc - 1) f |= 1u << 4;
+                            if (cci == 0) f |= (1u << 5) | ((uint32_t)((kc * 4 + nk16 - 1) >> 2) << 6);
+                            if (a.lstages > 0 && last) f |= 1u << 11;
+                            if (a.lstages > 0 && l == nL - 2 && cci == Ly.n_cc - 1 && kc == Ly.n_kc - 1) f |= 1u << 12;
+                            if (last) f |= 1u << 13;
+                            f |= (uint32_t)(l & 1) << 14;
+                            if (cci == 0 && kc == 0) f |= 1u << 15;
+                            const uint32_t idesc = last ? umma_idesc(128, MM_ROWS) : umma_idesc(128, ncols);
+                            sched[e] = make_uint4(x_lo0 + (uint32_t)kc * 64u, idesc, x_hi | (umma_desc_hi((uint32_t)kw * 16u) << 16), f);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            Prof pf;
+            pf.init(a.prof != nullptr && leader);
+            const long long t_start = pf.now();
+            uint32_t job = 0;
+            int ws = 0, ls = 0;
+            uint32_t wph = 0u, lph = 0u;
+            uint32_t xph[2] = {0u, 0u};
+            uint8_t *lst = ((nL - 2) & 1) ? xb : xa;
+            const uint32_t nbmask = (uint32_t)a.nbuf - 1u;
+            const int nent = a.sched_n;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                int xwait = 0, buf = 0;
+                uint32_t d_tmem = tmem_base;
+                for (int e = 0; e < nent; ++e) {
+                    const uint4 E = sched[e];
+                    const uint32_t f = E.w;
+                    if (f & (1u << 15)) xwait = 0;
+                    if (f & (1u << 3)) {
+                        buf = (int)(job & nbmask);
+                        const uint32_t use = job >> a.nbuf_log2;
+                        if (use > 0) { const long long t0 = pf.now(); mbar_wait(ACC_EMPTY(buf), (use - 1) & 1u); pf.add(PF_MMA_ACC_EMPTY, t0); }
+                        d_tmem = tmem_base + (uint32_t)(buf * 128);
+                    }
+                    uint32_t wbase, wempty;
+                    if (f & (1u << 11)) {
+                        { const long long t0 = pf.now(); mbar_wait(WL_FULL(ls), lph); pf.add(PF_MMA_ISSUE, t0); }   // (profile slot "mma_issue" = last-layer ring waits in this path)
+                        wbase = smem_u32(lst + (size_t)ls * MM_STAGE_BYTES);
+                        wempty = WL_EMPTY(ls);
+                        if (++ls == a.lstages) { ls = 0; lph ^= 1u; }
+                    } else {
+                        { const long long t0 = pf.now(); mbar_wait(W_FULL(ws), wph); pf.add(PF_MMA_W_FULL, t0); }
+                        wbase = smem_u32(wst + (size_t)ws * MM_STAGE_BYTES);
+                        wempty = W_EMPTY(ws);
+                        if (++ws == a.nstages) { ws = 0; wph ^= 1u; }
+                    }
+                    if (f & (1u << 5)) {
+                        const int need = (int)((f >> 6) & 31u);
+                        const int xbuf = (int)((f >> 14) & 1u);
+                        while (xwait <= need) {
+                            const long long t0 = pf.now();
+                            mbar_wait(XR(xbuf, xwait), (xph[xbuf] >> xwait) & 1u);
+                            pf.add(PF_MMA_XR, t0);
+                            xph[xbuf] ^= (1u << xwait);
+                            ++xwait;
+                        }
+                    }
+                    tc_fence_after();
+                    if (leader) {
+                        const uint32_t w_lo = umma_desc_lo(wbase, 128u);
+                        const uint32_t x_hi = E.z & 0xFFFFu, w_hi = E.z >> 16;
+                        const int nk16 = (int)(f & 7u);
+                        const uint32_t acc0 = (f & (1u << 3)) ? 0u : 1u;
+                        if (!(f & (1u << 13))) {
+                            umma_f16_lohi(d_tmem, E.x, x_hi, w_lo, w_hi, E.y, acc0);
+                            for (int j = 1; j < nk16; ++j) umma_f16_lohi(d_tmem, E.x + 16u * j, x_hi, w_lo + 16u * j, w_hi, E.y, 1u);
+                        } else {
+                            umma_f16_lohi(d_tmem, w_lo, w_hi, E.x, x_hi, E.y, acc0);
+                            for (int j = 1; j < nk16; ++j) umma_f16_lohi(d_tmem, w_lo + 16u * j, w_hi, E.x + 16u * j, x_hi, E.y, 1u);
+                        }
+                        umma_commit(wempty);   // stage reusable once these MMAs retire
+                        if (f & (1u << 4)) {
+                            umma_commit(ACC_FULL(buf));
+                            if (f & (1u << 12)) umma_commit(HID_DONE);
+                        }
+                    }
+                    __syncwarp();
+                    if (f & (1u << 4)) ++job;
+                }
+            }
+            pf.add(PF_MMA_TOTAL, t_start);
+            pf.flush(a.prof);
         } else {
             const bool leader = elect_one();
             Prof pf;
@@ -214,7 +330,8 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                     const uint32_t x_hi = umma_desc_hi((uint32_t)Ly.xw * 16u);
                     const int nk2 = 2 * (Ly.kpad >> 4);   // split: x blocks [0, nk2) are [hi | lo]; v >= nk2 re-reads hi
                     int xwait = 0;                        // readiness chunks of this layer's input already waited for
-                    for (int cc = 0; cc < Ly.n_cc; ++cc, ++job) {
+                    for (int cci = 0; cci < Ly.n_cc; ++cci, ++job) {
+                        const int cc = chunk_of(l, cci, Ly.n_cc);
                         const int ncols = min(128, Ly.cpad - cc * 128);  // couts in this chunk (multiple of 16)
                         const int buf = (int)(job & nbmask);
                         const uint32_t use = job >> a.nbuf_log2;
@@ -239,7 +356,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                                 if (++ws == a.nstages) { ws = 0; wph ^= 1u; }
                             }
                             const int nk16 = kw >> 4;
-                            if (cc == 0) {
+                            if (cci == 0) {
                                 // the activation chunks this weight tile touches must have landed (epilogue of layer l-1 / gather)
                                 int need = (kc * 4 + nk16 - 1) >> 2;
                                 if (a.split) need = Ly.n_xc - 1;   // hi | lo | hi re-read: simply wait for the whole (narrow) operand
@@ -281,7 +398,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                                 if (!a.resident) umma_commit(wempty);   // stage reusable once these MMAs retire
                                 if (kc == Ly.n_kc - 1) {
                                     umma_commit(ACC_FULL(buf));
-                                    if (a.lstages > 0 && l == nL - 2 && cc == Ly.n_cc - 1) umma_commit(HID_DONE);   // its input buffer may now hold weight tiles
+                                    if (a.lstages > 0 && l == nL - 2 && cci == Ly.n_cc - 1) umma_commit(HID_DONE);   // its input buffer may now hold weight tiles
                                 }
                                 pf.add(PF_MMA_COMMIT, t_c);
                             }
@@ -506,8 +623,9 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                 const long long bb0 = q0 / a.m;
                 const int p0 = (int)(q0 - bb0 * a.m);
                 const size_t sstride = (size_t)a.c_total * a.m;
-                for (int cc = 0; cc < Ly.n_cc; ++cc, ++job) {
+                for (int cci = 0; cci < Ly.n_cc; ++cci, ++job) {
                     if (G == 2 && (job & 1u) != grp) continue;
+                    const int cc = chunk_of(nL - 1, cci, Ly.n_cc);
                     const int buf = (int)(job & ((uint32_t)a.nbuf - 1u));
                     { const long long t0 = pf.now(); mbar_wait(ACC_FULL(buf), (job >> a.nbuf_log2) & 1u); pf.add(PF_EPI_WAIT_POOL, t0); }
                     tc_fence_after();
@@ -568,7 +686,7 @@ static unsigned long long *g_sa_prof = nullptr;
 // ---- host-side planning ---------------------------------------------------------------------------------
 struct SaPlan {
     SaLayer L[MM_MAX_LAYERS];
-    int xa_bytes, xb_bytes, w_total, l0_off, resident, nstages, lstages, ctas, tmem_cols, nbuf, smem;
+    int xa_bytes, xb_bytes, w_total, l0_off, resident, nstages, lstages, ctas, tmem_cols, nbuf, smem, sched_n;
 };
 
 constexpr int PR_HDR_BYTES = 2048;   // header of the pair kernel (sa_mma_pair.cu)
@@ -647,6 +765,15 @@ static int sa_plan(const spsk_sa_mma_desc *d, SaPlan *P) {
     }
     P->tmem_cols = ctas == 1 ? 512 : (ctas == 2 ? 256 : 128);
     P->nbuf = P->tmem_cols / 128;
+    // streaming chains: tabulate the per-tile MMA schedule in shared memory when it fits (one 16-byte entry per weight tile)
+    P->sched_n = 0;
+    if (!pair && !P->resident && !split && !getenv("SPSK_SA_NO_SCHED")) {
+        int ntab = 0;
+        for (int l = 0; l < nL; ++l) ntab += P->L[l].n_cc * P->L[l].n_kc;
+        const int tab_bytes = (ntab * 16 + 127) & ~127;
+        const int per = (sm_bytes / ctas - 1024) & ~127;
+        if (ntab <= MM_SCHED_MAX && P->smem + tab_bytes <= per) { P->sched_n = ntab; P->smem += tab_bytes; }
+    }
     // shared-memory floor so that no more than `ctas` CTAs land on an SM (their TMEM allocations would not fit)
     const int floor_bytes = (sm_bytes / (ctas + 1) - 1024 + 256) & ~127;
     if (P->smem < floor_bytes) P->smem = floor_bytes;
@@ -725,6 +852,8 @@ extern "C" int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stre
     SPSK_REQUIRE(ntiles <= 0x7FFFFFFF, SPSK_ERR_UNSUPPORTED, "sa_mma: too many rows");
     a.ntiles = (int)ntiles;
     a.lstages = P.lstages;
+    a.sched_n = P.sched_n;
+    a.rot_last = (P.L[d->nlayers - 1].n_cc > 1 && getenv("SPSK_SA_ROT")) ? 1 : 0;   // opt-in: measured neutral on B200 (the weight stream is not L2 hot-line bound)
     a.l0_fused = d->l0_fused ? 1 : 0;
     a.l0_off = P.l0_off;
     SPSK_REQUIRE(!a.l0_fused || P.resident, SPSK_ERR_UNSUPPORTED, "sa_mma: layer-0 fusion needs the chain resident in shared memory");

@@ -11,6 +11,7 @@ constexpr int MM_STAGE_BYTES = 16384; // largest weight tile: [128 cout][64 k] f
 constexpr int MM_MAX_LAYERS = 4;
 constexpr int MM_MAX_STAGES = 8;
 constexpr int MM_HDR = 1024;          // barriers + TMEM slot
+constexpr int MM_SCHED_MAX = 104;     // tabulated weight tiles per row tile (16 bytes each, placed after the header)
 constexpr int MM_MAX_XC = 16;         // 64-wide K chunks per activation buffer (K <= 1024)
 
 struct SaLayer {
@@ -35,6 +36,8 @@ struct SaArgs {
     int nstages, resident, w_total, tmem_cols, nbuf, nbuf_log2;
     int l0_fused, l0_off;   // split chains: layer 0 (K <= 11 real inputs) is evaluated in fp32 by the gather threads from the
                             // [16][cpad0] fp32 weights + bias appended to the resident weights at byte l0_off; the MMA chain starts at layer 1
+    int rot_last;    // rotate the last layer's cout-chunk order by blockIdx (de-synchronises the CTAs' weight streams)
+    int sched_n;     // > 0: streaming chain whose per-tile MMA schedule (sched_n weight tiles) is tabulated in shared memory
     int narrow;      // resident chain with one job per layer: the MMA warp runs the register-resident fast loop
     int lstages;     // > 0: the last layer streams its weights through `lstages` extra 16 KB slots overlaid on the activation
                      // buffer that is dead while it runs (the input of layer nlayers-2)
