@@ -273,7 +273,8 @@ SPSK_API int spsk_sa_mma_set_profile(unsigned long long *counters);
 typedef struct spsk_pw_desc {
     int rows, k, ldx, n, relu;
     int split;  /* 1: fp32-grade arithmetic on hi + lo fp16 halves: x rows hold hi in columns [0, k) and lo = fp16(v - hi) in
-                   [xlo, xlo + k); wtiles pack W' = [Wh ; Wh ; Wl] (3k rows of K); y = xh.Wh + xl.Wh + xh.Wl */
+                   [xlo, xlo + k); wtiles hold, per (cout chunk, 64-wide k chunk), the Wh tile immediately followed by the Wl tile
+                   (32 KB); y = xh.Wh + xl.Wh + xh.Wl */
     int xlo;
     const void *x;
     const void *wtiles;

@@ -22,13 +22,16 @@ namespace spsk {
 constexpr int PW_ROWS = 128;
 constexpr int PW_THREADS = 192;
 constexpr int PW_TILE_BYTES = 16384;                       // 128 rows x 64 k fp16
-// <stages, lag>: ring depth and how many chunks of cp.async stay in flight behind the one being issued.
-// short K: <3, 2> (96 KB, two CTAs per SM);  long K (the 1536-wide aggregation, x3 in split mode): <6, 4> (192 KB)
-constexpr int pw_smem(int stages) { return 256 + stages * 2 * PW_TILE_BYTES; }
+// <stages, lag, split>: ring depth, how many chunks of cp.async stay in flight behind the one being issued, arithmetic.
+// plain: a stage = [X chunk | W tile] = 32 KB; short K <3, 2> (96 KB, two CTAs per SM), long K <6, 4> (192 KB).
+// split: a stage = [Xh | Xl | Wh | Wl] = 64 KB (<3, 2>, 192 KB): each 64-wide chunk of the TRUE K is staged once and
+//        multiplied three ways (Xh.Wh + Xl.Wh + Xh.Wl) -- 2/3 of the shared-memory / L2 traffic of streaming the
+//        K-concatenated [Xh | Xl | Xh] . [Wh ; Wh ; Wl] product, and a third of the pipeline steps.
+constexpr int pw_smem(int stages, bool split) { return 256 + stages * (split ? 4 : 2) * PW_TILE_BYTES; }
 
 struct PwArgs {
     int rows, k, ldx, n, npad, n_kc, relu;
-    int split, xlo, vk;          // split: x rows are [hi (k) ... lo (k) at column xlo]; the MMAs run over vk = 3k = [hi | lo | hi]
+    int split, xlo;              // split: x rows are [hi (k) ... lo (k) at column xlo]
     int o16lo;                   // > 0: out16 also receives the fp16 residual of every value at column o16lo + c
     const __half *x;
     const __half *wtiles;
@@ -38,9 +41,10 @@ struct PwArgs {
     float *out_pm; int ldpm;
 };
 
-template <int PW_STAGES, int PW_LAG>
-__global__ void __launch_bounds__(PW_THREADS, PW_STAGES <= 3 ? 2 : 1)
+template <int PW_STAGES, int PW_LAG, bool SPLIT>
+__global__ void __launch_bounds__(PW_THREADS, (PW_STAGES <= 3 && !SPLIT) ? 2 : 1)
 pw_mma_kernel(const PwArgs a) {
+    constexpr int STAGE_BYTES = (SPLIT ? 4 : 2) * PW_TILE_BYTES;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 192);
@@ -49,8 +53,8 @@ pw_mma_kernel(const PwArgs a) {
     auto FULL = [&](int s) { return bar0 + 8u * s; };
     auto EMPTY = [&](int s) { return bar0 + 8u * (PW_STAGES + s); };
     const uint32_t ACC_FULL = bar0 + 8u * (2 * PW_STAGES);
-    auto XS = [&](int s) { return stage0 + (size_t)s * 2 * PW_TILE_BYTES; };
-    auto WS = [&](int s) { return stage0 + (size_t)s * 2 * PW_TILE_BYTES + PW_TILE_BYTES; };
+    auto XS = [&](int s) { return stage0 + (size_t)s * STAGE_BYTES; };                                        // [Xh | Xl]
+    auto WS = [&](int s) { return stage0 + (size_t)s * STAGE_BYTES + (SPLIT ? 2 : 1) * PW_TILE_BYTES; };       // [Wh | Wl]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile = blockIdx.x, cc = blockIdx.y;
@@ -74,8 +78,9 @@ pw_mma_kernel(const PwArgs a) {
             const uint32_t ph = (kc / PW_STAGES) & 1u;
             mbar_wait(EMPTY(s), ph ^ 1u);
             if (leader) {
-                mbar_expect_tx(FULL(s), PW_TILE_BYTES);
-                bulk_g2s(smem_u32(WS(s)), a.wtiles + (size_t)(cc * a.n_kc + kc) * (PW_TILE_BYTES / 2), PW_TILE_BYTES, FULL(s));
+                constexpr uint32_t WB = (SPLIT ? 2 : 1) * PW_TILE_BYTES;   // split: [Wh tile | Wl tile] are adjacent in the packing
+                mbar_expect_tx(FULL(s), WB);
+                bulk_g2s(smem_u32(WS(s)), a.wtiles + (size_t)(cc * a.n_kc + kc) * (WB / 2), WB, FULL(s));
             }
             __syncwarp();
         }
@@ -88,11 +93,16 @@ pw_mma_kernel(const PwArgs a) {
             mbar_wait(FULL(s), ph);
             tc_fence_after();
             const uint32_t xb = smem_u32(XS(s)), wb = smem_u32(WS(s));
-            const int nk16 = min(4, (a.vk - kc * 64) / 16);
+            const int nk16 = min(4, (a.k - kc * 64) / 16);
             if (leader) {
-                for (int j = 0; j < nk16; ++j)
-                    umma_f16(tmem_base, umma_desc(xb + (uint32_t)j * 256u, 128u, 1024u), umma_desc(wb + (uint32_t)j * 256u, 128u, 1024u),
-                             idesc, (kc | j) ? 1u : 0u);
+                for (int j = 0; j < nk16; ++j) {
+                    const uint64_t xh = umma_desc(xb + (uint32_t)j * 256u, 128u, 1024u), wh = umma_desc(wb + (uint32_t)j * 256u, 128u, 1024u);
+                    umma_f16(tmem_base, xh, wh, idesc, (kc | j) ? 1u : 0u);
+                    if (SPLIT) {
+                        umma_f16(tmem_base, umma_desc(xb + PW_TILE_BYTES + (uint32_t)j * 256u, 128u, 1024u), wh, idesc, 1u);   // Xl . Wh
+                        umma_f16(tmem_base, xh, umma_desc(wb + PW_TILE_BYTES + (uint32_t)j * 256u, 128u, 1024u), idesc, 1u);   // Xh . Wl
+                    }
+                }
                 umma_commit(EMPTY(s));
                 if (kc == a.n_kc - 1) umma_commit(ACC_FULL);
             }
@@ -107,7 +117,7 @@ pw_mma_kernel(const PwArgs a) {
             const uint32_t ph = (kc / PW_STAGES) & 1u;
             mbar_wait(EMPTY(s), ph ^ 1u);
             const uint32_t xs = smem_u32(XS(s));
-            const int ng = min(8, (a.vk - kc * 64) / 8);   // valid 16-byte groups in this chunk
+            const int ng = min(8, (a.k - kc * 64) / 8);   // valid 16-byte groups in this chunk
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
                 const int r = warp * 32 + it * 8 + r8;
@@ -118,9 +128,10 @@ pw_mma_kernel(const PwArgs a) {
                 for (int j = 0; j < 2; ++j) {
                     const int g = gq + 4 * j;
                     if (g < ng) {
-                        int col = kc * 64 + g * 8;   // virtual k -> source column ([hi | lo | hi] when split)
-                        if (a.split) col = col < a.k ? col : (col < 2 * a.k ? a.xlo + (col - a.k) : col - 2 * a.k);
-                        cp_async16(xs + (uint32_t)(r >> 3) * 1024u + (uint32_t)g * 128u + (uint32_t)(r & 7) * 16u, src + col, ok ? 16u : 0u);
+                        const int col = kc * 64 + g * 8;
+                        const uint32_t dst = xs + (uint32_t)(r >> 3) * 1024u + (uint32_t)g * 128u + (uint32_t)(r & 7) * 16u;
+                        cp_async16(dst, src + col, ok ? 16u : 0u);
+                        if (SPLIT) cp_async16(dst + PW_TILE_BYTES, src + a.xlo + col, ok ? 16u : 0u);
                     }
                 }
             }
@@ -217,8 +228,7 @@ extern "C" int spsk_pw_mma_forward(const spsk_pw_desc *d, spsk_stream_t stream) 
     a.npad = (d->n + 15) / 16 * 16;
     a.split = d->split ? 1 : 0;
     a.xlo = d->xlo;
-    a.vk = a.split ? 3 * d->k : d->k;
-    a.n_kc = (a.vk + 63) / 64;
+    a.n_kc = (d->k + 63) / 64;
     if (a.split)
         SPSK_REQUIRE(d->xlo >= d->k && d->xlo % 8 == 0 && d->xlo + d->k <= d->ldx, SPSK_ERR_INVALID_ARG,
                      "pw_mma: split input needs the lo part at a column xlo >= k, multiple of 8, inside ldx");
@@ -239,19 +249,22 @@ extern "C" int spsk_pw_mma_forward(const spsk_pw_desc *d, spsk_stream_t stream) 
                      SPSK_ERR_INVALID_ARG, "pw_mma: fp16 output needs ld16, n16 multiples of 8, n <= n16 <= ld16, 16-byte alignment");
     a.out_pm = d->out_pm; a.ldpm = d->ldpm;
     if (a.out_pm) SPSK_REQUIRE(d->ldpm >= d->n, SPSK_ERR_INVALID_ARG, "pw_mma: ldpm < n");
-    const bool deep = a.n_kc >= 12;
-    static SmemAttrOnce attr_s, attr_d;
-    if (deep) {
-        if (int rc = attr_d.ensure(reinterpret_cast<const void *>(pw_mma_kernel<6, 4>), pw_smem(6), "pw_mma_kernel<6,4>")) return rc;
+    const bool deep = !a.split && a.n_kc >= 12;
+    static SmemAttrOnce attr_s, attr_d, attr_x;
+    if (a.split) {
+        if (int rc = attr_x.ensure(reinterpret_cast<const void *>(pw_mma_kernel<3, 2, true>), pw_smem(3, true), "pw_mma_kernel<3,2,split>")) return rc;
+    } else if (deep) {
+        if (int rc = attr_d.ensure(reinterpret_cast<const void *>(pw_mma_kernel<6, 4, false>), pw_smem(6, false), "pw_mma_kernel<6,4>")) return rc;
     } else {
-        if (int rc = attr_s.ensure(reinterpret_cast<const void *>(pw_mma_kernel<3, 2>), pw_smem(3), "pw_mma_kernel<3,2>")) return rc;
+        if (int rc = attr_s.ensure(reinterpret_cast<const void *>(pw_mma_kernel<3, 2, false>), pw_smem(3, false), "pw_mma_kernel<3,2>")) return rc;
     }
     // n16 may extend past npad (zero columns up to the consumer's K padding): cover them with column tiles
     const int ncover = a.out16 ? max(a.npad, a.n16) : a.npad;
     a.npad = (ncover + 15) / 16 * 16;
     dim3 grid((unsigned)((d->rows + PW_ROWS - 1) / PW_ROWS), (unsigned)((a.npad + 127) / 128));
-    if (deep) pw_mma_kernel<6, 4><<<grid, PW_THREADS, pw_smem(6), as_stream(stream)>>>(a);
-    else pw_mma_kernel<3, 2><<<grid, PW_THREADS, pw_smem(3), as_stream(stream)>>>(a);
+    if (a.split) pw_mma_kernel<3, 2, true><<<grid, PW_THREADS, pw_smem(3, true), as_stream(stream)>>>(a);
+    else if (deep) pw_mma_kernel<6, 4, false><<<grid, PW_THREADS, pw_smem(6, false), as_stream(stream)>>>(a);
+    else pw_mma_kernel<3, 2, false><<<grid, PW_THREADS, pw_smem(3, false), as_stream(stream)>>>(a);
     SPSK_LAUNCH_CHECK("pw_mma_kernel");
     return SPSK_OK;
 }

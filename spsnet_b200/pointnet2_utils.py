@@ -598,7 +598,8 @@ def sa_mma_forward(*, xyz, new_xyz, idx, chain: MmaChain, twin=None, features=No
 class PwLayer:
     """One folded Conv1d(k=1)[+BN][+ReLU] layer packed for spsk_pw_mma_forward: W (c_out x K) as 128-cout x 64-k
     fp16 tiles (16 KB each, canonical K-major layout), zero padded to cover ceil128(max(c_out, n16)) couts.
-    split=True packs W' = [Wh ; Wh ; Wl] (K = 3 * ceil16(c_in)) for inputs carried as hi + lo fp16 halves."""
+    split=True packs, per (cout chunk, k chunk), the Wh tile followed by the Wl tile, for inputs carried as hi + lo
+    fp16 halves (y = xh.Wh + xl.Wh + xh.Wl)."""
 
     def __init__(self, wt: torch.Tensor, bias: torch.Tensor, relu: bool, split: bool = False):
         dev = wt.device
@@ -608,19 +609,21 @@ class PwLayer:
         self.k = _ceil(self.c_in, 16)
         self.n16 = _ceil(self.c_out, 16)
         ncov = _ceil(max(self.c_out, self.n16), 128)
-        W = torch.zeros((self.k, ncov), dtype=torch.float32, device=dev)
-        W[:self.c_in, :self.c_out] = wt
+        n_cc, n_kc = ncov // 128, _ceil(self.k, 64) // 64
+        Wt = torch.zeros((ncov, n_kc * 64), dtype=torch.float32, device=dev)
+        Wt[:self.c_out, :self.c_in] = wt.t()
+
+        def tiles(M):  # (ncov, n_kc*64) -> (cc, kc, rg, kg, r, k) canonical 16 KB tiles
+            return M.view(n_cc, 16, 8, n_kc, 8, 8).permute(0, 3, 1, 4, 2, 5).contiguous()
+
         if self.split:
-            Wh = W.half()
-            Wv = torch.cat([Wh, Wh, (W - Wh.float()).half()], dim=0)
+            Wh = Wt.half()
+            Wl = (Wt - Wh.float()).half()
+            # per (cc, kc): the Wh tile immediately followed by the Wl tile (one 32 KB bulk copy per pipeline step)
+            T = torch.stack([tiles(Wh), tiles(Wl)], dim=2)
         else:
-            Wv = W.half()
-        vk = Wv.shape[0]
-        n_cc, n_kc = ncov // 128, _ceil(vk, 64) // 64
-        Wt = torch.zeros((ncov, n_kc * 64), dtype=torch.float16, device=dev)
-        Wt[:, :vk] = Wv.t()
-        T = Wt.view(n_cc, 16, 8, n_kc, 8, 8).permute(0, 3, 1, 4, 2, 5).contiguous()  # (cc, kc, rg, kg, r, k)
-        self.wtiles = T.reshape(-1)
+            T = tiles(Wt.half())
+        self.wtiles = T.reshape(-1).contiguous()
         self.bias = torch.zeros(ncov, dtype=torch.float32, device=dev)
         self.bias[:self.c_out] = bias
 
