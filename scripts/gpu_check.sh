@@ -21,7 +21,7 @@ fi
 # ncu launch list (cold-cache, serialised: shares only) -- only after the same command exited 0 without ncu
 NCU_CMD="python bench.py --steps 2 --warmup 3 --depth 1 --no-graph --no-profile --cpu-sample 0 --pool 2"
 timeout 300 $NCU_CMD > gpurun_out/ncu_plain.log 2>&1 && \
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $NCU_CMD > gpurun_out/ncu_run.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches_check.csv $NCU_CMD > gpurun_out/ncu_run.log 2>&1
 echo "ncu exit: $?" >> gpurun_out/ncu_run.log
 tail -5 gpurun_out/pytest_gpu.log; tail -2 gpurun_out/golden.log; tail -2 gpurun_out/smoke.log
 for f in bench_ours bench_ours_d1 bench_ours_eager bench_ref; do echo "== $f"; cat gpurun_out/$f.json 2>/dev/null | cut -c1-1500; tail -2 gpurun_out/$f.err 2>/dev/null; done
