@@ -286,6 +286,67 @@ typedef struct spsk_pw_desc {
 } spsk_pw_desc;
 SPSK_API int spsk_pw_mma_forward(const spsk_pw_desc *d, spsk_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Section 3 -- the consumer of the path: rotated IoU / NMS and the fused
+ * IA-SSD head post-processing.  Boxes are (N,7) f32 [x, y, z, dx, dy, dz, heading], contiguous.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* ans_overlap[i,j] = area of the BEV intersection of boxes_a[i] and boxes_b[j].  Replaces boxes_overlap_bev_gpu
+ * (pcdet/ops/iou3d_nms/src/iou3d_nms.cpp:48-67 -> src/iou3d_nms_kernel.cu:236-250). */
+SPSK_API int spsk_boxes_overlap_bev(int num_a, const float *boxes_a, int num_b, const float *boxes_b,
+                                    float *ans_overlap, spsk_stream_t stream);
+/* ans_iou[i,j] = rotated BEV IoU.  Replaces boxes_iou_bev_gpu (src/iou3d_nms.cpp:69-88 ->
+ * src/iou3d_nms_kernel.cu:251-265). */
+SPSK_API int spsk_boxes_iou_bev(int num_a, const float *boxes_a, int num_b, const float *boxes_b, float *ans_iou,
+                                spsk_stream_t stream);
+/* ans_iou[i,j] = 3-D IoU (BEV overlap x height overlap over the union volume): one launch for the kernel + ~14
+ * torch ops of boxes_iou3d_gpu (pcdet/ops/iou3d_nms/iou3d_nms_utils.py:48-81), same per-op fp32 rounding. */
+SPSK_API int spsk_boxes_iou3d(int num_a, const float *boxes_a, int num_b, const float *boxes_b, float *ans_iou,
+                              spsk_stream_t stream);
+
+/* Greedy NMS over boxes already sorted by descending score, `batch` independent scenes per call.  Replaces nms_gpu
+ * (normal = 0: rotated BEV IoU) and nms_normal_gpu (normal = 1: axis-aligned BEV IoU), src/iou3d_nms.cpp:90-188 ->
+ * src/iou3d_nms_kernel.cu:267-365, INCLUDING the host-side suppression loop, which runs on the device here: the
+ * call never allocates, never copies to the host and never synchronises.
+ *   boxes (batch,n,7); counts (batch) device ints = boxes actually present per scene (NULL: all n);
+ *   keep (batch,n) int64 out: positions (into the sorted order) of the surviving boxes, ascending;
+ *   num_keep (batch) int32 out; workspace >= spsk_nms_workspace_bytes(batch,n) (the suppression bit mask). */
+#define SPSK_NMS_MAX_N 32768
+SPSK_API long long spsk_nms_workspace_bytes(int batch, int n);
+SPSK_API int spsk_nms(int batch, int n, const float *boxes, const int *counts, float thresh, int normal,
+                      long long *keep, int *num_keep, void *workspace, long long workspace_bytes,
+                      spsk_stream_t stream);
+
+/* IA-SSD head post-processing for a whole batch in 3 launches: per centre label = argmax class logit, score =
+ * sigmoid(max logit), box = PointResidual_BinOri_Coder.decode_torch (pcdet/utils/box_coder_utils.py:279-319,
+ * called from point_head_template.py:193-207); per scene score >= score_thresh -> top pre_max by score ->
+ * rotated NMS -> first post_max survivors (detector3d_template.py:207-290 non-multi-class branch,
+ * model_nms_utils.py:6-27).  Replaces ~40 torch ops + cudaMalloc + D2H mask copy + host loop PER SCENE.
+ *   cls (batch*m, ld_cls) logits; reg (batch*m, ld_reg) box encodings (6 + 2*bin_size used);
+ *   centers (batch*m, ld_centers): xyz of each centre (pass centers + 1 with ld 4 for [bs,x,y,z] rows);
+ *   mean_size (num_class,3) device floats or NULL (use_mean_size = False);
+ *   decoded, every row: box_preds (batch*m,7), scores (batch*m), labels (batch*m) int32 in 1..num_class;
+ *   padded detections: out_boxes (batch,post_max,7), out_scores (batch,post_max), out_labels (batch,post_max)
+ *   int64, out_index (batch,post_max) int64 = centre index within the scene (-1 padding), out_count (batch).
+ * Optional parts: reg = NULL -> box_preds is an INPUT (already decoded boxes); cls = NULL -> labels is an input
+ * (decode with given classes, = box_coder.decode_torch(enc, points, pred_classes)); out_boxes = NULL -> decode only
+ * (one launch, no workspace needed). */
+#define SPSK_DETECT_MAX_M 4096
+typedef struct spsk_detect_desc {
+    int batch, m, num_class, bin_size;
+    const float *cls; int ld_cls;
+    const float *reg; int ld_reg;
+    const float *centers; int ld_centers;
+    const float *mean_size;
+    float score_thresh, nms_thresh;
+    int nms_normal, pre_max, post_max;
+    float *box_preds; float *scores; int *labels;
+    float *out_boxes; float *out_scores; long long *out_labels; long long *out_index; int *out_count;
+    void *workspace; long long workspace_bytes;
+} spsk_detect_desc;
+SPSK_API long long spsk_detect_workspace_bytes(int batch, int m);
+SPSK_API int spsk_detect_postprocess(const spsk_detect_desc *d, spsk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,4 +50,42 @@ BB=$OUT/pcdet/models/backbones_3d
 mkdir -p "$BB"
 install -m 0644 "$REF/pcdet/models/backbones_3d/IASSD_backbone.py" "$REF/pcdet/models/backbones_3d/PAGNet_backbone.py" "$BB/"
 for d in "$OUT/pcdet" "$OUT/pcdet/ops" "$OUT/pcdet/ops/pointnet2" "$PKG" "$OUT/pcdet/models" "$BB"; do : > "$d/__init__.py"; done
+
+# ---- the consumer of the path (head + rotated NMS), rebuilt the same way -----------
+#   oracle/_ref/pcdet/ops/iou3d_nms/iou3d_nms_cuda.so            <- 4 TUs (incl. the reference's CPU IoU)
+#   oracle/_ref/pcdet/ops/roiaware_pool3d/roiaware_pool3d_cuda.so <- 2 TUs (imported by box_utils / the head)
+#   + installed copies of iou3d_nms_utils.py, roiaware_pool3d_utils.py, model_nms_utils.py, IASSD_head.py,
+#     point_head_template.py and pcdet/utils/{box_coder_utils,box_utils,loss_utils,common_utils}.py
+build_ext () {  # name  srcdir  outdir  files...
+  local name=$1 sdir=$2 odir=$3; shift 3
+  local o=$OBJ/$name; mkdir -p "$o" "$odir"
+  local d="-DTORCH_EXTENSION_NAME=$name -DTORCH_API_INCLUDE_EXTENSION_H"
+  local ps=()
+  for f in "$@"; do
+    local b=${f%.*}
+    if [ "${f##*.}" = cu ]; then
+      ( [ "$o/$b.o" -nt "$sdir/src/$f" ] || nvcc -std=c++17 -O2 -w -Xcompiler -fPIC $TI -I$PI -gencode arch=compute_100a,code=sm_100a \
+           --expt-relaxed-constexpr $d -c "$sdir/src/$f" -o "$o/$b.o" ) &
+    else
+      ( [ "$o/$b.o" -nt "$sdir/src/$f" ] || g++ -std=c++17 -O2 -fPIC -w $TI -I$PI -I/usr/local/cuda/include $d -c "$sdir/src/$f" -o "$o/$b.o" ) &
+    fi
+    ps+=($!)
+  done
+  for p in "${ps[@]}"; do wait "$p"; done
+  g++ -shared -o "$odir/$name.so" "$o"/*.o -L"$TDIR/lib" -lc10 -ltorch -ltorch_cpu -ltorch_python \
+      -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,"$TDIR/lib"
+}
+IOU=$OUT/pcdet/ops/iou3d_nms
+ROI=$OUT/pcdet/ops/roiaware_pool3d
+build_ext iou3d_nms_cuda "$REF/pcdet/ops/iou3d_nms" "$IOU" iou3d_cpu.cpp iou3d_nms_api.cpp iou3d_nms.cpp iou3d_nms_kernel.cu
+build_ext roiaware_pool3d_cuda "$REF/pcdet/ops/roiaware_pool3d" "$ROI" roiaware_pool3d.cpp roiaware_pool3d_kernel.cu
+install -m 0644 "$REF/pcdet/ops/iou3d_nms/iou3d_nms_utils.py" "$IOU/"
+install -m 0644 "$REF/pcdet/ops/roiaware_pool3d/roiaware_pool3d_utils.py" "$ROI/"
+UT=$OUT/pcdet/utils; MU=$OUT/pcdet/models/model_utils; DH=$OUT/pcdet/models/dense_heads
+mkdir -p "$UT" "$MU" "$DH"
+install -m 0644 "$REF/pcdet/utils/box_coder_utils.py" "$REF/pcdet/utils/box_utils.py" "$REF/pcdet/utils/loss_utils.py" \
+                "$REF/pcdet/utils/common_utils.py" "$UT/"
+install -m 0644 "$REF/pcdet/models/model_utils/model_nms_utils.py" "$MU/"
+install -m 0644 "$REF/pcdet/models/dense_heads/IASSD_head.py" "$REF/pcdet/models/dense_heads/point_head_template.py" "$DH/"
+for d in "$IOU" "$ROI" "$UT" "$MU" "$DH"; do : > "$d/__init__.py"; done
 echo "build_ref: ok -> $PKG"

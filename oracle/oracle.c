@@ -318,6 +318,154 @@ ORC_API uint32_t orc_fps_rank(int k, int S) {
     return rev | ((uint32_t)k >> L);
 }
 
+/* =====================================================================================================
+ * rotated BEV IoU / 3-D IoU / NMS of pcdet/ops/iou3d_nms, restated literally
+ * (per-pair trigonometry, atan2 inside every comparison of the bubble sort, host-style greedy loop), i.e.
+ * deliberately NOT organised like the CUDA kernels it checks.
+ * PARITY PIN: tests/golden/iou3d_reference_cpu.npz holds outputs of the reference's own CPU implementation
+ * (src/iou3d_cpu.cpp, compiled unmodified into oracle/_ref and run in the build container by
+ * tests/golden/make_golden_iou3d.py); tests/test_oracle_cpu.py requires bit-equality with it.
+ * ===================================================================================================== */
+typedef struct { float x, y; } orc_pt;
+
+static float orc_cross3(orc_pt p1, orc_pt p2, orc_pt p0) { /* iou3d_nms_kernel.cu:39-41 */
+    return (p1.x - p0.x) * (p2.y - p0.y) - (p2.x - p0.x) * (p1.y - p0.y);
+}
+static float orc_fmin(float a, float b) { return a > b ? b : a; } /* iou3d_cpu.cpp:30-36 */
+static float orc_fmax(float a, float b) { return a > b ? a : b; }
+
+static int orc_in_box(const float *box, orc_pt p) { /* iou3d_nms_kernel.cu:48-58 */
+    const float margin = 1e-2f;
+    float c = cosf(-box[6]), s = sinf(-box[6]);
+    float rx = (p.x - box[0]) * c + (p.y - box[1]) * (-s);
+    float ry = (p.x - box[0]) * s + (p.y - box[1]) * c;
+    return fabsf(rx) < box[3] / 2 + margin && fabsf(ry) < box[4] / 2 + margin;
+}
+
+static int orc_seg_x(orc_pt p1, orc_pt p0, orc_pt q1, orc_pt q0, orc_pt *ans) { /* iou3d_nms_kernel.cu:60-96 */
+    const float eps = 1e-8f;
+    int hit = orc_fmin(p0.x, p1.x) <= orc_fmax(q0.x, q1.x) && orc_fmin(q0.x, q1.x) <= orc_fmax(p0.x, p1.x) &&
+              orc_fmin(p0.y, p1.y) <= orc_fmax(q0.y, q1.y) && orc_fmin(q0.y, q1.y) <= orc_fmax(p0.y, p1.y);
+    if (!hit) return 0;
+    float s1 = orc_cross3(q0, p1, p0), s2 = orc_cross3(p1, q1, p0);
+    float s3 = orc_cross3(p0, q1, q0), s4 = orc_cross3(q1, p1, q0);
+    if (!(s1 * s2 > 0 && s3 * s4 > 0)) return 0;
+    float s5 = orc_cross3(q1, p1, p0);
+    if (fabsf(s5 - s1) > eps) {
+        ans->x = (s5 * q0.x - s1 * q1.x) / (s5 - s1);
+        ans->y = (s5 * q0.y - s1 * q1.y) / (s5 - s1);
+    } else {
+        float a0 = p0.y - p1.y, b0 = p1.x - p0.x, c0 = p0.x * p1.y - p1.x * p0.y;
+        float a1 = q0.y - q1.y, b1 = q1.x - q0.x, c1 = q0.x * q1.y - q1.x * q0.y;
+        float D = a0 * b1 - a1 * b0;
+        ans->x = (b0 * c1 - b1 * c0) / D;
+        ans->y = (a1 * c0 - a0 * c1) / D;
+    }
+    return 1;
+}
+
+static void orc_corners(const float *box, orc_pt *out /*5*/) { /* iou3d_nms_kernel.cu:112-158 */
+    float hx = box[3] / 2, hy = box[4] / 2;
+    float x1 = box[0] - hx, y1 = box[1] - hy, x2 = box[0] + hx, y2 = box[1] + hy;
+    float c = cosf(box[6]), s = sinf(box[6]);
+    float px[4] = {x1, x2, x2, x1}, py[4] = {y1, y1, y2, y2};
+    for (int k = 0; k < 4; ++k) {
+        out[k].x = (px[k] - box[0]) * c + (py[k] - box[1]) * (-s) + box[0];
+        out[k].y = (px[k] - box[0]) * s + (py[k] - box[1]) * c + box[1];
+    }
+    out[4] = out[0];
+}
+
+static float orc_overlap1(const float *a, const float *b) { /* box_overlap, iou3d_nms_kernel.cu:108-216 */
+    orc_pt ca[5], cb[5], pts[16], ctr = {0.f, 0.f};
+    int cnt = 0;
+    orc_corners(a, ca);
+    orc_corners(b, cb);
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            orc_pt t;
+            if (cnt < 16 && orc_seg_x(ca[i + 1], ca[i], cb[j + 1], cb[j], &t)) {
+                pts[cnt++] = t;
+                ctr.x = ctr.x + t.x;
+                ctr.y = ctr.y + t.y;
+            }
+        }
+    for (int k = 0; k < 4; ++k) {
+        if (cnt < 16 && orc_in_box(a, cb[k])) { ctr.x = ctr.x + cb[k].x; ctr.y = ctr.y + cb[k].y; pts[cnt++] = cb[k]; }
+        if (cnt < 16 && orc_in_box(b, ca[k])) { ctr.x = ctr.x + ca[k].x; ctr.y = ctr.y + ca[k].y; pts[cnt++] = ca[k]; }
+    }
+    if (cnt == 0) return 0.f; /* the reference divides 0/0 here and then sums nothing: area 0 */
+    ctr.x /= cnt;
+    ctr.y /= cnt;
+    for (int j = 0; j < cnt - 1; ++j)
+        for (int i = 0; i < cnt - j - 1; ++i)
+            if (atan2f(pts[i].y - ctr.y, pts[i].x - ctr.x) > atan2f(pts[i + 1].y - ctr.y, pts[i + 1].x - ctr.x)) {
+                orc_pt t = pts[i]; pts[i] = pts[i + 1]; pts[i + 1] = t;
+            }
+    float area = 0.f;
+    for (int k = 0; k < cnt - 1; ++k) {
+        float ax = pts[k].x - pts[0].x, ay = pts[k].y - pts[0].y;
+        float bx = pts[k + 1].x - pts[0].x, by = pts[k + 1].y - pts[0].y;
+        area += ax * by - ay * bx;
+    }
+    return fabsf(area) / 2.0f;
+}
+
+static float orc_iou_bev1(const float *a, const float *b) { /* iou3d_nms_kernel.cu:218-225 */
+    float sa = a[3] * a[4], sb = b[3] * b[4], so = orc_overlap1(a, b);
+    return so / fmaxf(sa + sb - so, 1e-8f);
+}
+
+static float orc_iou_normal1(const float *a, const float *b) { /* iou3d_nms_kernel.cu:321-333 */
+    float left = fmaxf(a[0] - a[3] / 2, b[0] - b[3] / 2), right = fminf(a[0] + a[3] / 2, b[0] + b[3] / 2);
+    float top = fmaxf(a[1] - a[4] / 2, b[1] - b[4] / 2), bottom = fminf(a[1] + a[4] / 2, b[1] + b[4] / 2);
+    float w = fmaxf(right - left, 0.f), h = fmaxf(bottom - top, 0.f);
+    float inter = w * h, sa = a[3] * a[4], sb = b[3] * b[4];
+    return inter / fmaxf(sa + sb - inter, 1e-8f);
+}
+
+/* mode 0: BEV overlap, 1: BEV IoU, 2: 3-D IoU (iou3d_nms_utils.py:48-81, one fp32 rounding per torch op) */
+ORC_API void orc_boxes_matrix(int na, const float *A, int nb, const float *B, float *out, int mode) {
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int i = 0; i < na; ++i)
+        for (int j = 0; j < nb; ++j) {
+            const float *a = A + (size_t)i * 7, *b = B + (size_t)j * 7;
+            float r;
+            if (mode == 0) r = orc_overlap1(a, b);
+            else if (mode == 1) r = orc_iou_bev1(a, b);
+            else {
+                float ov = orc_overlap1(a, b);
+                float amax = a[2] + a[5] / 2, amin = a[2] - a[5] / 2, bmax = b[2] + b[5] / 2, bmin = b[2] - b[5] / 2;
+                float oh = fmaxf(fminf(amax, bmax) - fmaxf(amin, bmin), 0.f);
+                float o3 = ov * oh;
+                float va = a[3] * a[4] * a[5], vb = b[3] * b[4] * b[5];
+                r = o3 / fmaxf(va + vb - o3, 1e-6f);
+            }
+            out[(size_t)i * nb + j] = r;
+        }
+}
+
+/* nms_gpu / nms_normal_gpu (iou3d_nms.cpp:90-188): boxes sorted by descending score; a box survives unless an
+ * earlier SURVIVOR overlaps it by more than thresh.  Returns the number kept; keep[] = their positions. */
+ORC_API int orc_nms(int n, const float *boxes, float thresh, int normal, long long *keep) {
+    unsigned char *dead = (unsigned char *)calloc((size_t)(n > 0 ? n : 1), 1);
+    int nk = 0;
+    for (int i = 0; i < n; ++i) {
+        if (dead[i]) continue;
+        keep[nk++] = i;
+        const float *a = boxes + (size_t)i * 7;
+#pragma omp parallel for schedule(static)
+        for (int j = i + 1; j < n; ++j) {
+            if (dead[j]) continue;
+            const float *b = boxes + (size_t)j * 7;
+            float v = normal ? orc_iou_normal1(a, b) : orc_iou_bev1(a, b);
+            if (v > thresh) dead[j] = 1;
+        }
+    }
+    free(dead);
+    return nk;
+}
+
 ORC_API int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -337,3 +337,104 @@ def backbone_forward(backbone, points_bnc, stds=None, dtype=None):
     out["encoder_xyz"], out["encoder_features"] = enc_xyz, enc_feat
     out["centers_features"] = np.ascontiguousarray(np.transpose(enc_feat[-1], (0, 2, 1))).reshape(-1, enc_feat[-1].shape[1])
     return out
+
+
+# ---- iou3d_nms + IA-SSD head post-processing ---------------------------------------
+
+def boxes_matrix(boxes_a, boxes_b, mode):
+    """mode 'overlap' | 'iou_bev' | 'iou3d': reference boxes_overlap_bev_gpu / boxes_iou_bev_gpu
+    (iou3d_nms_kernel.cu:236-265) / boxes_iou3d_gpu (iou3d_nms_utils.py:48-81)."""
+    a, b = _f32(boxes_a), _f32(boxes_b)
+    out = np.zeros((a.shape[0], b.shape[0]), np.float32)
+    if out.size:
+        lib().orc_boxes_matrix(a.shape[0], _p(a), b.shape[0], _p(b), _p(out), {"overlap": 0, "iou_bev": 1, "iou3d": 2}[mode])
+    return out
+
+
+def nms_sorted(boxes, thresh, normal=False):
+    """Greedy NMS over boxes sorted by descending score (iou3d_nms.cpp:90-188): positions kept, ascending."""
+    bx = _f32(boxes)
+    keep = np.zeros(max(bx.shape[0], 1), np.int64)
+    lib().orc_nms.restype = C.c_int
+    n = lib().orc_nms(bx.shape[0], _p(bx), C.c_float(float(thresh)), int(bool(normal)), _p(keep))
+    return keep[:n].copy()
+
+
+def nms_gpu(boxes, scores, thresh, pre_maxsize=None, normal=False):
+    """reference iou3d_nms_utils.nms_gpu / nms_normal_gpu (iou3d_nms_utils.py:84-116); ties by ascending index."""
+    s = _f32(scores)
+    order = np.lexsort((np.arange(s.shape[0]), -s.astype(np.float64)))
+    if pre_maxsize is not None:
+        order = order[:pre_maxsize]
+    keep = nms_sorted(_f32(boxes)[order], thresh, normal)
+    return order[keep]
+
+
+def decode_bin_ori(box_encodings, points, pred_classes, mean_size, bin_size=12):
+    """PointResidual_BinOri_Coder.decode_torch (box_coder_utils.py:279-319), each torch op rounded to fp32 once.
+    pred_classes in 1..num_class; mean_size (num_class, 3) or None."""
+    enc, pts = _f32(box_encodings), _f32(points)
+    f = np.float32
+    if mean_size is not None:
+        anchor = _f32(mean_size)[np.asarray(pred_classes) - 1]
+        dxa, dya, dza = anchor[:, 0], anchor[:, 1], anchor[:, 2]
+        diag = np.sqrt((dxa * dxa).astype(f) + (dya * dya).astype(f), dtype=f)
+        xg = (enc[:, 0] * diag).astype(f) + pts[:, 0]
+        yg = (enc[:, 1] * diag).astype(f) + pts[:, 1]
+        zg = (enc[:, 2] * dza).astype(f) + pts[:, 2]
+        dxg = np.exp(enc[:, 3], dtype=f) * dxa
+        dyg = np.exp(enc[:, 4], dtype=f) * dya
+        dzg = np.exp(enc[:, 5], dtype=f) * dza
+    else:
+        xg, yg, zg = enc[:, 0] + pts[:, 0], enc[:, 1] + pts[:, 1], enc[:, 2] + pts[:, 2]
+        dxg, dyg, dzg = (np.exp(enc[:, k], dtype=f) for k in (3, 4, 5))
+    bin_inter = 2 * np.pi / bin_size
+    bins = enc[:, 6:6 + bin_size]
+    bin_id = bins.argmax(axis=1)
+    res = enc[np.arange(enc.shape[0]), 6 + bin_size + bin_id]
+    rg = (bin_id.astype(f) * f(bin_inter)).astype(f) - f(np.pi)
+    rg = (rg + f(bin_inter / 2)).astype(f)
+    rg = (rg + (res * f(bin_inter / 2)).astype(f)).astype(f)
+    return np.stack([xg, yg, zg, dxg, dyg, dzg, rg], axis=1).astype(f)
+
+
+def fc_stack(seq, x, dtype=None):
+    """point_head_template.make_fc_layers stack (Linear/BN1d/ReLU ... Linear+bias) on CPU in `dtype`."""
+    import torch
+
+    dtype = dtype or torch.float64
+    with torch.no_grad():
+        return seq.to(dtype)(_t(_f32(x)).to(dtype)).float().numpy()
+
+
+def head_forward(head, centers_features, centers, dtype=None):
+    """IASSD_Head.forward in eval mode (IASSD_head.py:788-840): cls / box stacks + generate_predicted_boxes
+    (point_head_template.py:193-207).  `head` is any object with cls_center_layers, box_center_layers (nn.Sequential),
+    mean_size (num_class,3 array or None), bin_size.  centers (R,4) [bs,x,y,z]."""
+    cls = fc_stack(head.cls_center_layers, centers_features, dtype)
+    reg = fc_stack(head.box_center_layers, centers_features, dtype)
+    pred_classes = cls.argmax(axis=1) + 1
+    boxes = decode_bin_ori(reg, _f32(centers)[:, 1:4], pred_classes, head.mean_size, head.bin_size)
+    return cls, reg, boxes
+
+
+def post_processing(cls_logits, box_preds, batch_size, score_thresh, nms_thresh, pre_max, post_max, normal=False):
+    """Detector3DTemplate.post_processing, class-agnostic branch (detector3d_template.py:207-290) +
+    class_agnostic_nms (model_nms_utils.py:6-27), equal number of centres per scene.  Returns a list of dicts
+    with pred_boxes / pred_scores / pred_labels / index (centre index within the scene)."""
+    cls, boxes = _f32(cls_logits), _f32(box_preds)
+    m = cls.shape[0] // batch_size
+    out = []
+    for b in range(batch_size):
+        c, bx = cls[b * m:(b + 1) * m], boxes[b * m:(b + 1) * m]
+        sc = _sigmoid32(c.max(axis=1))
+        lab = c.argmax(axis=1) + 1
+        ok = np.nonzero(sc >= np.float32(score_thresh))[0]
+        sel = np.zeros(0, np.int64)
+        if ok.size:
+            s_ok = sc[ok]
+            order = np.lexsort((np.arange(ok.size), -s_ok.astype(np.float64)))[:min(pre_max, ok.size)]
+            keep = nms_sorted(bx[ok][order], nms_thresh, normal)
+            sel = ok[order[keep[:post_max]]]
+        out.append({"pred_boxes": bx[sel], "pred_scores": sc[sel], "pred_labels": lab[sel].astype(np.int64), "index": sel})
+    return out

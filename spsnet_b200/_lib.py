@@ -47,9 +47,17 @@ SIGNATURES = {
     "spsk_sa_mma_forward": [_p, _p],
     "spsk_sa_mma_set_profile": [_p],
     "spsk_pw_mma_forward": [_p, _p],
+    "spsk_boxes_overlap_bev": [_i, _p, _i, _p, _p, _p],
+    "spsk_boxes_iou_bev": [_i, _p, _i, _p, _p, _p],
+    "spsk_boxes_iou3d": [_i, _p, _i, _p, _p, _p],
+    "spsk_nms_workspace_bytes": [_i, _i],
+    "spsk_nms": [_i, _i, _p, _p, _f, _i, _p, _p, _p, C.c_longlong, _p],
+    "spsk_detect_workspace_bytes": [_i, _i],
+    "spsk_detect_postprocess": [_p, _p],
 }
 _RESTYPE = {"spsk_last_error": C.c_char_p, "spsk_launch_count": C.c_ulonglong,
-            "spsk_ball_query_grid_workspace_bytes": C.c_longlong}
+            "spsk_ball_query_grid_workspace_bytes": C.c_longlong, "spsk_nms_workspace_bytes": C.c_longlong,
+            "spsk_detect_workspace_bytes": C.c_longlong}
 
 
 class GroupDesc(C.Structure):
@@ -87,6 +95,23 @@ class PwDesc(C.Structure):
         ("out_cm", _p), ("m", _i), ("c_total", _i), ("co_off", _i),
         ("out16", _p), ("ld16", _i), ("n16", _i), ("o16lo", _i),
         ("out_pm", _p), ("ldpm", _i),
+    ]
+
+
+class DetectDesc(C.Structure):
+    """struct spsk_detect_desc (include/spsk.h)."""
+
+    _fields_ = [
+        ("batch", _i), ("m", _i), ("num_class", _i), ("bin_size", _i),
+        ("cls", _p), ("ld_cls", _i),
+        ("reg", _p), ("ld_reg", _i),
+        ("centers", _p), ("ld_centers", _i),
+        ("mean_size", _p),
+        ("score_thresh", _f), ("nms_thresh", _f),
+        ("nms_normal", _i), ("pre_max", _i), ("post_max", _i),
+        ("box_preds", _p), ("scores", _p), ("labels", _p),
+        ("out_boxes", _p), ("out_scores", _p), ("out_labels", _p), ("out_index", _p), ("out_count", _p),
+        ("workspace", _p), ("workspace_bytes", C.c_longlong),
     ]
 
 

@@ -178,7 +178,13 @@ class IASSD_Backbone(nn.Module):
         batch_dict["centers"] = torch.cat((ctr_batch_idx[:, None].float(), centers.contiguous().view(-1, 3)), dim=1)
         batch_dict["centers_origin"] = torch.cat((ctr_batch_idx[:, None].float(), centers_origin.contiguous().view(-1, 3)), dim=1)
         last = encoder_features[-1]
-        batch_dict["centers_features"] = last.permute(0, 2, 1).contiguous().view(-1, last.shape[1])
+        cf = last.permute(0, 2, 1).contiguous().view(-1, last.shape[1])
+        hit = getattr(last, "_spsk_twin", None)
+        if hit is not None and hit[1] == last._version and hit[2] > 0:
+            # the producing layer's point-major fp16 rows [values | residuals] ARE the rows of centers_features:
+            # hand them to the head (dense_head.IASSD_Head) so it does not convert again
+            cf._spsk_rows16 = (hit[0].view(cf.shape[0], -1), cf._version, hit[2])
+        batch_dict["centers_features"] = cf
         batch_dict["ctr_batch_idx"] = ctr_batch_idx
         batch_dict["encoder_xyz"] = encoder_xyz
         batch_dict["encoder_coords"] = encoder_coords

@@ -79,3 +79,29 @@ def make_stds(seed: int, b: int, n: int) -> np.ndarray:
     """8 * exp(N(0, 0.5)): the stability generator sums 8 exp(0.5*logvar) terms
     (reference stability_generate/model.py:577)."""
     return (8.0 * np.exp(0.5 * np.random.default_rng(seed).standard_normal((b, n)))).astype(np.float32)
+
+
+def make_boxes(seed: int, n: int, n_objects: int | None = None, extent: float = 35.0) -> np.ndarray:
+    """Detection-shaped boxes (n, 7) [x, y, z, dx, dy, dz, heading] for the IoU / NMS tests and benches: centres
+    cluster around `n_objects` object locations (a detector proposes many near-duplicate boxes per object), sizes are
+    jittered KITTI mean sizes (car / pedestrian / cyclist, reference IA-SSD.yaml:79-83), headings arbitrary, plus a few
+    exact duplicates and a few axis-aligned boxes (degenerate clipping cases).  Deterministic in (seed, n)."""
+    rng = np.random.default_rng(9000 + seed)
+    if n == 0:
+        return np.zeros((0, 7), np.float32)
+    n_objects = n_objects or max(1, n // 8)
+    means = np.array([[3.9, 1.6, 1.56], [0.8, 0.6, 1.73], [1.76, 0.6, 1.73]], np.float32)
+    obj_xy = rng.uniform(-extent, extent, (n_objects, 2))
+    obj_cls = rng.integers(0, 3, n_objects)
+    obj_ang = rng.uniform(-np.pi, np.pi, n_objects)
+    which = rng.integers(0, n_objects, n)
+    boxes = np.zeros((n, 7), np.float64)
+    boxes[:, :2] = obj_xy[which] + rng.normal(0.0, 0.6, (n, 2))
+    boxes[:, 2] = rng.uniform(-1.5, 0.0, n)
+    boxes[:, 3:6] = means[obj_cls[which]] * rng.uniform(0.8, 1.25, (n, 3))
+    boxes[:, 6] = obj_ang[which] + rng.normal(0.0, 0.25, n) + np.pi * rng.integers(0, 2, n)
+    k = max(1, n // 16)
+    boxes[rng.integers(0, n, k)] = boxes[rng.integers(0, n, k)]       # exact duplicates
+    boxes[rng.integers(0, n, k), 6] = 0.0                            # axis-aligned
+    boxes[rng.integers(0, n, k), 6] = np.float32(np.pi / 2)
+    return boxes.astype(np.float32)

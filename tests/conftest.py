@@ -65,3 +65,34 @@ def ref_ops():
 
     R.utils, R.modules = utils, modules
     return R
+
+
+@pytest.fixture(scope="session")
+def ref_det():
+    """The reference's own iou3d_nms extension, IASSD_Head, box coder and class_agnostic_nms (oracle/_ref, unmodified,
+    rebuilt by oracle/build_ref.sh), or None.  `SharedArray` -- an absent dependency of pcdet.utils.common_utils that
+    nothing on this path uses -- is satisfied with an empty module."""
+    ref_root = ROOT / "oracle" / "_ref"
+    if not (ref_root / "pcdet" / "ops" / "iou3d_nms" / "iou3d_nms_cuda.so").exists():
+        return None
+    import importlib
+    import types
+    import warnings
+
+    if str(ref_root) not in sys.path:
+        sys.path.insert(0, str(ref_root))
+    sys.modules.setdefault("SharedArray", types.ModuleType("SharedArray"))
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            R = types.SimpleNamespace(
+                cuda=importlib.import_module("pcdet.ops.iou3d_nms.iou3d_nms_cuda"),
+                utils=importlib.import_module("pcdet.ops.iou3d_nms.iou3d_nms_utils"),
+                nms_utils=importlib.import_module("pcdet.models.model_utils.model_nms_utils"),
+                head=importlib.import_module("pcdet.models.dense_heads.IASSD_head"),
+                coder=importlib.import_module("pcdet.utils.box_coder_utils"),
+            )
+    except Exception as e:  # pragma: no cover
+        print("reference detection modules not importable:", e)
+        return None
+    return R
