@@ -57,6 +57,9 @@ WORKLOADS = {
     "spsnet_e2e": dict(batch=16, npts=16384, ncols=5, kind="kitti", cfg="kitti_spsnet_cfg", bb="SPSNetIA",
                        text="SPSNet-IA end to end on the path: stability generator (SA layer with M = N = 16384 centres + logvar "
                             "head -> stds) feeding the PAGNet backbone with stability-score top-k, batch 16 x 16384 pts per GPU, eval"),
+    "kitti_det": dict(batch=16, npts=16384, ncols=5, kind="kitti", cfg="kitti_iassd_cfg", bb="IASSD_DET",
+                      text="IA-SSD KITTI detector, inference: the full SA stack + IASSD_Head (2 x 3-layer FC on 256 centres x 512 ch) + box "
+                           "decode + score filter + rotated-IoU NMS -> final boxes (SURVEY.md 8f rank 3), batch 16 x 16384 pts per GPU"),
     "waymo": dict(batch=8, npts=65536, ncols=6, kind="waymo", cfg="waymo_iassd_cfg", bb="IASSD_Backbone",
                   text="IA-SSD Waymo cfg full SA stack (D-FPS 65536->16384->4096, ctr-aware top-k ->2048->1024, vote, MSG ball "
                        "query + shared MLP), batch 8 x 65536 pts per GPU, eval"),
@@ -65,8 +68,10 @@ _WL = WORKLOADS["kitti"]
 
 
 def set_workload(name: str):
-    global BATCH, NPTS, NCOLS, WORKLOAD, KIND, _WL
+    global BATCH, NPTS, NCOLS, WORKLOAD, KIND, _WL, METRIC
     _WL = WORKLOADS[name]
+    if _WL["bb"] == "IASSD_DET":
+        METRIC = "IA-SSD detector (SA backbone + head + NMS) scenes/s (16k pts)"
     BATCH, NPTS, NCOLS, WORKLOAD, KIND = _WL["batch"], _WL["npts"], _WL["ncols"], _WL["text"], _WL["kind"]
 
 
@@ -132,7 +137,11 @@ def build_net(seed=0):
     from spsnet_b200 import backbone as bb
 
     torch.manual_seed(seed)
-    if _WL["bb"] == "SPSNetIA":
+    if _WL["bb"] == "IASSD_DET":
+        from spsnet_b200 import detector
+
+        net = detector.IASSD(num_class=3, input_channels=NCOLS - 1)
+    elif _WL["bb"] == "SPSNetIA":
         from spsnet_b200 import stability as st
 
         net = st.SPSNetIAFrontEnd(st.Generate_center(st.sf_unc_cfg()),
@@ -169,9 +178,28 @@ def cpu_baseline(net_cpu, sample_scenes: int):
     from spsnet_b200 import scenes
 
     pts = scenes.make_batch(0, sample_scenes, NPTS, KIND)
-    O.backbone_forward(net_cpu, pts[:1], dtype=torch.float32)  # warm (page in, build)
+    det = hasattr(net_cpu, "point_head")
+    backbone = net_cpu.backbone_3d if det else net_cpu
+
+    def run(p):
+        out = O.backbone_forward(backbone, p, dtype=torch.float32)
+        if det:  # head + decode + post-processing restatement (oracle.py: head_forward, post_processing)
+            import types
+
+            from spsnet_b200 import dense_head as dh
+
+            h = net_cpu.point_head
+            ns = types.SimpleNamespace(cls_center_layers=h.cls_center_layers, box_center_layers=h.box_center_layers,
+                                       mean_size=h.box_coder._mean_np, bin_size=h.box_coder.bin_size)
+            centers = np.concatenate([np.repeat(np.arange(p.shape[0]), out["centers"].shape[1])[:, None].astype(np.float32),
+                                      out["centers"].reshape(-1, 3)], axis=1)
+            cls, _, boxes = O.head_forward(ns, out["centers_features"], centers, dtype=torch.float32)
+            pp, nc = dh.KITTI_POST_PROCESSING, dh.KITTI_POST_PROCESSING["NMS_CONFIG"]
+            O.post_processing(cls, boxes, p.shape[0], pp["SCORE_THRESH"], nc["NMS_THRESH"], nc["NMS_PRE_MAXSIZE"], nc["NMS_POST_MAXSIZE"])
+
+    run(pts[:1])  # warm (page in, build)
     t0 = time.perf_counter()
-    O.backbone_forward(net_cpu, pts, dtype=torch.float32)
+    run(pts)
     dt = time.perf_counter() - t0
     cores = max(O.num_threads(), torch.get_num_threads())
     return {"value": sample_scenes / dt, "unit": UNIT, "cores": cores, "kind": "port",
@@ -210,6 +238,9 @@ def profile_kernels(net, dev_points, steps: int):
                 a = (int(g.rows), int(g.k), int(g.n))
             elif name.startswith("spsk_ball_query_msg"):
                 a = tuple(a[:5]) + ([int(a[5][i]) for i in range(int(a[3]))],)
+            elif name == "spsk_detect_postprocess":
+                g = a[0]._obj
+                a = (int(g.batch), int(g.m), int(g.post_max))
             records.append((name, a, e0, e1))
             return rc
         return inner
@@ -222,7 +253,7 @@ def profile_kernels(net, dev_points, steps: int):
             for i in range(steps):
                 d = {"batch_size": BATCH, "points": dev_points[i % len(dev_points)]}
                 d.update(extra_inputs("cuda") or {})
-                net(d)
+                net.forward_padded(d) if hasattr(net, "forward_padded") else net(d)
         torch.cuda.synchronize()
     finally:
         for n in names:
@@ -297,6 +328,12 @@ def _roof_entry(key, t, peaks, traffic):
         alg_bytes = b * (n * 12 + m * 12 + m * nsum * 4)
         e.update(bound="hbm", achieved=alg_bytes / avg_s / 1e9, peak=hbm, unit="GB/s",
                  note="algorithmic bytes = xyz + centres + index lists; the kernel is fp32-issue / latency bound, not HBM bound")
+    elif key.startswith("spsk_detect_postprocess"):
+        b, m, post = a
+        alg_bytes = b * m * (33 + 3 + 7 + 2) * 4 + b * post * (7 + 1 + 2 + 2) * 4   # logits + encodings + centres in, boxes/scores/labels out
+        e.update(bound="hbm", achieved=alg_bytes / avg_s / 1e9, peak=hbm, unit="GB/s",
+                 note="3 launches (decode + score sort, IoU bit mask, greedy pass); latency-bound: 256 boxes per scene, the greedy "
+                      "pass is sequential over 64-box blocks -- neither roofline applies")
     else:
         e.update(bound="hbm", achieved=None, peak=hbm, unit="GB/s")
     e["frac"] = (e["achieved"] / e["peak"]) if e.get("achieved") else None
@@ -399,7 +436,8 @@ class EagerRef:
     def submit_host(self, host_points):
         self.dev_in.copy_(host_points, non_blocking=True)
         self._fwd(self.dev_in)
-        if self.host_outs is None:
+        if self.host_outs is None or any(self.host_outs[k].shape != v.shape for k, v in self.last.items()):
+            # (the reference detector returns variable-length results: fresh pinned mirrors when the shapes change)
             self.host_outs = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in self.last.items()}
         for k, v in self.last.items():
             self.host_outs[k].copy_(v, non_blocking=True)
@@ -420,6 +458,62 @@ class EagerRef:
         return sum(v.numel() * v.element_size() for v in self.last.values())
 
 
+class RefDetector(torch.nn.Module):
+    """The reference's own detector pieces, unmodified, wired the way Detector3DTemplate does: IASSD_Backbone ->
+    IASSD_Head (pcdet/models/dense_heads/IASSD_head.py) -> post_processing (detector3d_template.py:207-290, the
+    class-agnostic branch, restated here around the reference's class_agnostic_nms / nms_gpu because the template class
+    itself imports the whole of pcdet)."""
+
+    def __init__(self, backbone, head, post_cfg, nms_utils):
+        super().__init__()
+        self.backbone_3d, self.point_head = backbone, head
+        self.post_cfg, self.nms_utils = post_cfg, nms_utils
+
+    def forward(self, batch_dict):
+        batch_dict = self.point_head(self.backbone_3d(batch_dict))
+        cfg = self.post_cfg
+        boxes_out, scores_out, labels_out = [], [], []
+        for index in range(batch_dict["batch_size"]):
+            batch_mask = batch_dict["batch_index"] == index
+            box_preds = batch_dict["batch_box_preds"][batch_mask]
+            cls_preds = torch.sigmoid(batch_dict["batch_cls_preds"][batch_mask])
+            cls_preds, label_preds = torch.max(cls_preds, dim=-1)
+            label_preds = label_preds + 1
+            selected, selected_scores = self.nms_utils.class_agnostic_nms(
+                box_scores=cls_preds, box_preds=box_preds, nms_config=cfg.NMS_CONFIG, score_thresh=cfg.SCORE_THRESH)
+            boxes_out.append(box_preds[selected])
+            scores_out.append(selected_scores)
+            labels_out.append(label_preds[selected])
+        counts = torch.tensor([b.shape[0] for b in boxes_out], dtype=torch.int32)
+        return {"det_boxes": torch.cat(boxes_out), "det_scores": torch.cat(scores_out), "det_labels": torch.cat(labels_out),
+                "det_count": counts}
+
+
+def load_reference_detector(state_dict):
+    import importlib
+    import types
+    import warnings
+
+    from spsnet_b200 import backbone as bb
+    from spsnet_b200 import dense_head as dh
+
+    backbone = load_reference_backbone({k[len("backbone_3d."):]: v for k, v in state_dict.items() if k.startswith("backbone_3d.")})
+    sys.modules.setdefault("SharedArray", types.ModuleType("SharedArray"))  # absent dependency of pcdet.utils.common_utils, unused here
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        hm = importlib.import_module("pcdet.models.dense_heads.IASSD_head")
+        nu = importlib.import_module("pcdet.models.model_utils.model_nms_utils")
+    import copy
+
+    hcfg = copy.deepcopy(dh.KITTI_IASSD_HEAD)
+    hcfg["LOSS_CONFIG"] = {"LOSS_CLS": "WeightedCrossEntropy", "LOSS_REG": "WeightedSmoothL1Loss", "LOSS_INS": "WeightedCrossEntropy",
+                           "CORNER_LOSS_REGULARIZATION": False, "CENTERNESS_REGULARIZATION": False, "IOU3D_REGULARIZATION": False,
+                           "LOSS_WEIGHTS": {"code_weights": [1.0] * 6}}
+    head = hm.IASSD_Head(3, 512, bb.Cfg(hcfg))
+    head.load_state_dict({k[len("point_head."):]: v for k, v in state_dict.items() if k.startswith("point_head.")}, strict=False)
+    return RefDetector(backbone, head.eval(), bb.Cfg(dh.KITTI_POST_PROCESSING), nu).eval()
+
+
 def load_reference_backbone(state_dict):
     ref_root = ROOT / "oracle" / "_ref"
     so = ref_root / "pcdet" / "ops" / "pointnet2" / "pointnet2_batch" / "pointnet2_batch_cuda.so"
@@ -434,8 +528,8 @@ def load_reference_backbone(state_dict):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         mod = importlib.import_module("pcdet.models.backbones_3d.IASSD_backbone")
-    if _WL["bb"] != "IASSD_Backbone":
-        raise RuntimeError("the reference arm runs IASSD_Backbone workloads (kitti, waymo)")
+    if _WL["bb"] not in ("IASSD_Backbone", "IASSD_DET"):
+        raise RuntimeError("the reference arm runs IASSD_Backbone workloads (kitti, waymo, kitti_det)")
     net = mod.IASSD_Backbone(getattr(bb, _WL["cfg"])(), num_class=3, input_channels=NCOLS - 1)
     net.load_state_dict(state_dict)
     return net.eval()
@@ -483,13 +577,14 @@ def main():
 
     if args.impl == "reference":
         try:
-            ref = load_reference_backbone(state).cuda()
+            ref = (load_reference_detector(state) if _WL["bb"] == "IASSD_DET" else load_reference_backbone(state)).cuda()
         except Exception as e:  # fall back to the CPU port of the oracle
             if rank == 0:
                 sys.stderr.write(f"[bench] reference CUDA module unavailable ({e}); using the CPU oracle port\n")
             return run_reference_cpu(args, rank, world)
         torch.backends.cudnn.allow_tf32 = True  # the reference's stock setting
-        pipe = EagerRef(ref)
+        pipe = EagerRef(ref, outputs=("det_boxes", "det_scores", "det_labels", "det_count") if _WL["bb"] == "IASSD_DET"
+                        else ("centers_features", "centers"))
         pipe.submit_device(dev_pool[0])
         pipe.sync()
         sampler = ClockSampler(local)
@@ -520,7 +615,9 @@ def main():
     from spsnet_b200.runtime import BackbonePipeline
 
     net = net.cuda()
-    pipe = BackbonePipeline(net, BATCH, NPTS, NCOLS, depth=args.depth, use_graph=not args.no_graph, extra_inputs=extra_inputs("cuda"))
+    outputs = ("det_boxes", "det_scores", "det_labels", "det_count") if _WL["bb"] == "IASSD_DET" else ("centers_features", "centers")
+    pipe = BackbonePipeline(net, BATCH, NPTS, NCOLS, depth=args.depth, use_graph=not args.no_graph, extra_inputs=extra_inputs("cuda"),
+                            outputs=outputs)
     pipe.prepare(dev_pool[0])
     sampler = ClockSampler(local)
     sampler.start()

@@ -33,7 +33,7 @@ from . import pointnet2_utils as pu
 from ._lib import DetectDesc, check, lib
 from .backbone import Cfg
 
-__all__ = ["PointResidual_BinOri_Coder", "IASSD_Head", "Detections", "class_agnostic_nms", "post_processing",
+__all__ = ["PointResidual_BinOri_Coder", "IASSD_Head", "MLT_SSD_Head", "detections_padded", "Detections", "class_agnostic_nms", "post_processing",
            "kitti_iassd_head_cfg", "KITTI_POST_PROCESSING"]
 
 
@@ -388,6 +388,11 @@ class IASSD_Head(nn.Module):
         _, pred = cls.max(dim=-1)
         boxes = self.box_coder.decode_torch(reg, xyz, pred + 1)
         return boxes, None, None, None
+
+
+# SPSNet-IA's head (reference MLT_SSD_head.py:10-41,788-841): same layers, same eval-mode forward; it differs from
+# IASSD_Head only in training-time target assignment / losses, which are out of scope.
+MLT_SSD_Head = IASSD_Head
 
 
 def _nms_args(cfg):

@@ -52,7 +52,8 @@ class BackbonePipeline:
     def _forward(self, s: _Slot) -> Dict[str, torch.Tensor]:
         d = {"batch_size": self.B, "points": s.static_in}
         d.update(self.extra)
-        out = self.net(d)
+        # detectors expose a fixed-shape, sync-free forward (spsnet_b200.detector.IASSD.forward_padded)
+        out = self.net.forward_padded(d) if hasattr(self.net, "forward_padded") else self.net(d)
         return {k: out[k] for k in self.outputs}
 
     def prepare(self, example_points: torch.Tensor) -> None:
