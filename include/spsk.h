@@ -347,6 +347,37 @@ typedef struct spsk_detect_desc {
 SPSK_API long long spsk_detect_workspace_bytes(int batch, int m);
 SPSK_API int spsk_detect_postprocess(const spsk_detect_desc *d, spsk_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Section 4 -- SPSNet's surface-feature extractor (USE_SURFACE: True in SPSNet.yaml:48):
+ * one unit of FeatureExtraction = FCLayer transform + DenseEdgeConv with 3 FC layers, growth 12, max aggregation
+ * (pcdet/ops/pointnet2/pointnet2_batch/surface_feature.py:45-115,118-187) in two launches.  The neighbour lists come
+ * from spsk_ball_query (the reference calls QueryAndGroup(radius, knn, use_xyz=False), :54,79).
+ * Weight blocks are HOST structs passed by value into the launch (constant-bank operands); [k][o] = input-major.
+ * ---------------------------------------------------------------------------------------------- */
+#define SPSK_EDGE_CH 24      /* conv_channels */
+#define SPSK_EDGE_GROW 12    /* conv_growth_rate */
+#define SPSK_EDGE_MAX_CIN 64
+typedef struct spsk_edge_point_weights {
+    int cin, relu;                                   /* transform FC: cin -> 24, optional ReLU (units 1..3) */
+    float wt[SPSK_EDGE_MAX_CIN * SPSK_EDGE_CH];       /* wt[k*24 + o] = W_trans[o][k] */
+    float bt[SPSK_EDGE_CH];
+    float m[SPSK_EDGE_CH * 4 * SPSK_EDGE_GROW];       /* m[k*48 + o]: rows of [P | Q | R2 | R3] (see csrc/edge_conv.cu) */
+    float c[4 * SPSK_EDGE_GROW];                      /* [b1 | 0 | b2 | b3] */
+} spsk_edge_point_weights;
+typedef struct spsk_edge_aggr_weights {
+    float w2a[SPSK_EDGE_GROW * SPSK_EDGE_GROW];       /* [i*12 + o]: middle layer, columns that multiply l1 */
+    float w3a[SPSK_EDGE_GROW * SPSK_EDGE_GROW];       /* last layer, columns that multiply l2 */
+    float w3b[SPSK_EDGE_GROW * SPSK_EDGE_GROW];       /* last layer, columns that multiply l1 */
+} spsk_edge_aggr_weights;
+/* Per point: t = act(W_trans x + b) (rows, 24) and u = M t + c (rows, 48) = [P | Q | R2 | R3].  x (rows, ldx) f32. */
+SPSK_API int spsk_edge_conv_point(const spsk_edge_point_weights *w, int rows, const float *x, int ldx, float *t,
+                                  float *u, spsk_stream_t stream);
+/* Per point i of scene s: out[i] = [max_j l3 | max_j l2 | max_j l1 | t_i] (60 floats, row stride ldo) over the k
+ * neighbours j = idx[s, i, :] (indices within the scene), l1 = relu(P_i + Q_j), l2 = relu(W2a l1 + R2_i),
+ * l3 = W3a l2 + W3b l1 + R3_i.  idx (b, n, k) int32; t (b*n, 24); u (b*n, 48). */
+SPSK_API int spsk_edge_conv_aggregate(const spsk_edge_aggr_weights *w, int b, int n, int k, const int *idx,
+                                      const float *t, const float *u, float *out, int ldo, spsk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -438,3 +438,61 @@ def post_processing(cls_logits, box_preds, batch_size, score_thresh, nms_thresh,
             sel = ok[order[keep[:post_max]]]
         out.append({"pred_boxes": bx[sel], "pred_scores": sc[sel], "pred_labels": lab[sel].astype(np.int64), "index": sel})
     return out
+
+
+# ---- SPSNet surface-feature extractor ------------------------------------------------
+
+def as_ball_query_coords(pos):
+    """What the reference ball-query kernel reads when DenseEdgeConv hands it a (B, N, d) FEATURE tensor as xyz
+    (surface_feature.py:79 with pos = x in dynamic-graph mode, :170-173): 3 floats per point from the flat buffer
+    (ball_query_gpu.cu:18-20), i.e. the first B*N*3 floats viewed as (B, N, 3)."""
+    pos = _f32(pos)
+    B, N = pos.shape[:2]
+    return np.ascontiguousarray(pos.reshape(-1)[:B * N * 3].reshape(B, N, 3))
+
+
+def dense_edge_conv(conv, x_t, idx):
+    """DenseEdgeConv.forward (surface_feature.py:73-115), literally (grouped tensors, concatenations) in x_t's dtype.
+    x_t: torch (B, N, d); idx: (B, N, K) integer array of neighbour indices."""
+    import torch
+
+    B, N, d = x_t.shape
+    ii = torch.from_numpy(np.asarray(idx).astype(np.int64))
+    knn_feat = torch.stack([x_t[b][ii[b]] for b in range(B)])            # (B, N, K, d)
+    x_tiled = x_t.unsqueeze(-2).expand_as(knn_feat)
+    edge = knn_feat - x_tiled if conv.relative_feat_only else torch.cat([x_tiled, knn_feat, knn_feat - x_tiled], dim=3)
+    y = torch.cat([conv.layer_first(edge), x_tiled], dim=-1)
+    for layer in conv.layers:
+        y = torch.cat([layer(y), y], dim=-1)
+    y = torch.cat([conv.layer_last(y), y], dim=-1)
+    assert conv.aggr.oper == "max"
+    return y.max(dim=-2)[0]
+
+
+def surface_feature_extraction(fe, x, dtype=None, forced_idx=None, forced_t=None):
+    """FeatureExtraction.forward (surface_feature.py:118-187) on CPU.  `fe` is a module with the reference's layout
+    (transforms[i], convs[i]); pass a deep copy, it is cast to `dtype`.  forced_idx[i]: use these neighbour lists
+    (teacher-forcing); forced_t[i]: use these fp32 coordinates for the ball query of unit i.
+    Returns (out (B, N, 60) fp32, [idx_i], [t_i fp32])."""
+    import torch
+
+    dtype = dtype or torch.float64
+    fe = fe.to(dtype)
+    cur = _t(_f32(x)).to(dtype)
+    pos0 = _f32(x)
+    idxs, ts = [], []
+    with torch.no_grad():
+        for i in range(len(fe.convs)):
+            conv = fe.convs[i]
+            t = fe.transforms[i](cur)
+            t32 = t.float().numpy()
+            if forced_idx is not None:
+                idx = np.asarray(forced_idx[i])
+            else:
+                pos = (forced_t[i] if forced_t is not None else t32) if fe.dynamic_graph else pos0
+                coords = as_ball_query_coords(pos)
+                idx = ball_query(conv.group.radius, conv.knn, coords, coords)
+            idxs.append(idx)
+            ts.append(t32)
+            cur = dense_edge_conv(conv, t, idx)
+    return cur.float().numpy(), idxs, ts

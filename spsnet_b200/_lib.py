@@ -54,6 +54,8 @@ SIGNATURES = {
     "spsk_nms": [_i, _i, _p, _p, _f, _i, _p, _p, _p, C.c_longlong, _p],
     "spsk_detect_workspace_bytes": [_i, _i],
     "spsk_detect_postprocess": [_p, _p],
+    "spsk_edge_conv_point": [_p, _i, _p, _i, _p, _p, _p],
+    "spsk_edge_conv_aggregate": [_p, _i, _i, _i, _p, _p, _p, _p, _i, _p],
 }
 _RESTYPE = {"spsk_last_error": C.c_char_p, "spsk_launch_count": C.c_ulonglong,
             "spsk_ball_query_grid_workspace_bytes": C.c_longlong, "spsk_nms_workspace_bytes": C.c_longlong,
@@ -113,6 +115,18 @@ class DetectDesc(C.Structure):
         ("out_boxes", _p), ("out_scores", _p), ("out_labels", _p), ("out_index", _p), ("out_count", _p),
         ("workspace", _p), ("workspace_bytes", C.c_longlong),
     ]
+
+
+class EdgePointWeights(C.Structure):
+    """struct spsk_edge_point_weights (include/spsk.h)."""
+
+    _fields_ = [("cin", _i), ("relu", _i), ("wt", _f * (64 * 24)), ("bt", _f * 24), ("m", _f * (24 * 48)), ("c", _f * 48)]
+
+
+class EdgeAggrWeights(C.Structure):
+    """struct spsk_edge_aggr_weights (include/spsk.h)."""
+
+    _fields_ = [("w2a", _f * 144), ("w3a", _f * 144), ("w3b", _f * 144)]
 
 
 def declared_symbols(header: Path | None = None) -> list[str]:

@@ -15,7 +15,7 @@ from typing import Any
 import torch
 import torch.nn as nn
 
-from . import pointnet2_modules
+from . import pointnet2_modules, pointnet2_utils
 
 
 class Cfg(dict):
@@ -71,6 +71,15 @@ def kitti_spsnet_cfg() -> Cfg:
     return Cfg({"SA_CONFIG": c})
 
 
+def kitti_spsnet_surface_cfg() -> Cfg:
+    """SPSNet-IA exactly as shipped (reference tools/cfgs/kitti_models/SPSNet.yaml:38-71): stability-aware top-k,
+    USE_SURFACE: True (60 surface channels into the vote layer) and the 124-wide first MLP of SA layer 1."""
+    c = copy.deepcopy(kitti_spsnet_cfg()["SA_CONFIG"])
+    c["USE_SURFACE"] = True
+    c["MLPS"][1] = [[124, 64, 128], [124, 96, 128]]
+    return Cfg({"SA_CONFIG": c})
+
+
 def waymo_iassd_cfg() -> Cfg:
     """reference tools/cfgs/waymo_models/IA-SSD.yaml:45-65: all point counts x4."""
     c = copy.deepcopy(KITTI_IASSD_SA_CONFIG)
@@ -98,6 +107,12 @@ class IASSD_Backbone(nn.Module):
         self.max_translate_range = sa.get("MAX_TRANSLATE_RANGE", None)
 
         self.SA_modules = nn.ModuleList()
+        # SPSNet's surface feature (reference PAGNet_backbone.py:29-31; USE_SURFACE: True in SPSNet.yaml:48)
+        self._use_surface = bool(self._pass_stds and sa.get("USE_SURFACE", False))
+        if self._use_surface:
+            from . import surface_feature
+
+            self.SF_extract = surface_feature.FeatureExtraction()
         channel_in = input_channels - 3
         channel_out_list = [channel_in]
         channel_out = channel_in
@@ -123,6 +138,8 @@ class IASSD_Backbone(nn.Module):
                 self.SA_modules.append(pointnet2_modules.Vote_layer(
                     mlp_list=sa.MLPS[k], pre_channel=channel_out_list[self.layer_inputs[k]],
                     max_translate_range=self.max_translate_range))
+            if self._use_surface and k == 3:
+                channel_out += 60  # the vote layer also sees the 60 surface channels (PAGNet_backbone.py:91-92)
             channel_out_list.append(channel_out)
         self.num_point_features = channel_out
 
@@ -150,17 +167,25 @@ class IASSD_Backbone(nn.Module):
         encoder_coords = [torch.cat([bidx2d.unsqueeze(-1), xyz], dim=-1)]
         li_cls_pred = None
         centers = centers_origin = ctr_offsets = None
+        surface = None  # (B, n_i, 60) point-major surface features of the points kept so far
         for i, module in enumerate(self.SA_modules):
             xyz_input = encoder_xyz[self.layer_inputs[i]]
             feature_input = encoder_features[self.layer_inputs[i]]
             if self.layer_types[i] == "SA_Layer":
                 ctr_xyz = encoder_xyz[self.ctr_idx_list[i]] if self.ctr_idx_list[i] != -1 else None
                 kw = {"stds": stds} if self._pass_stds else {}
-                li_xyz, li_features, li_cls_pred, _, stds_out = module(xyz_input, feature_input, li_cls_pred, ctr_xyz=ctr_xyz, **kw)
+                li_xyz, li_features, li_cls_pred, sampled_idx, stds_out = module(xyz_input, feature_input, li_cls_pred, ctr_xyz=ctr_xyz, **kw)
                 if self._pass_stds:
                     stds = stds_out
+                if self._use_surface and i <= 4:
+                    # reference PAGNet_backbone.py:153-157: extract once on the full cloud, then follow the samplers
+                    # (kept point-major here: one row gather per layer instead of permute + gather_operation)
+                    if i == 0:
+                        surface = self.SF_extract(xyz)
+                    surface = pointnet2_utils.gather_rows(surface.contiguous(), sampled_idx.int().contiguous())
             else:  # Vote_Layer
-                li_xyz, li_features, xyz_select, ctr_offsets = module(xyz_input, feature_input)
+                kw = {"center_surface_futures": surface.permute(0, 2, 1).contiguous()} if surface is not None else {}
+                li_xyz, li_features, xyz_select, ctr_offsets = module(xyz_input, feature_input, **kw)
                 centers, centers_origin = li_xyz, xyz_select
                 encoder_coords.append(torch.cat([bidx2d[:, :centers_origin.shape[1], None].float(),
                                                  centers_origin.view(batch_size, -1, 3)], dim=-1))

@@ -20,6 +20,7 @@ constexpr int BG_MAXC = 11264;        // max cells per scene (44 KB of counters)
 constexpr int BG_GMAX = 106;          // max cells per axis (106 * 106 <= BG_MAXC)
 constexpr int BG_WARPS = 8;
 constexpr int BG_MAX_N = 65536;
+constexpr int BG_PREFIX = 1024;      // dense scenes: points scanned in index order before the grid is consulted
 
 struct GridParams {   // per scene, written by the build kernel
     float minx, miny, inv_c;
@@ -42,7 +43,9 @@ bq_grid_build_kernel(int n, float rmax, const float *__restrict__ xyz, GridParam
     __shared__ int cnt[BG_MAXC];
     __shared__ float red[4][32];
     __shared__ int wsum[32];
+    __shared__ unsigned long long dense_acc;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) dense_acc = 0ull;
     const float *pts = xyz + (size_t)b * n * 3;
     float x0 = 3.0e38f, x1 = -3.0e38f, y0 = 3.0e38f, y1 = -3.0e38f;
     for (int i = tid; i < n; i += 1024) {
@@ -81,7 +84,16 @@ bq_grid_build_kernel(int n, float rmax, const float *__restrict__ xyz, GridParam
     const int per = (ncell + 1023) / 1024;
     const int beg = tid * per, end = min(beg + per, ncell);
     int local = 0;
-    for (int i = beg; i < end; ++i) local += cnt[i];
+    unsigned long long sq = 0ull;   // sum of squared cell populations: n * (mean own-cell population seen by a point)
+    for (int i = beg; i < end; ++i) { local += cnt[i]; sq += (unsigned long long)cnt[i] * (unsigned long long)cnt[i]; }
+    {
+        // Dense scenes (SPSNet's DenseEdgeConv queries 24-wide FEATURES, most of them clustered inside one radius):
+        // a point's 3 x 3 neighbourhood holds thousands of candidates, while the reference's index-order scan stops after
+        // a few hundred points.  Flag the scene so the query starts with an index-order prefix scan (see below).
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, o);
+        if (lane == 0) atomicAdd(&dense_acc, sq);
+    }
     int incl = local;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -108,7 +120,11 @@ bq_grid_build_kernel(int n, float rmax, const float *__restrict__ xyz, GridParam
         cnt[i] = run;
         run += c0;
     }
-    if (tid == 0) cs[ncell] = n;
+    if (tid == 0) {
+        cs[ncell] = n;
+        // expected candidates per query ~ 9 x mean own-cell population; prefix scan pays off above ~2 x BG_PREFIX
+        params[b].pad0 = (9ull * dense_acc > 2ull * BG_PREFIX * (unsigned long long)n) ? 1 : 0;
+    }
     __syncthreads();
     // scatter (order inside a cell is irrelevant: the query orders hits through its bitmap)
     float4 *out = sorted + (size_t)b * n;
@@ -129,8 +145,8 @@ struct BgScales {
 template <int NS>
 __global__ void __launch_bounds__(BG_WARPS * 32)
 bq_grid_query_kernel(int n, int m, int words, BgScales sc, const float *__restrict__ new_xyz,
-                     const GridParams *__restrict__ params, const int *__restrict__ cell_start,
-                     const float4 *__restrict__ sorted) {
+                     const float *__restrict__ xyz, const GridParams *__restrict__ params,
+                     const int *__restrict__ cell_start, const float4 *__restrict__ sorted) {
     extern __shared__ uint32_t bitmaps[];   // [BG_WARPS][NS][words]
     const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5;
@@ -143,9 +159,38 @@ bq_grid_query_kernel(int n, int m, int words, BgScales sc, const float *__restri
     const GridParams gp = params[b];
     const int *cs = cell_start + (size_t)b * (BG_MAXC + 1);
     const float4 *pts = sorted + (size_t)b * n;
+    const float *raw = xyz + (size_t)b * n * 3;
+    const int tn = gp.pad0 ? min(BG_PREFIX, n) : 0;   // dense scene: index-order prefix scan over the first tn points
     for (int p = blockIdx.x * BG_WARPS + warp; p < m; p += gridDim.x * BG_WARPS) {
         const float *c = new_xyz + ((size_t)b * m + p) * 3;
         const float qx = __ldg(c), qy = __ldg(c + 1), qz = __ldg(c + 2);
+        int pcnt[NS], pfirst[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) { pcnt[s] = 0; pfirst[s] = -1; }
+        bool alldone = false;
+        // Prefix phase (dense scenes only): exactly the reference's scan order, 32 points per step, hits appended in
+        // index order through a ballot; stops as soon as every scale has its nsample indices (the reference's break).
+        for (int k0 = 0; k0 < tn && !alldone; k0 += 32) {
+            const int k = k0 + (int)lane;
+            float d2 = 3.0e38f;
+            if (k < tn) d2 = sqdist3(qx, qy, qz, __ldg(raw + (size_t)k * 3), __ldg(raw + (size_t)k * 3 + 1), __ldg(raw + (size_t)k * 3 + 2));
+            alldone = true;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const int ns = sc.nsample[s];
+                if (pcnt[s] < ns) {
+                    const bool hit = d2 < sc.r2[s];
+                    const uint32_t hm = __ballot_sync(0xFFFFFFFFu, hit);
+                    if (hm) {
+                        if (pfirst[s] < 0) pfirst[s] = k0 + __ffs(hm) - 1;
+                        const int pos = pcnt[s] + __popc(hm & ((1u << lane) - 1u));
+                        if (hit && pos < ns) sc.idx[s][((size_t)b * m + p) * ns + pos] = k;
+                        pcnt[s] += __popc(hm);
+                    }
+                }
+                alldone = alldone && pcnt[s] >= ns;
+            }
+        }
         // rows (32 words = 1024 point ids) that received a hit, per scale: 64 rows cover n <= 65536
         uint32_t tlo[NS], thi[NS];
 #pragma unroll
@@ -153,7 +198,7 @@ bq_grid_query_kernel(int n, int m, int words, BgScales sc, const float *__restri
         // the centre may lie outside the scene box (vote centres): unclamped cell coordinate, clamped ranges
         const int ccx = (int)floorf((qx - gp.minx) * gp.inv_c), ccy = (int)floorf((qy - gp.miny) * gp.inv_c);
         const int xlo = max(ccx - 1, 0), xhi = min(ccx + 1, gp.gx - 1);
-        if (xlo <= xhi) {
+        if (xlo <= xhi && !alldone) {
             for (int cy = max(ccy - 1, 0); cy <= min(ccy + 1, gp.gy - 1); ++cy) {
                 const int beg = __ldg(cs + cy * gp.gx + xlo), end = __ldg(cs + cy * gp.gx + xhi + 1);
                 for (int k0 = beg; k0 < end; k0 += 32) {
@@ -168,7 +213,8 @@ bq_grid_query_kernel(int n, int m, int words, BgScales sc, const float *__restri
                     const uint32_t row = oi >> 10;
 #pragma unroll
                     for (int s = 0; s < NS; ++s) {
-                        const bool hit = d2 < sc.r2[s];
+                        // (points below tn were already handled, in order, by the prefix phase)
+                        const bool hit = d2 < sc.r2[s] && (int)oi >= tn && pcnt[s] < sc.nsample[s];
                         if (hit) atomicOr(&bm[s * words + (oi >> 5)], 1u << (oi & 31u));
                         tlo[s] |= (hit && row < 32u) ? (1u << row) : 0u;
                         thi[s] |= (hit && row >= 32u) ? (1u << (row - 32u)) : 0u;
@@ -189,8 +235,8 @@ bq_grid_query_kernel(int n, int m, int words, BgScales sc, const float *__restri
             const int ns = sc.nsample[s];
             int *out = sc.idx[s] + ((size_t)b * m + p) * ns;
             uint32_t *w = bm + s * words;
-            int base = 0;       // hits written so far (warp-uniform)
-            int first = -1;     // smallest hit index (warp-uniform once found)
+            int base = pcnt[s];      // hits written so far (warp-uniform); the prefix phase may have written some
+            int first = pfirst[s];   // smallest hit index (warp-uniform once found)
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 uint32_t rows = half ? thi[s] : tlo[s];
@@ -282,7 +328,7 @@ extern "C" int spsk_ball_query_msg_grid(int b, int n, int m, int nscales, const 
             cudaError_t e = cudaFuncSetAttribute(bq_grid_query_kernel<NSV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(bq_grid_query_kernel)");              \
         }                                                                                                            \
-        bq_grid_query_kernel<NSV><<<grid, BG_WARPS * 32, smem, st>>>(n, m, words, sc, new_xyz, params, cell_start, sorted); \
+        bq_grid_query_kernel<NSV><<<grid, BG_WARPS * 32, smem, st>>>(n, m, words, sc, new_xyz, xyz, params, cell_start, sorted); \
     } while (0)
     switch (nscales) {
         case 1: SPSK_BG_LAUNCH(1); break;

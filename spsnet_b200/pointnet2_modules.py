@@ -145,6 +145,18 @@ def _get_twin(features: torch.Tensor, mult: int = 8):
     return pu.make_twin(features.contiguous(), _ceil(Cc, mult)), 0
 
 
+def _split_rows(features: torch.Tensor):
+    """Fresh point-major fp16 rows [values | residuals] of a channel-major (B, C, N) fp32 tensor: ((B, N, 2*c16), c16)."""
+    B, Cc, N = features.shape
+    c16 = _ceil(Cc, 16)
+    pm = features.permute(0, 2, 1)
+    rows = torch.zeros((B, N, 2 * c16), dtype=torch.float16, device=features.device)
+    hi = pm.half()
+    rows[:, :, :Cc] = hi
+    rows[:, :, c16:c16 + Cc] = (pm - hi.float()).half()
+    return rows, c16
+
+
 def _set_twin(features: torch.Tensor, twin: torch.Tensor, lo_off: int = 0) -> None:
     features._spsk_twin = (twin.view(features.shape[0], features.shape[2], -1), features._version, lo_off)
 
@@ -626,6 +638,8 @@ class Vote_layer(nn.Module):
             B_, _, M_ = features_select.shape
             caches = self.__dict__.setdefault("_pw_cache", {"mlp_modules": _PwCache(), "ctr_reg": _PwCache()})
             tw, lo = _get_twin(features_select.contiguous(), 16)
+            if lo == 0 and hasattr(self, "center_surface_futures"):
+                tw, lo = _split_rows(features_select)  # concatenated input: no producer twin, keep fp32-grade arithmetic
             layers = caches["mlp_modules"].get(self._folded("mlp_modules", self.mlp_modules), lo > 0) + \
                 caches["ctr_reg"].get(self._folded("ctr_reg", nn.Sequential(self.ctr_reg)), lo > 0)
             ctr_offsets = _pw_stack(layers, tw.view(B_ * M_, -1), lo, B_, M_, "pm")  # (B, npoint, 3 [+ extra])

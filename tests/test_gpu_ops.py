@@ -286,3 +286,27 @@ def test_ball_query_grid_equals_bruteforce(oracle, b, n, m, radii, ns):
     a = pu.ball_query_msg([0.5, 1.0], [16, 32], dev(lat), dev(ctr), grid=True)
     for r, s, o in zip([0.5, 1.0], [16, 32], a):
         np.testing.assert_array_equal(o.cpu().numpy(), oracle.ball_query(r, s, lat, ctr))
+
+
+@pytest.mark.parametrize("n,m,sigma", [(4096, 4096, 0.3), (16384, 2048, 0.5), (3000, 700, 0.05), (8192, 1024, 2.0)])
+def test_ball_query_grid_dense_scenes(oracle, n, m, sigma):
+    """Dense scenes (thousands of candidates per 3 x 3 neighbourhood, e.g. the feature-space queries of SPSNet's
+    DenseEdgeConv) take the index-order prefix scan inside the grid kernel: same lists as the brute-force kernel and the
+    oracle, also for centres that stay sparse (prefix finds too few, the grid finishes) and for mixed scenes in one batch."""
+    from spsnet_b200 import pointnet2_utils as pu
+
+    rng = np.random.default_rng(n + m)
+    dense = rng.normal(0.0, sigma, (1, n, 3)).astype(np.float32)
+    dense[0, n // 2:, :] = np.maximum(dense[0, n // 2:, :], 0.0)       # ReLU-like: many exact zeros / duplicates
+    mixed = dense.copy()
+    mixed[0, : n // 8] = rng.uniform(-60, 60, (n // 8, 3)).astype(np.float32)   # sparse outliers, also inside the prefix
+    sparse = _xyz(1, n, seed=9, kind="kitti")
+    xyz = np.concatenate([dense, mixed, sparse], axis=0)
+    sel = rng.choice(n, m, replace=False)
+    new_xyz = np.ascontiguousarray(xyz[:, sel])
+    radii, ns = [0.8, 0.2], [16, 32]
+    g = pu.ball_query_msg(radii, ns, dev(xyz), dev(new_xyz), grid=True)
+    bf = pu.ball_query_msg(radii, ns, dev(xyz), dev(new_xyz), grid=False)
+    for r, s, a, c in zip(radii, ns, g, bf):
+        np.testing.assert_array_equal(a.cpu().numpy(), c.cpu().numpy())
+        np.testing.assert_array_equal(a.cpu().numpy(), oracle.ball_query(r, s, xyz, new_xyz))
