@@ -54,6 +54,10 @@ WORKLOADS = {
     "spsnet": dict(batch=16, npts=16384, ncols=5, kind="kitti", cfg="kitti_spsnet_cfg", bb="PAGNet_Backbone",
                    text="SPSNet-IA KITTI cfg: stability-score (sss_aware) top-k sampling in SA layers 2,3 with per-point stds, "
                         "otherwise the IA-SSD SA stack, batch 16 x 16384 pts per GPU, eval"),
+    "spsnet_sf": dict(batch=16, npts=16384, ncols=5, kind="kitti", cfg="kitti_spsnet_surface_cfg", bb="PAGNet_Backbone",
+                      text="SPSNet-IA backbone exactly as shipped (SPSNet.yaml): stability-score top-k with per-point stds, USE_SURFACE "
+                           "(4 DenseEdgeConv units on all 16384 points -> 60 surface channels into the vote layer), 124-wide layer-1 "
+                           "MLPs, batch 16 x 16384 pts per GPU, eval"),
     "spsnet_e2e": dict(batch=16, npts=16384, ncols=5, kind="kitti", cfg="kitti_spsnet_cfg", bb="SPSNetIA",
                        text="SPSNet-IA end to end on the path: stability generator (SA layer with M = N = 16384 centres + logvar "
                             "head -> stds) feeding the PAGNet backbone with stability-score top-k, batch 16 x 16384 pts per GPU, eval"),
@@ -328,6 +332,16 @@ def _roof_entry(key, t, peaks, traffic):
         alg_bytes = b * (n * 12 + m * 12 + m * nsum * 4)
         e.update(bound="hbm", achieved=alg_bytes / avg_s / 1e9, peak=hbm, unit="GB/s",
                  note="algorithmic bytes = xyz + centres + index lists; the kernel is fp32-issue / latency bound, not HBM bound")
+    elif key.startswith("spsk_edge_conv_point"):
+        rows_n, cin = int(a[1]), int(a[3])
+        e.update(bound="tensor", achieved=2.0 * rows_n * (cin * 24 + 24 * 48) / avg_s / 1e12, peak=74.4, unit="TFLOP/s",
+                 note="per-point transform FC + [P|Q|R2|R3] projections of a DenseEdgeConv unit, fp32 FFMA with constant-bank "
+                      "weights; peak = fp32 CUDA-core peak")
+    elif key.startswith("spsk_edge_conv_aggregate"):
+        b, n, k = int(a[1]), int(a[2]), int(a[3])
+        e.update(bound="tensor", achieved=2.0 * b * n * k * 432 / avg_s / 1e12, peak=74.4, unit="TFLOP/s",
+                 note="per-(point, neighbour) dense edge MLP + max over neighbours, fp32 FFMA (432 MACs per row; repeated padding "
+                      "indices are skipped, so this is an upper bound of the work done); peak = fp32 CUDA-core peak")
     elif key.startswith("spsk_detect_postprocess"):
         b, m, post = a
         alg_bytes = b * m * (33 + 3 + 7 + 2) * 4 + b * post * (7 + 1 + 2 + 2) * 4   # logits + encodings + centres in, boxes/scores/labels out
@@ -418,8 +432,9 @@ def timed_region(pipe, inputs, steps, warmup, host: bool, world: int):
 class EagerRef:
     """Adapter giving the reference backbone the same submit/sync surface (no graphs: its forward host-syncs)."""
 
-    def __init__(self, net, outputs=("centers_features", "centers")):
+    def __init__(self, net, outputs=("centers_features", "centers"), extra=None):
         self.net, self.outputs = net, outputs
+        self.extra = extra or {}
         self.stream = torch.cuda.current_stream()
         self.host_outs = None
         self.dev_in = torch.zeros((BATCH * NPTS, NCOLS), dtype=torch.float32, device="cuda")
@@ -427,7 +442,7 @@ class EagerRef:
 
     def _fwd(self, pts):
         with torch.no_grad():
-            out = self.net({"batch_size": BATCH, "points": pts})
+            out = self.net({"batch_size": BATCH, "points": pts, **self.extra})
         self.last = {k: out[k] for k in self.outputs}
 
     def submit_device(self, dev_points):
@@ -525,12 +540,13 @@ def load_reference_backbone(state_dict):
     sys.path.insert(0, str(ref_root))
     from spsnet_b200 import backbone as bb
 
+    if _WL["bb"] not in ("IASSD_Backbone", "IASSD_DET", "PAGNet_Backbone"):
+        raise RuntimeError("the reference arm runs the IASSD_Backbone / PAGNet_Backbone workloads (kitti, waymo, kitti_det, spsnet, spsnet_sf)")
+    cls_name = "PAGNet_Backbone" if _WL["bb"] == "PAGNet_Backbone" else "IASSD_Backbone"
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        mod = importlib.import_module("pcdet.models.backbones_3d.IASSD_backbone")
-    if _WL["bb"] not in ("IASSD_Backbone", "IASSD_DET"):
-        raise RuntimeError("the reference arm runs IASSD_Backbone workloads (kitti, waymo, kitti_det)")
-    net = mod.IASSD_Backbone(getattr(bb, _WL["cfg"])(), num_class=3, input_channels=NCOLS - 1)
+        mod = importlib.import_module("pcdet.models.backbones_3d." + cls_name.replace("_Backbone", "_backbone"))
+    net = getattr(mod, cls_name)(getattr(bb, _WL["cfg"])(), num_class=3, input_channels=NCOLS - 1)
     net.load_state_dict(state_dict)
     return net.eval()
 
@@ -584,7 +600,7 @@ def main():
             return run_reference_cpu(args, rank, world)
         torch.backends.cudnn.allow_tf32 = True  # the reference's stock setting
         pipe = EagerRef(ref, outputs=("det_boxes", "det_scores", "det_labels", "det_count") if _WL["bb"] == "IASSD_DET"
-                        else ("centers_features", "centers"))
+                        else ("centers_features", "centers"), extra=extra_inputs("cuda"))
         pipe.submit_device(dev_pool[0])
         pipe.sync()
         sampler = ClockSampler(local)

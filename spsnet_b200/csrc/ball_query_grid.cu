@@ -20,7 +20,7 @@ constexpr int BG_MAXC = 11264;        // max cells per scene (44 KB of counters)
 constexpr int BG_GMAX = 106;          // max cells per axis (106 * 106 <= BG_MAXC)
 constexpr int BG_WARPS = 8;
 constexpr int BG_MAX_N = 65536;
-constexpr int BG_PREFIX = 1024;      // dense scenes: points scanned in index order before the grid is consulted
+constexpr int BG_PREFIX_MIN = 1024;  // neighbourhoods with at least this many candidates start with an index-order prefix scan
 
 struct GridParams {   // per scene, written by the build kernel
     float minx, miny, inv_c;
@@ -43,9 +43,7 @@ bq_grid_build_kernel(int n, float rmax, const float *__restrict__ xyz, GridParam
     __shared__ int cnt[BG_MAXC];
     __shared__ float red[4][32];
     __shared__ int wsum[32];
-    __shared__ unsigned long long dense_acc;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) dense_acc = 0ull;
     const float *pts = xyz + (size_t)b * n * 3;
     float x0 = 3.0e38f, x1 = -3.0e38f, y0 = 3.0e38f, y1 = -3.0e38f;
     for (int i = tid; i < n; i += 1024) {
@@ -84,16 +82,7 @@ bq_grid_build_kernel(int n, float rmax, const float *__restrict__ xyz, GridParam
     const int per = (ncell + 1023) / 1024;
     const int beg = tid * per, end = min(beg + per, ncell);
     int local = 0;
-    unsigned long long sq = 0ull;   // sum of squared cell populations: n * (mean own-cell population seen by a point)
-    for (int i = beg; i < end; ++i) { local += cnt[i]; sq += (unsigned long long)cnt[i] * (unsigned long long)cnt[i]; }
-    {
-        // Dense scenes (SPSNet's DenseEdgeConv queries 24-wide FEATURES, most of them clustered inside one radius):
-        // a point's 3 x 3 neighbourhood holds thousands of candidates, while the reference's index-order scan stops after
-        // a few hundred points.  Flag the scene so the query starts with an index-order prefix scan (see below).
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, o);
-        if (lane == 0) atomicAdd(&dense_acc, sq);
-    }
+    for (int i = beg; i < end; ++i) local += cnt[i];
     int incl = local;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -120,11 +109,7 @@ bq_grid_build_kernel(int n, float rmax, const float *__restrict__ xyz, GridParam
         cnt[i] = run;
         run += c0;
     }
-    if (tid == 0) {
-        cs[ncell] = n;
-        // expected candidates per query ~ 9 x mean own-cell population; prefix scan pays off above ~2 x BG_PREFIX
-        params[b].pad0 = (9ull * dense_acc > 2ull * BG_PREFIX * (unsigned long long)n) ? 1 : 0;
-    }
+    if (tid == 0) cs[ncell] = n;
     __syncthreads();
     // scatter (order inside a cell is irrelevant: the query orders hits through its bitmap)
     float4 *out = sorted + (size_t)b * n;
@@ -160,7 +145,6 @@ bq_grid_query_kernel(int n, int m, int words, BgScales sc, const float *__restri
     const int *cs = cell_start + (size_t)b * (BG_MAXC + 1);
     const float4 *pts = sorted + (size_t)b * n;
     const float *raw = xyz + (size_t)b * n * 3;
-    const int tn = gp.pad0 ? min(BG_PREFIX, n) : 0;   // dense scene: index-order prefix scan over the first tn points
     for (int p = blockIdx.x * BG_WARPS + warp; p < m; p += gridDim.x * BG_WARPS) {
         const float *c = new_xyz + ((size_t)b * m + p) * 3;
         const float qx = __ldg(c), qy = __ldg(c + 1), qz = __ldg(c + 2);
@@ -168,8 +152,26 @@ bq_grid_query_kernel(int n, int m, int words, BgScales sc, const float *__restri
 #pragma unroll
         for (int s = 0; s < NS; ++s) { pcnt[s] = 0; pfirst[s] = -1; }
         bool alldone = false;
-        // Prefix phase (dense scenes only): exactly the reference's scan order, 32 points per step, hits appended in
-        // index order through a ballot; stops as soon as every scale has its nsample indices (the reference's break).
+        // the centre may lie outside the scene box (vote centres): unclamped cell coordinate, clamped ranges
+        const int ccx = (int)floorf((qx - gp.minx) * gp.inv_c), ccy = (int)floorf((qy - gp.miny) * gp.inv_c);
+        const int xlo = max(ccx - 1, 0), xhi = min(ccx + 1, gp.gx - 1);
+        const int ylo = max(ccy - 1, 0), yhi = min(ccy + 1, gp.gy - 1);
+        // Candidates the grid phase would have to test for this centre.  In a dense neighbourhood (SPSNet's DenseEdgeConv
+        // queries 24-wide FEATURES, thousands of them inside one radius) the reference's index-order scan stops after a few
+        // hundred points while the grid would test them all: scan the first `tn` points in index order first.  tn = the
+        // candidate count itself, so the detour costs at most as much again as the grid phase it may save (and nothing for
+        // the LiDAR-shaped neighbourhoods of the SA layers, which stay below BG_PREFIX_MIN).
+        int cand = 0;
+        if (xlo <= xhi && (int)lane <= yhi - ylo) {
+            const int cy = ylo + (int)lane;
+            cand = __ldg(cs + cy * gp.gx + xhi + 1) - __ldg(cs + cy * gp.gx + xlo);
+        }
+        cand += __shfl_xor_sync(0xFFFFFFFFu, cand, 1);
+        cand += __shfl_xor_sync(0xFFFFFFFFu, cand, 2);
+        cand = __shfl_sync(0xFFFFFFFFu, cand, 0);
+        const int tn = cand >= BG_PREFIX_MIN ? min(n, (cand + 31) & ~31) : 0;
+        // Prefix phase: exactly the reference's scan order, 32 points per step, hits appended in index order through a
+        // ballot; stops as soon as every scale has its nsample indices (the reference's break).
         for (int k0 = 0; k0 < tn && !alldone; k0 += 32) {
             const int k = k0 + (int)lane;
             float d2 = 3.0e38f;
@@ -195,11 +197,8 @@ bq_grid_query_kernel(int n, int m, int words, BgScales sc, const float *__restri
         uint32_t tlo[NS], thi[NS];
 #pragma unroll
         for (int s = 0; s < NS; ++s) { tlo[s] = 0u; thi[s] = 0u; }
-        // the centre may lie outside the scene box (vote centres): unclamped cell coordinate, clamped ranges
-        const int ccx = (int)floorf((qx - gp.minx) * gp.inv_c), ccy = (int)floorf((qy - gp.miny) * gp.inv_c);
-        const int xlo = max(ccx - 1, 0), xhi = min(ccx + 1, gp.gx - 1);
-        if (xlo <= xhi && !alldone) {
-            for (int cy = max(ccy - 1, 0); cy <= min(ccy + 1, gp.gy - 1); ++cy) {
+        if (xlo <= xhi && !alldone && tn < n) {
+            for (int cy = ylo; cy <= yhi; ++cy) {
                 const int beg = __ldg(cs + cy * gp.gx + xlo), end = __ldg(cs + cy * gp.gx + xhi + 1);
                 for (int k0 = beg; k0 < end; k0 += 32) {
                     const int k = k0 + (int)lane;
