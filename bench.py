@@ -58,6 +58,9 @@ WORKLOADS = {
                       text="SPSNet-IA backbone exactly as shipped (SPSNet.yaml): stability-score top-k with per-point stds, USE_SURFACE "
                            "(4 DenseEdgeConv units on all 16384 points -> 60 surface channels into the vote layer), 124-wide layer-1 "
                            "MLPs, batch 16 x 16384 pts per GPU, eval"),
+    "spsnet_full": dict(batch=16, npts=16384, ncols=5, kind="kitti", cfg="kitti_spsnet_surface_cfg", bb="SPSNET_DET",
+                        text="SPSNet-IA detector as shipped (SPSNet.yaml), inference: stability generator (-> stds) -> PAGNet_Backbone with "
+                             "stability-score top-k + USE_SURFACE -> MLT_SSD_Head -> decode + rotated-IoU NMS, batch 16 x 16384 pts per GPU"),
     "spsnet_e2e": dict(batch=16, npts=16384, ncols=5, kind="kitti", cfg="kitti_spsnet_cfg", bb="SPSNetIA",
                        text="SPSNet-IA end to end on the path: stability generator (SA layer with M = N = 16384 centres + logvar "
                             "head -> stds) feeding the PAGNet backbone with stability-score top-k, batch 16 x 16384 pts per GPU, eval"),
@@ -76,6 +79,8 @@ def set_workload(name: str):
     _WL = WORKLOADS[name]
     if _WL["bb"] == "IASSD_DET":
         METRIC = "IA-SSD detector (SA backbone + head + NMS) scenes/s (16k pts)"
+    if _WL["bb"] == "SPSNET_DET":
+        METRIC = "SPSNet-IA detector (stability generator + SA backbone + head + NMS) scenes/s (16k pts)"
     BATCH, NPTS, NCOLS, WORKLOAD, KIND = _WL["batch"], _WL["npts"], _WL["ncols"], _WL["text"], _WL["kind"]
 
 
@@ -145,6 +150,11 @@ def build_net(seed=0):
         from spsnet_b200 import detector
 
         net = detector.IASSD(num_class=3, input_channels=NCOLS - 1)
+    elif _WL["bb"] == "SPSNET_DET":
+        from spsnet_b200 import detector
+        from spsnet_b200 import stability as st
+
+        net = detector.SPSNetIA(num_class=3, input_channels=NCOLS - 1, generator=st.Generate_center(st.sf_unc_cfg()))
     elif _WL["bb"] == "SPSNetIA":
         from spsnet_b200 import stability as st
 
@@ -631,7 +641,7 @@ def main():
     from spsnet_b200.runtime import BackbonePipeline
 
     net = net.cuda()
-    outputs = ("det_boxes", "det_scores", "det_labels", "det_count") if _WL["bb"] == "IASSD_DET" else ("centers_features", "centers")
+    outputs = ("det_boxes", "det_scores", "det_labels", "det_count") if _WL["bb"] in ("IASSD_DET", "SPSNET_DET") else ("centers_features", "centers")
     pipe = BackbonePipeline(net, BATCH, NPTS, NCOLS, depth=args.depth, use_graph=not args.no_graph, extra_inputs=extra_inputs("cuda"),
                             outputs=outputs)
     pipe.prepare(dev_pool[0])

@@ -45,13 +45,35 @@ class IASSD(nn.Module):
         return dh.post_processing(batch_dict, self.model_cfg.POST_PROCESSING)
 
 
-class SPSNetIA(IASSD):
-    """SPSNet-IA detector (reference tools/cfgs/kitti_models/SPSNet.yaml:26-73: model NAME IASSD with PAGNet_Backbone
-    = stability-aware sampling, and MLT_SSD_Head, whose eval-mode forward is IASSD_Head's, MLT_SSD_head.py:788-841).
-    batch_dict needs the per-point `stds` of the stability generator (spsnet_b200.stability)."""
+class _StabilityEncoding(nn.Module):
+    """The role of the reference's `PAGNet_encoding` (pcdet/models/backbones_2d/map_to_bev/PAGNet_encoding.py:10-31): run
+    the frozen stability generator and leave per-point `stds` in batch_dict.  Its point-deletion block (:33-69) is an
+    ablation that needs ground-truth `fake_labels`; it is available separately as stability.delete_unstable_points."""
 
-    def __init__(self, model_cfg=None, num_class: int = 3, input_channels: int = 4):
+    def __init__(self, generator: nn.Module):
+        super().__init__()
+        self.generator = generator
+
+    def forward(self, batch_dict):
+        batch_dict = self.generator(batch_dict)
+        for k in ("encoder_xyz", "encoder_coords", "sa_ins_preds", "soc_feature"):
+            batch_dict.pop(k, None)
+        return batch_dict
+
+
+class SPSNetIA(IASSD):
+    """SPSNet-IA detector as shipped (reference tools/cfgs/kitti_models/SPSNet.yaml:24-121): model NAME IASSD with
+    MAP_TO_BEV = PAGNet_encoding (the stability generator -> per-point stds), BACKBONE_3D = PAGNet_Backbone (stability-aware
+    sampling, USE_SURFACE) and POINT_HEAD = MLT_SSD_Head (eval-mode forward identical to IASSD_Head,
+    MLT_SSD_head.py:788-841); modules run in the reference's topology order map_to_bev_module -> backbone_3d -> point_head
+    (detector3d_template.py:23-26).  generator=None: batch_dict must already hold `stds`."""
+
+    def __init__(self, model_cfg=None, num_class: int = 3, input_channels: int = 4, generator: nn.Module = None,
+                 surface: bool = True):
         if model_cfg is None:
-            model_cfg = {"BACKBONE_3D": bb.kitti_spsnet_cfg(), "POINT_HEAD": dh.kitti_iassd_head_cfg(),
-                         "POST_PROCESSING": dh.KITTI_POST_PROCESSING}
+            model_cfg = {"BACKBONE_3D": bb.kitti_spsnet_surface_cfg() if surface else bb.kitti_spsnet_cfg(),
+                         "POINT_HEAD": dh.kitti_iassd_head_cfg(), "POST_PROCESSING": dh.KITTI_POST_PROCESSING}
         super().__init__(model_cfg, num_class, input_channels, backbone_cls=bb.PAGNet_Backbone)
+        if generator is not None:
+            self.map_to_bev_module = _StabilityEncoding(generator)
+            self.module_list = [self.map_to_bev_module, self.backbone_3d, self.point_head]

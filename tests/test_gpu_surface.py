@@ -187,3 +187,39 @@ def test_pagnet_backbone_with_surface(oracle, ref_ops):
         assert_close(out["encoder_features"][1].cpu().numpy(), rout["encoder_features"][1].cpu().numpy(), 1e-3, "layer-0 features")
         same = (out["encoder_xyz"][4] == rout["encoder_xyz"][4]).all(dim=-1).float().mean().item()
         assert same > 0.8, f"only {same:.2f} of the layer-3 centres coincide with the reference"
+
+
+def test_spsnet_detector_as_shipped_end_to_end():
+    """SPSNet.yaml topology: stability generator -> PAGNet_Backbone (USE_SURFACE) -> MLT_SSD_Head -> NMS; the detector equals
+    its modules run one by one, the reference's checkpoint key prefixes are kept, and the padded (graph-capturable) result
+    matches the list-of-dicts result."""
+    from spsnet_b200 import backbone as bb
+    from spsnet_b200 import dense_head as dh
+    from spsnet_b200 import detector, scenes
+    from spsnet_b200 import stability as st
+
+    torch.manual_seed(1)
+    cfg = bb.kitti_spsnet_surface_cfg()
+    cfg["SA_CONFIG"]["NPOINT_LIST"] = [[1024], [256], [128], [64], [-1], [64]]
+    model_cfg = {"BACKBONE_3D": cfg, "POINT_HEAD": dh.kitti_iassd_head_cfg(), "POST_PROCESSING": dh.KITTI_POST_PROCESSING}
+    net = detector.SPSNetIA(model_cfg, generator=st.Generate_center(st.sf_unc_cfg()))
+    bb.randomize_bn_stats(net, seed=3)
+    net = net.cuda().eval()
+    keys = net.state_dict().keys()
+    assert any(k.startswith("map_to_bev_module.generator.") for k in keys)
+    assert any(k.startswith("backbone_3d.SF_extract.") for k in keys) and any(k.startswith("point_head.cls_center_layers.") for k in keys)
+    B, N = 2, 4096
+    pts = torch.from_numpy(scenes.to_points(scenes.make_batch(70, B, N))).cuda()
+    with torch.no_grad():
+        pred, _ = net({"batch_size": B, "points": pts})
+        bd = net.map_to_bev_module({"batch_size": B, "points": pts})
+        assert bd["stds"].shape == (B, N)
+        bd = net.point_head(net.backbone_3d(bd))
+        pred2, _ = dh.post_processing(bd, dh.KITTI_POST_PROCESSING)
+        padded = net.forward_padded({"batch_size": B, "points": pts})
+    assert len(pred) == B
+    for b in range(B):
+        assert torch.equal(pred[b]["pred_boxes"], pred2[b]["pred_boxes"]) and torch.equal(pred[b]["pred_scores"], pred2[b]["pred_scores"])
+        n = int(padded["det_count"][b])
+        assert n == pred[b]["pred_boxes"].shape[0] and torch.equal(padded["det_boxes"][b, :n], pred[b]["pred_boxes"])
+        assert torch.isfinite(pred[b]["pred_boxes"]).all()
