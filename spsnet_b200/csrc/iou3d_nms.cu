@@ -108,13 +108,15 @@ __device__ float overlap_bev(const BoxP &a, const BoxP &b) {
     float ptx[MAXP], pty[MAXP], pang[MAXP];
     int cnt = 0;
     float sx = 0.0f, sy = 0.0f;
-#pragma unroll
+    // rolled on purpose: one copy of the segment test instead of 16 keeps the kernel inside the instruction cache (ncu
+    // showed no-instruction stalls on the unrolled version); the corners are read from shared memory with dynamic indices
+#pragma unroll 1
     for (int i = 0; i < 4; ++i) {
-#pragma unroll
+        const float a1x = a.px[(i + 1) & 3], a1y = a.py[(i + 1) & 3], a0x = a.px[i], a0y = a.py[i];
+#pragma unroll 1
         for (int j = 0; j < 4; ++j) {
             float ox, oy;
-            if (seg_intersect(a.px[(i + 1) & 3], a.py[(i + 1) & 3], a.px[i], a.py[i], b.px[(j + 1) & 3],
-                              b.py[(j + 1) & 3], b.px[j], b.py[j], ox, oy)) {
+            if (seg_intersect(a1x, a1y, a0x, a0y, b.px[(j + 1) & 3], b.py[(j + 1) & 3], b.px[j], b.py[j], ox, oy)) {
                 if (cnt < MAXP) {
                     sx = sx + ox;
                     sy = sy + oy;
@@ -125,7 +127,7 @@ __device__ float overlap_bev(const BoxP &a, const BoxP &b) {
             }
         }
     }
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < 4; ++k) {
         if (in_box(a, b.px[k], b.py[k]) && cnt < MAXP) {
             sx = sx + b.px[k];
@@ -222,54 +224,109 @@ boxes_matrix_kernel(int num_a, const float *__restrict__ boxes_a, int num_b, con
 }
 
 // ---- NMS: suppression bit mask (upper triangle) -------------------------------------------------------------
-// One CTA = one 64 x 64 tile of (row box, column box) pairs of one scene; 256 threads: 4 lanes per row, lane q takes
-// columns q, q+4, ... (conflict-free shared reads of consecutive prepared boxes) and the 4 partial words are OR-ed with
-// two shuffles.  Bit j of mask[row][col_blk] = IoU(row, 64*col_blk + j) > thresh, only for columns after the row.
-constexpr int NT = 64;
+// One CTA = one 32 x 64 tile of (row box, column box) pairs of one scene; 256 threads: 8 lanes per row, lane q takes
+// columns q, q+8, ... (conflict-free shared reads of consecutive prepared boxes) and the 8 partial words are OR-ed with
+// three shuffles.  Bit j of mask[row][col_blk] = IoU(row, 64*col_blk + j) > thresh, only for columns after the row.
+constexpr int NT = 64;   // columns per tile = bits per mask word
+constexpr int NR = 32;   // rows per tile
 template <bool NORMAL>
 __global__ void __launch_bounds__(256)
 nms_mask_kernel(int n, const float *__restrict__ boxes, const int *__restrict__ counts, float thresh,
                 unsigned long long *__restrict__ mask) {
     const int cb = (n + NT - 1) / NT;
     const int row_blk = blockIdx.x / cb, col_blk = blockIdx.x % cb;
-    if (col_blk < row_blk) return;
+    const int row0 = row_blk * NR, col0 = col_blk * NT;
+    if (col0 + NT - 1 <= row0) return;   // every column of the tile precedes (or is) every row: never read
     const int scene = blockIdx.y;
     const int nb = counts ? min(counts[scene], n) : n;
-    if (row_blk * NT >= nb || col_blk * NT >= nb) return;
+    if (row0 >= nb || col0 >= nb) return;
     const float *bx = boxes + (size_t)scene * n * 7;
     unsigned long long *mk = mask + (size_t)scene * n * cb;
-    const int row_size = min(nb - row_blk * NT, NT), col_size = min(nb - col_blk * NT, NT);
+    const int row_size = min(nb - row0, NR), col_size = min(nb - col0, NT);
 
-    __shared__ float raw[NORMAL ? 2 * NT * 7 : 1];
-    __shared__ BoxP prep[NORMAL ? 1 : 2 * NT];
+    __shared__ float raw[NORMAL ? (NR + NT) * 7 : 1];
+    __shared__ BoxP prep[NORMAL ? 1 : NR + NT];
     if (NORMAL) {
-        for (int i = threadIdx.x; i < 2 * NT * 7; i += 256) {
-            const int half = i / (NT * 7), off = i % (NT * 7), bi = off / 7;
-            const int base = (half ? col_blk : row_blk) * NT, lim = half ? col_size : row_size;
-            raw[i] = bi < lim ? bx[(size_t)base * 7 + off] : 0.0f;
+        for (int i = threadIdx.x; i < (NR + NT) * 7; i += 256) {
+            const int bi = i / 7, c = i - bi * 7;
+            const bool is_col = bi >= NR;
+            const int local = is_col ? bi - NR : bi, lim = is_col ? col_size : row_size, base = is_col ? col0 : row0;
+            raw[i] = local < lim ? bx[(size_t)(base + local) * 7 + c] : 0.0f;
         }
-    } else if (threadIdx.x < 2 * NT) {
-        const int half = threadIdx.x / NT, t = threadIdx.x % NT;
-        const int base = (half ? col_blk : row_blk) * NT, lim = half ? col_size : row_size;
-        if (t < lim) box_prep(bx + (size_t)(base + t) * 7, prep[threadIdx.x]);
+    } else if (threadIdx.x < NR + NT) {
+        const bool is_col = threadIdx.x >= NR;
+        const int local = is_col ? threadIdx.x - NR : threadIdx.x, lim = is_col ? col_size : row_size, base = is_col ? col0 : row0;
+        if (local < lim) box_prep(bx + (size_t)(base + local) * 7, prep[threadIdx.x]);
     }
     __syncthreads();
-    const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
+    const int r = threadIdx.x >> 3, q = threadIdx.x & 7;
     unsigned long long t = 0ull;
     if (r < row_size) {
-        const int start = row_blk == col_blk ? r + 1 : 0;
+        const int gr = row0 + r;
         if (NORMAL) {
-            for (int c = q; c < col_size; c += 4)
-                if (c >= start && iou_normal_raw(raw + r * 7, raw + (NT + c) * 7) > thresh) t |= 1ull << c;
+            for (int c = q; c < col_size; c += 8)
+                if (col0 + c > gr && iou_normal_raw(raw + r * 7, raw + (NR + c) * 7) > thresh) t |= 1ull << c;
         } else {
-            const BoxP a = prep[r];
-            for (int c = q; c < col_size; c += 4)
-                if (c >= start && iou_bev_p(a, prep[NT + c]) > thresh) t |= 1ull << c;
+            const BoxP &a = prep[r];
+            for (int c = q; c < col_size; c += 8)
+                if (col0 + c > gr && iou_bev_p(a, prep[NR + c]) > thresh) t |= 1ull << c;
         }
     }
     t |= __shfl_xor_sync(0xffffffffu, t, 1);
     t |= __shfl_xor_sync(0xffffffffu, t, 2);
-    if (q == 0 && r < row_size) mk[(size_t)(row_blk * NT + r) * cb + col_blk] = t;
+    t |= __shfl_xor_sync(0xffffffffu, t, 4);
+    if (q == 0 && r < row_size) mk[(size_t)(row0 + r) * cb + col_blk] = t;
+}
+
+// Small scenes (n <= 1024; IA-SSD post-processing has 256 boxes per scene): the kernel above is bound by the LATENCY of its
+// longest thread (8 polygon clippings in sequence at low occupancy; ncu: 74 us for 16 x 256 boxes at 14 % warps active).
+// Here every thread owns exactly ONE pair: a tile is 4 rows x 64 columns, warp w handles row w/2, columns 32 (w%2) + lane,
+// and the mask word is assembled from two ballots.
+constexpr int FR = 4;
+template <bool NORMAL>
+__global__ void __launch_bounds__(256)
+nms_mask_fine_kernel(int n, const float *__restrict__ boxes, const int *__restrict__ counts, float thresh,
+                     unsigned long long *__restrict__ mask) {
+    const int cb = (n + NT - 1) / NT;
+    const int row_blk = blockIdx.x / cb, col_blk = blockIdx.x % cb;
+    const int row0 = row_blk * FR, col0 = col_blk * NT;
+    if (col0 + NT - 1 <= row0) return;
+    const int scene = blockIdx.y;
+    const int nb = counts ? min(counts[scene], n) : n;
+    if (row0 >= nb || col0 >= nb) return;
+    const float *bx = boxes + (size_t)scene * n * 7;
+    unsigned long long *mk = mask + (size_t)scene * n * cb;
+    const int row_size = min(nb - row0, FR), col_size = min(nb - col0, NT);
+    __shared__ float raw[NORMAL ? (FR + NT) * 7 : 1];
+    __shared__ BoxP prep[NORMAL ? 1 : FR + NT];
+    __shared__ uint32_t part[FR][2];
+    if (NORMAL) {
+        for (int i = threadIdx.x; i < (FR + NT) * 7; i += 256) {
+            const int bi = i / 7, c = i - bi * 7;
+            const bool is_col = bi >= FR;
+            const int local = is_col ? bi - FR : bi, lim = is_col ? col_size : row_size, base = is_col ? col0 : row0;
+            raw[i] = local < lim ? bx[(size_t)(base + local) * 7 + c] : 0.0f;
+        }
+    } else if (threadIdx.x < FR + NT) {
+        const bool is_col = threadIdx.x >= FR;
+        const int local = is_col ? threadIdx.x - FR : threadIdx.x, lim = is_col ? col_size : row_size, base = is_col ? col0 : row0;
+        if (local < lim) box_prep(bx + (size_t)(base + local) * 7, prep[threadIdx.x]);
+    }
+    __syncthreads();
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = w >> 1, c = (w & 1) * 32 + lane;
+    bool hit = false;
+    if (r < row_size && c < col_size && col0 + c > row0 + r) {
+        if (NORMAL)
+            hit = iou_normal_raw(raw + r * 7, raw + (FR + c) * 7) > thresh;
+        else
+            hit = iou_bev_p(prep[r], prep[FR + c]) > thresh;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) part[r][w & 1] = m;
+    __syncthreads();
+    if (threadIdx.x < row_size)
+        mk[(size_t)(row0 + threadIdx.x) * cb + col_blk] = (unsigned long long)part[threadIdx.x][0] | ((unsigned long long)part[threadIdx.x][1] << 32);
 }
 
 // ---- NMS: greedy pass on the device --------------------------------------------------------------------------
@@ -288,6 +345,86 @@ struct NmsEmit {
     long long *out_index;    // (batch, post_max) original row within the scene
     int *out_count;          // (batch)
 };
+
+// survivor `srt` (position in the sorted order) is the rank-th kept box of its scene
+__device__ __forceinline__ void emit_kept(const NmsEmit &em, long long *kp, int scene, int n, int srt, int rank) {
+    if (kp) kp[rank] = srt;
+    if (em.order && rank < em.post_max) {
+        const int orig = em.order[(size_t)scene * n + srt];
+        const size_t row = (size_t)scene * em.m + orig, o = (size_t)scene * em.post_max + rank;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) em.out_boxes[o * 7 + c] = em.box_preds[row * 7 + c];
+        em.out_scores[o] = em.scores[row];
+        em.out_labels[o] = em.labels[row];
+        em.out_index[o] = orig;
+    }
+}
+
+__device__ __forceinline__ void emit_tail(const NmsEmit &em, int *num_keep, int scene, int total, int nthreads) {
+    if (threadIdx.x == 0 && num_keep) num_keep[scene] = total;
+    if (em.order) {
+        const int cnt = min(total, em.post_max);
+        if (threadIdx.x == 0) em.out_count[scene] = cnt;
+        for (int i = cnt * 7 + threadIdx.x; i < em.post_max * 7; i += nthreads) em.out_boxes[(size_t)scene * em.post_max * 7 + i] = 0.0f;
+        for (int i = cnt + threadIdx.x; i < em.post_max; i += nthreads) {
+            const size_t o = (size_t)scene * em.post_max + i;
+            em.out_scores[o] = 0.0f;
+            em.out_labels[o] = 0;
+            em.out_index[o] = -1;
+        }
+    }
+}
+
+// Scenes of at most 512 boxes (IA-SSD: 256 centres): the whole upper-triangular mask fits in shared memory (<= 32 KB), one
+// coalesced load, then ONE WARP walks the rows in order with lane j owning "removed" word j: per row a shuffle to fetch
+// the owner's word, a bit test, and for survivors one shared-memory OR per lane.  No global latency inside the
+// sequential part (the block-wise kernel below pays ~1 us of L2 latency per 64 rows).
+constexpr int RS_MAXN = 512, RS_W = RS_MAXN / NT;
+__global__ void __launch_bounds__(256)
+nms_reduce_small_kernel(int n, const int *__restrict__ counts, const unsigned long long *__restrict__ mask,
+                        long long *__restrict__ keep, int *__restrict__ num_keep, NmsEmit em) {
+    __shared__ unsigned long long sm[RS_MAXN * RS_W];
+    __shared__ unsigned long long skb[RS_W];
+    __shared__ int spre[RS_W + 1];
+    const int cb = (n + NT - 1) / NT;
+    const int scene = blockIdx.x;
+    const int nb = counts ? min(counts[scene], n) : n;
+    const int cbb = (nb + NT - 1) / NT;
+    const unsigned long long *mk = mask + (size_t)scene * n * cb;
+    for (int i = threadIdx.x; i < nb * RS_W; i += 256) {
+        const int row = i / RS_W, j = i - row * RS_W;
+        sm[i] = (j >= (row >> 6) && j < cbb) ? mk[(size_t)row * cb + j] : 0ull;   // words below the diagonal are never written
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        unsigned long long remv = 0ull, kb = 0ull;
+        for (int t = 0; t < nb; ++t) {
+            const int blk = t >> 6, bit = t & 63;
+            const unsigned long long cur = __shfl_sync(0xffffffffu, remv, blk);
+            if (!((cur >> bit) & 1ull)) {
+                if (lane == blk) kb |= 1ull << bit;
+                if (lane < RS_W) remv |= sm[t * RS_W + lane];
+            }
+        }
+        if (lane < RS_W) skb[lane] = kb;
+        int c = lane < RS_W ? __popcll(kb) : 0, incl = c;
+#pragma unroll
+        for (int o = 1; o < RS_W; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane < RS_W) spre[lane + 1] = incl;
+        if (lane == 0) spre[0] = 0;
+    }
+    __syncthreads();
+    long long *kp = keep ? keep + (size_t)scene * n : nullptr;
+    for (int t = threadIdx.x; t < nb; t += 256) {
+        const unsigned long long kb = skb[t >> 6];
+        if ((kb >> (t & 63)) & 1ull) emit_kept(em, kp, scene, n, t, spre[t >> 6] + __popcll(kb & ((1ull << (t & 63)) - 1ull)));
+    }
+    emit_tail(em, num_keep, scene, spre[RS_W], 256);
+}
 
 constexpr int RT = 256;
 __global__ void __launch_bounds__(RT)
@@ -330,35 +467,12 @@ nms_reduce_kernel(int n, const int *__restrict__ counts, const unsigned long lon
             }
             remv[j] = acc;
         }
-        if (threadIdx.x < NT && ((kb >> threadIdx.x) & 1ull)) {
-            const int rank = total + __popcll(kb & ((1ull << threadIdx.x) - 1ull));
-            const int srt = blk * NT + threadIdx.x;
-            if (kp) kp[rank] = srt;
-            if (em.order && rank < em.post_max) {
-                const int orig = em.order[(size_t)scene * n + srt];
-                const size_t row = (size_t)scene * em.m + orig, o = (size_t)scene * em.post_max + rank;
-#pragma unroll
-                for (int c = 0; c < 7; ++c) em.out_boxes[o * 7 + c] = em.box_preds[row * 7 + c];
-                em.out_scores[o] = em.scores[row];
-                em.out_labels[o] = em.labels[row];
-                em.out_index[o] = orig;
-            }
-        }
+        if (threadIdx.x < NT && ((kb >> threadIdx.x) & 1ull))
+            emit_kept(em, kp, scene, n, blk * NT + threadIdx.x, total + __popcll(kb & ((1ull << threadIdx.x) - 1ull)));
         total += __popcll(kb);
         __syncthreads();
     }
-    if (threadIdx.x == 0 && num_keep) num_keep[scene] = total;
-    if (em.order) {
-        const int cnt = min(total, em.post_max);
-        if (threadIdx.x == 0) em.out_count[scene] = cnt;
-        for (int i = cnt * 7 + threadIdx.x; i < em.post_max * 7; i += RT) em.out_boxes[(size_t)scene * em.post_max * 7 + i] = 0.0f;
-        for (int i = cnt + threadIdx.x; i < em.post_max; i += RT) {
-            const size_t o = (size_t)scene * em.post_max + i;
-            em.out_scores[o] = 0.0f;
-            em.out_labels[o] = 0;
-            em.out_index[o] = -1;
-        }
-    }
+    emit_tail(em, num_keep, scene, total, RT);
 }
 
 static int nms_launch(int batch, int n, const float *boxes, const int *counts, float thresh, int normal,
@@ -368,15 +482,26 @@ static int nms_launch(int batch, int n, const float *boxes, const int *counts, f
     const long long need = (long long)batch * n * cb * 8;
     SPSK_REQUIRE(workspace && ws_bytes >= need, SPSK_ERR_WORKSPACE, "nms: workspace %lld < %lld bytes", ws_bytes, need);
     SPSK_REQUIRE(n <= SPSK_NMS_MAX_N, SPSK_ERR_UNSUPPORTED, "nms: n=%d > %d", n, SPSK_NMS_MAX_N);
-    SPSK_REQUIRE((long long)cb * cb <= 0x7fffffffLL && batch <= 65535, SPSK_ERR_UNSUPPORTED, "nms: grid too large");
+    SPSK_REQUIRE((long long)((n + NR - 1) / NR) * cb <= 0x7fffffffLL && batch <= 65535, SPSK_ERR_UNSUPPORTED, "nms: grid too large");
     unsigned long long *mask = static_cast<unsigned long long *>(workspace);
-    dim3 grid(cb * cb, batch);
-    if (normal)
-        nms_mask_kernel<true><<<grid, 256, 0, st>>>(n, boxes, counts, thresh, mask);
-    else
-        nms_mask_kernel<false><<<grid, 256, 0, st>>>(n, boxes, counts, thresh, mask);
+    if (n <= 1024) {   // latency-bound regime: one pair per thread
+        dim3 grid(((n + FR - 1) / FR) * cb, batch);
+        if (normal)
+            nms_mask_fine_kernel<true><<<grid, 256, 0, st>>>(n, boxes, counts, thresh, mask);
+        else
+            nms_mask_fine_kernel<false><<<grid, 256, 0, st>>>(n, boxes, counts, thresh, mask);
+    } else {
+        dim3 grid(((n + NR - 1) / NR) * cb, batch);
+        if (normal)
+            nms_mask_kernel<true><<<grid, 256, 0, st>>>(n, boxes, counts, thresh, mask);
+        else
+            nms_mask_kernel<false><<<grid, 256, 0, st>>>(n, boxes, counts, thresh, mask);
+    }
     SPSK_LAUNCH_CHECK("nms_mask_kernel");
-    nms_reduce_kernel<<<batch, RT, cb * 8, st>>>(n, counts, mask, keep, num_keep, em);
+    if (n <= RS_MAXN)
+        nms_reduce_small_kernel<<<batch, 256, 0, st>>>(n, counts, mask, keep, num_keep, em);
+    else
+        nms_reduce_kernel<<<batch, RT, cb * 8, st>>>(n, counts, mask, keep, num_keep, em);
     SPSK_LAUNCH_CHECK("nms_reduce_kernel");
     return SPSK_OK;
 }
