@@ -88,7 +88,7 @@ fps_kernel_1024(int n, int m, const float *__restrict__ src, float *__restrict__
     }
 
     int old = 0;
-    if (tid == 0) idx[0] = 0;
+    int keep = 0;   // picks are flushed 32 at a time by warp 0 (see fps_pruned_kernel); idx[0] = 0 lives in lane 0
 
     for (int j = 1; j < m; ++j) {
         float x1 = 0.f, y1 = 0.f, z1 = 0.f;
@@ -117,8 +117,12 @@ fps_kernel_1024(int n, int m, const float *__restrict__ src, float *__restrict__
         const uint32_t u = ordered_bits(__fadd_rn(best, 0.f));
         const uint32_t inv_rank = ~fps_rank(kb, s_mask, s_log2);
         old = (int)block_argmax(u, inv_rank, slots[j & 1], T / 32, s_mask, s_log2);
-        if (tid == 0) idx[j] = old;
+        if (tid < 32) {
+            if ((tid & 31) == (j & 31)) keep = old;
+            if ((j & 31) == 31) idx[j - 31 + tid] = keep;
+        }
     }
+    if (tid < 32 && (m & 31) != 0 && tid < (m & 31)) idx[(m & ~31) + tid] = keep;   // the last partial line
 
     if (temp) {
 #pragma unroll
@@ -300,7 +304,10 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
     __shared__ uint2 slots2[2][W];            // single CTA: one (value, ~rank) slot per warp
     __shared__ uint4 crec[CL ? 2 : 1][CL ? 8 * W : 1][2];   // cluster: [parity][cta * W + warp] = {value, ~rank, x, y | z, -, -, -}
     uint32_t bpos = 0u;   // lane p: sorted position of sub-bucket p's best point
-    if (crank == 0 && tid == 0) idx[0] = 0;
+    // The picks are written 32 at a time: lane (j & 31) of warp 0 keeps pick j in a register and the warp stores one
+    // coalesced 128-byte line every 32 iterations.  A store per iteration sits on the latency chain: the CTA barrier of the
+    // next iteration orders memory, so it waits for the store's acknowledgement from L2.
+    int keep = 0;   // idx[0] = 0 (reference :113-115) lives in lane 0 until the first flush
     int qpos = CL ? 0 : pos_of[0];   // first sample is point 0 (reference :113-115)
     float qx = __ldg(scene_base), qy = __ldg(scene_base + 1), qz = __ldg(scene_base + 2);
     if (CL) cluster_sync_all();      // every CTA of the cluster is resident before the first remote store
@@ -402,7 +409,10 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
             const uint32_t rank = ~r2;
             const int old = (int)((__brev(rank) & s_mask) | ((rank & ((1u << (32u - s_log2)) - 1u)) << s_log2));
             qpos = pos_of[old];
-            if (tid == 0) idx[j] = old;
+            if (warp == 0) {
+                if (lane == (j & 31)) keep = old;
+                if ((j & 31) == 31) idx[j - 31 + lane] = keep;
+            }
             if (pf) { const long long t1 = clock64(); pc[4] += t1 - t0; t0 = t1; }
         } else {
             // this warp's record -> the record table of every CTA of the cluster
@@ -430,13 +440,15 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
             const int wi = __shfl_sync(0xFFFFFFFFu, bi, bl);
             const uint4 w0 = tab[wi][0], w1 = tab[wi][1];
             qx = __uint_as_float(w0.z); qy = __uint_as_float(w0.w); qz = __uint_as_float(w1.x);
-            if (crank == 0 && tid == 0) {
+            if (crank == 0 && warp == 0) {
                 const uint32_t rank = ~w0.y;
-                idx[j] = (int)((__brev(rank) & s_mask) | ((rank & ((1u << (32u - s_log2)) - 1u)) << s_log2));
+                if (lane == (j & 31)) keep = (int)((__brev(rank) & s_mask) | ((rank & ((1u << (32u - s_log2)) - 1u)) << s_log2));
+                if ((j & 31) == 31) idx[j - 31 + lane] = keep;
             }
         }
     }
 #undef SPSK_FPS_BUCKET
+    if (crank == 0 && warp == 0 && (m & 31) != 0 && lane < (m & 31)) idx[(m & ~31) + lane] = keep;   // the last partial line
     if (prof != nullptr) {
         if (pf) for (int i = 0; i < 5; ++i) atomicAdd(prof + i, pc[i]);
         if (lane == 0) atomicAdd(prof + 5, visited);
@@ -532,7 +544,7 @@ fps_kernel(int n, int m, uint32_t s_mask, uint32_t s_log2, const float *__restri
     }
 
     int old = 0;
-    if (tid == 0) idx[0] = 0;
+    int keep = 0;   // picks are flushed 32 at a time by warp 0 (see fps_pruned_kernel); idx[0] = 0 lives in lane 0
     const bool has_point = tid < n;
 
     for (int j = 1; j < m; ++j) {
@@ -562,8 +574,12 @@ fps_kernel(int n, int m, uint32_t s_mask, uint32_t s_log2, const float *__restri
         const uint32_t u = has_point ? ordered_bits(__fadd_rn(best, 0.f)) : 0u;
         const uint32_t inv_rank = has_point ? ~fps_rank(kb, s_mask, s_log2) : 0u;
         old = (int)block_argmax(u, inv_rank, slots[j & 1], nwarps, s_mask, s_log2);
-        if (tid == 0) idx[j] = old;
+        if (tid < 32) {
+            if ((tid & 31) == (j & 31)) keep = old;
+            if ((j & 31) == 31) idx[j - 31 + tid] = keep;
+        }
     }
+    if (tid < 32 && (m & 31) != 0 && tid < (m & 31)) idx[(m & ~31) + tid] = keep;   // the last partial line
 
     if (temp) {
 #pragma unroll
@@ -587,7 +603,7 @@ fps_generic_kernel(int n, int m, uint32_t s_mask, uint32_t s_log2, const float *
     temp += scene * (size_t)n;
     idx += scene * (size_t)m;
     int old = 0;
-    if (tid == 0) idx[0] = 0;
+    int keep = 0;   // picks are flushed 32 at a time by warp 0 (see fps_pruned_kernel); idx[0] = 0 lives in lane 0
     const bool has_point = tid < n;
     for (int j = 1; j < m; ++j) {
         float x1 = 0.f, y1 = 0.f, z1 = 0.f;
@@ -607,8 +623,12 @@ fps_generic_kernel(int n, int m, uint32_t s_mask, uint32_t s_log2, const float *
         const uint32_t u = has_point ? ordered_bits(__fadd_rn(best, 0.f)) : 0u;
         const uint32_t inv_rank = has_point ? ~fps_rank((uint32_t)bk, s_mask, s_log2) : 0u;
         old = (int)block_argmax(u, inv_rank, slots[j & 1], T >> 5, s_mask, s_log2);
-        if (tid == 0) idx[j] = old;
+        if (tid < 32) {
+            if ((tid & 31) == (j & 31)) keep = old;
+            if ((j & 31) == 31) idx[j - 31 + tid] = keep;
+        }
     }
+    if (tid < 32 && (m & 31) != 0 && tid < (m & 31)) idx[(m & ~31) + tid] = keep;   // the last partial line
 }
 
 template <int P, bool REGXYZ, bool DISTMAT>
