@@ -67,6 +67,9 @@ WORKLOADS = {
     "kitti_det": dict(batch=16, npts=16384, ncols=5, kind="kitti", cfg="kitti_iassd_cfg", bb="IASSD_DET",
                       text="IA-SSD KITTI detector, inference: the full SA stack + IASSD_Head (2 x 3-layer FC on 256 centres x 512 ch) + box "
                            "decode + score filter + rotated-IoU NMS -> final boxes (SURVEY.md 8f rank 3), batch 16 x 16384 pts per GPU"),
+    "waymo_det": dict(batch=8, npts=65536, ncols=6, kind="waymo", cfg="waymo_iassd_cfg", bb="IASSD_DET",
+                      text="IA-SSD Waymo detector, inference: the Waymo SA stack (65536 -> 16384 -> 4096 -> 2048 -> 1024 centres) + IASSD_Head + "
+                           "box decode + score filter + rotated-IoU NMS over 1024 boxes per scene, batch 8 x 65536 pts per GPU"),
     "waymo": dict(batch=8, npts=65536, ncols=6, kind="waymo", cfg="waymo_iassd_cfg", bb="IASSD_Backbone",
                   text="IA-SSD Waymo cfg full SA stack (D-FPS 65536->16384->4096, ctr-aware top-k ->2048->1024, vote, MSG ball "
                        "query + shared MLP), batch 8 x 65536 pts per GPU, eval"),
@@ -78,7 +81,7 @@ def set_workload(name: str):
     global BATCH, NPTS, NCOLS, WORKLOAD, KIND, _WL, METRIC
     _WL = WORKLOADS[name]
     if _WL["bb"] == "IASSD_DET":
-        METRIC = "IA-SSD detector (SA backbone + head + NMS) scenes/s (16k pts)"
+        METRIC = "IA-SSD detector (SA backbone + head + NMS) scenes/s (%s pts)" % ("64k" if _WL["kind"] == "waymo" else "16k")
     if _WL["bb"] == "SPSNET_DET":
         METRIC = "SPSNet-IA detector (stability generator + SA backbone + head + NMS) scenes/s (16k pts)"
     BATCH, NPTS, NCOLS, WORKLOAD, KIND = _WL["batch"], _WL["npts"], _WL["ncols"], _WL["text"], _WL["kind"]
@@ -149,7 +152,13 @@ def build_net(seed=0):
     if _WL["bb"] == "IASSD_DET":
         from spsnet_b200 import detector
 
-        net = detector.IASSD(num_class=3, input_channels=NCOLS - 1)
+        if KIND == "waymo":
+            from spsnet_b200 import dense_head as dh
+
+            net = detector.IASSD({"BACKBONE_3D": bb.waymo_iassd_cfg(), "POINT_HEAD": dh.waymo_iassd_head_cfg(),
+                                  "POST_PROCESSING": dh.waymo_post_processing()}, num_class=3, input_channels=NCOLS - 1)
+        else:
+            net = detector.IASSD(num_class=3, input_channels=NCOLS - 1)
     elif _WL["bb"] == "SPSNET_DET":
         from spsnet_b200 import detector
         from spsnet_b200 import stability as st
@@ -208,7 +217,8 @@ def cpu_baseline(net_cpu, sample_scenes: int):
             centers = np.concatenate([np.repeat(np.arange(p.shape[0]), out["centers"].shape[1])[:, None].astype(np.float32),
                                       out["centers"].reshape(-1, 3)], axis=1)
             cls, _, boxes = O.head_forward(ns, out["centers_features"], centers, dtype=torch.float32)
-            pp, nc = dh.KITTI_POST_PROCESSING, dh.KITTI_POST_PROCESSING["NMS_CONFIG"]
+            pp = dh.waymo_post_processing() if KIND == "waymo" else dh.KITTI_POST_PROCESSING
+            nc = pp["NMS_CONFIG"]
             O.post_processing(cls, boxes, p.shape[0], pp["SCORE_THRESH"], nc["NMS_THRESH"], nc["NMS_PRE_MAXSIZE"], nc["NMS_POST_MAXSIZE"])
 
     run(pts[:1])  # warm (page in, build)
@@ -530,13 +540,13 @@ def load_reference_detector(state_dict):
         nu = importlib.import_module("pcdet.models.model_utils.model_nms_utils")
     import copy
 
-    hcfg = copy.deepcopy(dh.KITTI_IASSD_HEAD)
+    hcfg = copy.deepcopy(dict(dh.waymo_iassd_head_cfg()) if KIND == "waymo" else dh.KITTI_IASSD_HEAD)
     hcfg["LOSS_CONFIG"] = {"LOSS_CLS": "WeightedCrossEntropy", "LOSS_REG": "WeightedSmoothL1Loss", "LOSS_INS": "WeightedCrossEntropy",
                            "CORNER_LOSS_REGULARIZATION": False, "CENTERNESS_REGULARIZATION": False, "IOU3D_REGULARIZATION": False,
                            "LOSS_WEIGHTS": {"code_weights": [1.0] * 6}}
     head = hm.IASSD_Head(3, 512, bb.Cfg(hcfg))
     head.load_state_dict({k[len("point_head."):]: v for k, v in state_dict.items() if k.startswith("point_head.")}, strict=False)
-    return RefDetector(backbone, head.eval(), bb.Cfg(dh.KITTI_POST_PROCESSING), nu).eval()
+    return RefDetector(backbone, head.eval(), bb.Cfg(dh.waymo_post_processing() if KIND == "waymo" else dh.KITTI_POST_PROCESSING), nu).eval()
 
 
 def load_reference_backbone(state_dict):

@@ -375,25 +375,25 @@ __device__ __forceinline__ void emit_tail(const NmsEmit &em, int *num_keep, int 
     }
 }
 
-// Scenes of at most 512 boxes (IA-SSD: 256 centres): the whole upper-triangular mask fits in shared memory (<= 32 KB), one
+// Scenes of at most 1024 boxes (IA-SSD: 256 centres on KITTI, 1024 on Waymo): the whole mask fits in shared memory, one
 // coalesced load, then ONE WARP walks the rows in order with lane j owning "removed" word j: per row a shuffle to fetch
 // the owner's word, a bit test, and for survivors one shared-memory OR per lane.  No global latency inside the
 // sequential part (the block-wise kernel below pays ~1 us of L2 latency per 64 rows).
-constexpr int RS_MAXN = 512, RS_W = RS_MAXN / NT;
+constexpr int RS_MAXN = 1024, RS_MAXW = RS_MAXN / NT;
 __global__ void __launch_bounds__(256)
 nms_reduce_small_kernel(int n, const int *__restrict__ counts, const unsigned long long *__restrict__ mask,
                         long long *__restrict__ keep, int *__restrict__ num_keep, NmsEmit em) {
-    __shared__ unsigned long long sm[RS_MAXN * RS_W];
-    __shared__ unsigned long long skb[RS_W];
-    __shared__ int spre[RS_W + 1];
-    const int cb = (n + NT - 1) / NT;
+    extern __shared__ unsigned long long sm[];   // n x cb words (8 KB at n = 256, 128 KB at n = 1024)
+    __shared__ unsigned long long skb[RS_MAXW];
+    __shared__ int spre[RS_MAXW + 1];
+    const int cb = (n + NT - 1) / NT;            // <= RS_MAXW <= 32: one "removed" word per lane
     const int scene = blockIdx.x;
     const int nb = counts ? min(counts[scene], n) : n;
     const int cbb = (nb + NT - 1) / NT;
     const unsigned long long *mk = mask + (size_t)scene * n * cb;
-    for (int i = threadIdx.x; i < nb * RS_W; i += 256) {
-        const int row = i / RS_W, j = i - row * RS_W;
-        sm[i] = (j >= (row >> 6) && j < cbb) ? mk[(size_t)row * cb + j] : 0ull;   // words below the diagonal are never written
+    for (int i = threadIdx.x; i < nb * cb; i += 256) {
+        const int row = i / cb, j = i - row * cb;
+        sm[i] = (j >= (row >> 6) && j < cbb) ? mk[i] : 0ull;   // words below the diagonal are never written
     }
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -404,17 +404,17 @@ nms_reduce_small_kernel(int n, const int *__restrict__ counts, const unsigned lo
             const unsigned long long cur = __shfl_sync(0xffffffffu, remv, blk);
             if (!((cur >> bit) & 1ull)) {
                 if (lane == blk) kb |= 1ull << bit;
-                if (lane < RS_W) remv |= sm[t * RS_W + lane];
+                if (lane < cb) remv |= sm[t * cb + lane];
             }
         }
-        if (lane < RS_W) skb[lane] = kb;
-        int c = lane < RS_W ? __popcll(kb) : 0, incl = c;
+        if (lane < RS_MAXW) skb[lane] = lane < cb ? kb : 0ull;
+        int c = lane < cb ? __popcll(kb) : 0, incl = c;
 #pragma unroll
-        for (int o = 1; o < RS_W; o <<= 1) {
+        for (int o = 1; o < RS_MAXW; o <<= 1) {
             const int v = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += v;
         }
-        if (lane < RS_W) spre[lane + 1] = incl;
+        if (lane < RS_MAXW) spre[lane + 1] = incl;
         if (lane == 0) spre[0] = 0;
     }
     __syncthreads();
@@ -423,7 +423,7 @@ nms_reduce_small_kernel(int n, const int *__restrict__ counts, const unsigned lo
         const unsigned long long kb = skb[t >> 6];
         if ((kb >> (t & 63)) & 1ull) emit_kept(em, kp, scene, n, t, spre[t >> 6] + __popcll(kb & ((1ull << (t & 63)) - 1ull)));
     }
-    emit_tail(em, num_keep, scene, spre[RS_W], 256);
+    emit_tail(em, num_keep, scene, spre[RS_MAXW], 256);
 }
 
 constexpr int RT = 256;
@@ -498,8 +498,13 @@ static int nms_launch(int batch, int n, const float *boxes, const int *counts, f
             nms_mask_kernel<false><<<grid, 256, 0, st>>>(n, boxes, counts, thresh, mask);
     }
     SPSK_LAUNCH_CHECK("nms_mask_kernel");
-    if (n <= RS_MAXN)
-        nms_reduce_small_kernel<<<batch, 256, 0, st>>>(n, counts, mask, keep, num_keep, em);
+    if (n <= RS_MAXN) {
+        const int smem = n * cb * 8;
+        static SmemAttrOnce attr;
+        if (smem > 48 * 1024)
+            if (int rc = attr.ensure((const void *)nms_reduce_small_kernel, RS_MAXN * RS_MAXW * 8, "cudaFuncSetAttribute(nms_reduce_small_kernel)")) return rc;
+        nms_reduce_small_kernel<<<batch, 256, smem, st>>>(n, counts, mask, keep, num_keep, em);
+    }
     else
         nms_reduce_kernel<<<batch, RT, cb * 8, st>>>(n, counts, mask, keep, num_keep, em);
     SPSK_LAUNCH_CHECK("nms_reduce_kernel");

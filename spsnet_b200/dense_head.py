@@ -34,7 +34,7 @@ from ._lib import DetectDesc, check, lib
 from .backbone import Cfg
 
 __all__ = ["PointResidual_BinOri_Coder", "IASSD_Head", "MLT_SSD_Head", "detections_padded", "Detections", "class_agnostic_nms", "post_processing",
-           "kitti_iassd_head_cfg", "KITTI_POST_PROCESSING"]
+           "kitti_iassd_head_cfg", "waymo_iassd_head_cfg", "waymo_post_processing", "KITTI_POST_PROCESSING"]
 
 
 def _stream() -> int:
@@ -64,6 +64,24 @@ KITTI_POST_PROCESSING = {
     "NMS_CONFIG": {"MULTI_CLASSES_NMS": False, "NMS_TYPE": "nms_gpu", "NMS_THRESH": 0.01, "NMS_PRE_MAXSIZE": 4096,
                    "NMS_POST_MAXSIZE": 500},
 }
+
+
+def waymo_iassd_head_cfg() -> Cfg:
+    """reference tools/cfgs/waymo_models/IA-SSD.yaml:69-93: same stacks, Waymo mean sizes."""
+    import copy
+
+    c = copy.deepcopy(KITTI_IASSD_HEAD)
+    c["TARGET_CONFIG"]["BOX_CODER_CONFIG"]["mean_size"] = [[4.7, 2.1, 1.7], [0.91, 0.86, 1.73], [1.78, 0.84, 1.78]]
+    return Cfg(c)
+
+
+def waymo_post_processing() -> dict:
+    """reference tools/cfgs/waymo_models/IA-SSD.yaml:118-130 (NMS_THRESH 0.1)."""
+    import copy
+
+    c = copy.deepcopy(KITTI_POST_PROCESSING)
+    c["NMS_CONFIG"]["NMS_THRESH"] = 0.1
+    return c
 
 
 def kitti_iassd_head_cfg() -> Cfg:
