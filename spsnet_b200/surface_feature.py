@@ -37,42 +37,36 @@ def _as_ball_query_coords(pos: torch.Tensor) -> torch.Tensor:
     return pos.contiguous().view(-1)[: B * N * 3].view(B, N, 3)
 
 
+_ACTIVATIONS = {None: nn.Identity, "relu": nn.ReLU, "elu": lambda: nn.ELU(alpha=1.0), "lrelu": lambda: nn.LeakyReLU(0.1)}
+
+
 class FCLayer(nn.Module):
-    """reference surface_feature.py:7-26."""
+    """Linear + optional activation; parameters `linear.weight` / `linear.bias` (reference surface_feature.py:7-26)."""
 
     def __init__(self, in_features, out_features, bias=True, activation=None):
         super().__init__()
+        if activation not in _ACTIVATIONS:
+            raise ValueError(f"unknown activation {activation!r}")
         self.linear = nn.Linear(in_features, out_features, bias=bias)
-        if activation is None:
-            self.activation = nn.Identity()
-        elif activation == "relu":
-            self.activation = nn.ReLU()
-        elif activation == "elu":
-            self.activation = nn.ELU(alpha=1.0)
-        elif activation == "lrelu":
-            self.activation = nn.LeakyReLU(0.1)
-        else:
-            raise ValueError()
+        self.activation = _ACTIVATIONS[activation]()
 
     def forward(self, x):
         return self.activation(self.linear(x))
 
 
 class Aggregator(nn.Module):
-    """reference surface_feature.py:28-43."""
+    """Reduction over the neighbour axis: 'mean' | 'sum' | 'max' (reference surface_feature.py:28-43)."""
 
     def __init__(self, oper):
         super().__init__()
-        assert oper in ("mean", "sum", "max")
+        if oper not in ("mean", "sum", "max"):
+            raise AssertionError(oper)
         self.oper = oper
 
     def forward(self, x, dim=2):
-        if self.oper == "mean":
-            return x.mean(dim=dim, keepdim=False)
-        if self.oper == "sum":
-            return x.sum(dim=dim, keepdim=False)
-        ret, _ = x.max(dim=dim, keepdim=False)
-        return ret
+        if self.oper == "max":
+            return x.max(dim=dim)[0]   # (not amax: ties must send the gradient to one element, like the reference)
+        return {"mean": torch.mean, "sum": torch.sum}[self.oper](x, dim=dim)
 
 
 class DenseEdgeConv(nn.Module):
