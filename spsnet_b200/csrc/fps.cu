@@ -302,7 +302,7 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
     // Ties are rare: each arg-max first reduces the value alone and only falls back to the second (rank) reduction
     // when the maximum is not unique.
     __shared__ uint2 slots2[2][W];            // single CTA: one (value, ~rank) slot per warp
-    __shared__ uint4 crec[CL ? 2 : 1][CL ? 8 * W : 1][2];   // cluster: [parity][cta * W + warp] = {value, ~rank, x, y | z, -, -, -}
+    __shared__ uint4 crec[CL ? 2 : 1][CL ? 16 * W : 1][2];   // cluster: [parity][cta * W + warp] = {value, ~rank, x, y | z, -, -, -}
     uint32_t bpos = 0u;   // lane p: sorted position of sub-bucket p's best point
     // The picks are written 32 at a time: lane (j & 31) of warp 0 keeps pick j in a register and the warp stores one
     // coalesced 128-byte line every 32 iterations.  A store per iteration sits on the latency chain: the CTA barrier of the
@@ -461,6 +461,7 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
 }
 
 static unsigned long long *g_fps_prof = nullptr;
+constexpr int SPSK_FPS_NO_CLUSTER = 1;   // internal: the requested cluster size cannot run here, use the streaming kernel
 
 template <int P, bool CL, int LADDER>
 static int launch_fps_pruned_v(int b, int n, int m, int csize, const float *src, float *temp, int *idx, cudaStream_t st) {
@@ -473,6 +474,11 @@ static int launch_fps_pruned_v(int b, int n, int m, int csize, const float *src,
     if (!CL) {
         kern<<<b, 512, smem, st>>>(n, m, src, temp, idx, g_fps_prof);
     } else {
+        if (csize > 8) {
+            // 16-CTA clusters are a non-portable size: opt in, and make sure this device can co-schedule one
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e != cudaSuccess) { (void)cudaGetLastError(); return SPSK_FPS_NO_CLUSTER; }
+        }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(b * csize));
         cfg.blockDim = dim3(512);
@@ -485,6 +491,11 @@ static int launch_fps_pruned_v(int b, int n, int m, int csize, const float *src,
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
+        if (csize > 8) {
+            int nclusters = 0;
+            cudaError_t q = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
+            if (q != cudaSuccess || nclusters < 1) { (void)cudaGetLastError(); return SPSK_FPS_NO_CLUSTER; }
+        }
         cudaError_t e = cudaLaunchKernelEx(&cfg, kern, n, m, src, temp, idx, g_fps_prof);
         if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(fps_pruned_kernel, cluster)");
     }
@@ -680,18 +691,22 @@ static int fps_dispatch(int b, int n, int m, const float *src, float *temp, int 
     // n > 16384 (Waymo-shaped scenes): one 8-CTA cluster per scene, each CTA prunes its own slice, DSMEM arg-max
     // cluster size: the fewest CTAs that hold the scene (16384 points each) -- least SM-time per scene, which is what a
     // pipelined serving loop pays; SPSK_FPS_CLUSTER=8 trades SMs for latency
-    if (!DISTMAT && threads == 1024 && n > 16384 && n <= 8 * 16384 && !fps_dense_forced()) {
-        int cl = n <= 2 * 16384 ? 2 : (n <= 4 * 16384 ? 4 : 8);
-        if (const char *e = getenv("SPSK_FPS_CLUSTER")) { const int v = atoi(e); if ((v == 2 || v == 4 || v == 8) && v >= cl) cl = v; }
+    // 131072 < n <= 262144: one 16-CTA cluster (non-portable size; falls through to the streaming kernel if the device
+    // cannot co-schedule it)
+    if (!DISTMAT && threads == 1024 && n > 16384 && n <= 16 * 16384 && !fps_dense_forced()) {
+        int cl = n <= 2 * 16384 ? 2 : (n <= 4 * 16384 ? 4 : (n <= 8 * 16384 ? 8 : 16));
+        if (const char *e = getenv("SPSK_FPS_CLUSTER")) { const int v = atoi(e); if ((v == 2 || v == 4 || v == 8 || v == 16) && v >= cl) cl = v; }
         const int per_cta = (n + cl - 1) / cl;
-        if (per_cta <= 2048) return launch_fps_pruned<4, true>(b, n, m, cl, src, temp, idx, st);
-        if (per_cta <= 4096) return launch_fps_pruned<8, true>(b, n, m, cl, src, temp, idx, st);
-        if (per_cta <= 8192) return launch_fps_pruned<16, true>(b, n, m, cl, src, temp, idx, st);
-        return launch_fps_pruned<32, true>(b, n, m, cl, src, temp, idx, st);
+        int rc;
+        if (per_cta <= 2048) rc = launch_fps_pruned<4, true>(b, n, m, cl, src, temp, idx, st);
+        else if (per_cta <= 4096) rc = launch_fps_pruned<8, true>(b, n, m, cl, src, temp, idx, st);
+        else if (per_cta <= 8192) rc = launch_fps_pruned<16, true>(b, n, m, cl, src, temp, idx, st);
+        else rc = launch_fps_pruned<32, true>(b, n, m, cl, src, temp, idx, st);
+        if (rc != SPSK_FPS_NO_CLUSTER) return rc;
     }
     if (!fits) {
         SPSK_REQUIRE(temp != nullptr, SPSK_ERR_UNSUPPORTED,
-                     "fps: n=%d exceeds the on-chip variants (<=131072); pass a (b,n) `temp` scratch filled with 1e10", n);
+                     "fps: n=%d exceeds the on-chip variants (<=131072, or <=262144 where 16-CTA clusters can run); pass a (b,n) `temp` scratch filled with 1e10", n);
         fps_generic_kernel<DISTMAT><<<b, threads, 0, st>>>(n, m, s_mask, s_log2, src, temp, idx);
         SPSK_LAUNCH_CHECK("fps_generic_kernel");
         return SPSK_OK;

@@ -25,7 +25,8 @@ __all__ = [
     "score_topk", "gather_rows", "ball_query_msg",
 ]
 
-FPS_ONCHIP_MAX_N = 131072  # <= 16384: one CTA per scene; <= 131072: one 8-CTA cluster per scene; above: `temp` scratch in L2
+FPS_ONCHIP_MAX_N = 131072  # <= 16384: one CTA per scene; <= 131072: one 2/4/8-CTA cluster per scene; above: a 16-CTA cluster
+# (<= 262144) where the device can schedule one, else the streaming kernel over the `temp` scratch, which is allocated from here on
 
 
 def _stream() -> int:

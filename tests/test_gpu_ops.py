@@ -74,13 +74,26 @@ def test_fps_cluster_ties(oracle):
     np.testing.assert_array_equal(got, oracle.fps(xyz, 400))
 
 
-def test_fps_large_n_generic(oracle):
-    """n > 131072: running minima in the caller-provided `temp` scratch (L2), same samples."""
+@pytest.mark.parametrize("b,n,m", [(1, 140000, 120), (2, 200000, 300), (1, 262144, 150)])
+def test_fps_16cta_cluster(oracle, b, n, m):
+    """131072 < n <= 262144: one 16-CTA cluster per scene (non-portable cluster size; the streaming kernel takes over where
+    the device cannot co-schedule it) -- same samples, also with lattice ties across all 16 CTAs."""
     from spsnet_b200 import pointnet2_utils as pu
 
-    xyz = _xyz(1, 140000, seed=3, kind="waymo")
-    got = pu.furthest_point_sample(dev(xyz), 120).cpu().numpy()
-    np.testing.assert_array_equal(got, oracle.fps(xyz, 120))
+    xyz = _xyz(b, n, seed=3, kind="waymo")
+    got = pu.furthest_point_sample(dev(xyz), m).cpu().numpy()
+    np.testing.assert_array_equal(got, oracle.fps(xyz, m))
+    lat = np.random.default_rng(n).integers(0, 9, (1, n, 3)).astype(np.float32)
+    np.testing.assert_array_equal(pu.furthest_point_sample(dev(lat), 200).cpu().numpy(), oracle.fps(lat, 200))
+
+
+def test_fps_large_n_generic(oracle):
+    """n > 262144: running minima in the caller-provided `temp` scratch (L2), same samples."""
+    from spsnet_b200 import pointnet2_utils as pu
+
+    xyz = _xyz(1, 270000, seed=3, kind="waymo")
+    got = pu.furthest_point_sample(dev(xyz), 60).cpu().numpy()
+    np.testing.assert_array_equal(got, oracle.fps(xyz, 60))
 
 
 @pytest.mark.parametrize("b,n,m", [(2, 64, 20), (2, 1000, 128), (1, 2048, 512)])
