@@ -124,6 +124,17 @@ SPSK_API int spsk_three_interpolate(int b, int c, int m, int n, const float *poi
 SPSK_API int spsk_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
                                 const float *weight, float *grad_points, spsk_stream_t stream);
 
+/* Atomic-free, bit-reproducible form of the three backward scatters above: a stable sort of the
+ * (scene, target) keys followed by a segment reduction in ascending entry order (csrc/scatter_grad.cu).
+ *   grad_points[b, ch, idx[b, l]] += weight[b, l] * grad_out[b, ch, l / div]      l = 0 .. l_per_scene-1
+ * gather: l_per_scene = npoints, div = 1, weight = NULL; group: l_per_scene = npoints * nsample, div = 1, weight = NULL;
+ * three_interpolate: l_per_scene = 3 n, div = 3, weight = the (b, n, 3) weights.  grad_out (b, c, cols) with
+ * cols >= ceil(l_per_scene / div); grad_points (b, c, n) is fully written (no pre-zeroing needed). */
+SPSK_API long long spsk_scatter_grad_workspace_bytes(int b, int n, long long l_per_scene);
+SPSK_API int spsk_scatter_grad(int b, int c, int n, long long l_per_scene, int cols, int div, const float *grad_out,
+                               const int *idx, const float *weight, float *grad_points, void *workspace,
+                               long long workspace_bytes, spsk_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Section 2 -- fused replacements for torch-op chains in pointnet2_modules.py
  * ---------------------------------------------------------------------------------------------- */

@@ -35,6 +35,8 @@ SIGNATURES = {
     "spsk_three_nn": [_i, _i, _i, _p, _p, _p, _p, _p],
     "spsk_three_interpolate": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
     "spsk_three_interpolate_grad": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
+    "spsk_scatter_grad_workspace_bytes": [_i, _i, C.c_longlong],
+    "spsk_scatter_grad": [_i, _i, _i, C.c_longlong, _i, _i, _p, _p, _p, _p, _p, C.c_longlong, _p],
     "spsk_score_topk": [_i, _i, _i, _i, _p, _p, _p, _p, _p],
     "spsk_gather_rows": [_i, _i, _i, _i, _p, _p, _p, _p],
     "spsk_ball_query_msg": [_i, _i, _i, _i, C.POINTER(_f), C.POINTER(_i), _p, _p, C.POINTER(_p), _p],
@@ -58,7 +60,7 @@ SIGNATURES = {
     "spsk_edge_conv_aggregate": [_p, _i, _i, _i, _p, _p, _p, _p, _i, _p],
 }
 _RESTYPE = {"spsk_last_error": C.c_char_p, "spsk_launch_count": C.c_ulonglong,
-            "spsk_ball_query_grid_workspace_bytes": C.c_longlong, "spsk_nms_workspace_bytes": C.c_longlong,
+            "spsk_ball_query_grid_workspace_bytes": C.c_longlong, "spsk_nms_workspace_bytes": C.c_longlong, "spsk_scatter_grad_workspace_bytes": C.c_longlong,
             "spsk_detect_workspace_bytes": C.c_longlong}
 
 

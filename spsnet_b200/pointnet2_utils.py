@@ -33,6 +33,30 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def deterministic_grads() -> bool:
+    """Backward of gather / group / three_interpolate through the sorted segment reduction (spsk_scatter_grad: no atomics,
+    bit-reproducible) instead of the reference-style atomicAdd scatters.  On when torch.use_deterministic_algorithms(True)
+    is set or SPSK_DETERMINISTIC_GRAD=1."""
+    return torch.are_deterministic_algorithms_enabled() or os.environ.get("SPSK_DETERMINISTIC_GRAD", "0") == "1"
+
+
+def scatter_grad(grad_out: torch.Tensor, idx: torch.Tensor, n: int, weight: torch.Tensor = None, div: int = 1) -> torch.Tensor:
+    """grad_points[b, c, idx[b, l]] += weight[b, l] * grad_out[b, c, l // div] without atomics (include/spsk.h).
+    grad_out (B, C, cols) f32, idx (B, L) i32, weight (B, L) f32 or None -> (B, C, n)."""
+    B, Cc, cols = grad_out.shape
+    L = idx.shape[1]
+    out = torch.empty((B, Cc, n), dtype=torch.float32, device=grad_out.device)
+    need = int(lib.spsk_scatter_grad_workspace_bytes(B, n, L))
+    if need < 0:
+        raise RuntimeError("scatter_grad: problem too large")
+    ws = torch.empty(max(need, 8), dtype=torch.uint8, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        check(lib.spsk_scatter_grad(B, Cc, n, L, cols, div, grad_out.data_ptr(), idx.data_ptr(),
+                                    weight.data_ptr() if weight is not None else None, out.data_ptr(), ws.data_ptr(),
+                                    ws.numel(), _stream()), "scatter_grad")
+    return out
+
+
 def _chk(t: torch.Tensor, name: str, dtype: torch.dtype, ndim: int) -> None:
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor")
@@ -117,8 +141,10 @@ class GatherOperation(Function):
     def backward(ctx, grad_out):
         idx, Cc, N = ctx.for_backwards
         B, npoint = idx.shape
-        grad_features = torch.zeros((B, Cc, N), dtype=torch.float32, device=grad_out.device)
         g = grad_out.detach().contiguous()
+        if deterministic_grads():
+            return scatter_grad(g, idx, N), None
+        grad_features = torch.zeros((B, Cc, N), dtype=torch.float32, device=grad_out.device)
         with torch.cuda.device(g.device):
             check(lib.spsk_gather_points_grad(B, Cc, N, npoint, g.data_ptr(), idx.data_ptr(), grad_features.data_ptr(), _stream()),
                   "gather_points_grad")
@@ -174,8 +200,10 @@ class ThreeInterpolate(Function):
     def backward(ctx, grad_out: torch.Tensor):
         idx, weight, m = ctx.three_interpolate_for_backward
         B, c, n = grad_out.shape
-        grad_features = torch.zeros((B, c, m), dtype=torch.float32, device=grad_out.device)
         g = grad_out.detach().contiguous()
+        if deterministic_grads():
+            return scatter_grad(g, idx.view(B, -1), m, weight=weight.contiguous().view(B, -1), div=3), None, None
+        grad_features = torch.zeros((B, c, m), dtype=torch.float32, device=grad_out.device)
         with torch.cuda.device(g.device):
             check(lib.spsk_three_interpolate_grad(B, c, n, m, g.data_ptr(), idx.data_ptr(), weight.data_ptr(),
                                                   grad_features.data_ptr(), _stream()), "three_interpolate_grad")
@@ -205,8 +233,10 @@ class GroupingOperation(Function):
     def backward(ctx, grad_out: torch.Tensor):
         idx, N = ctx.for_backwards
         B, Cc, npoint, nsample = grad_out.shape
-        grad_features = torch.zeros((B, Cc, N), dtype=torch.float32, device=grad_out.device)
         g = grad_out.detach().contiguous()
+        if deterministic_grads():
+            return scatter_grad(g.view(B, Cc, -1), idx.view(B, -1), N), None
+        grad_features = torch.zeros((B, Cc, N), dtype=torch.float32, device=grad_out.device)
         with torch.cuda.device(g.device):
             check(lib.spsk_group_points_grad(B, Cc, N, npoint, nsample, g.data_ptr(), idx.data_ptr(),
                                              grad_features.data_ptr(), _stream()), "group_points_grad")

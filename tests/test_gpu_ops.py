@@ -323,3 +323,45 @@ def test_ball_query_grid_dense_scenes(oracle, n, m, sigma):
     for r, s, a, c in zip(radii, ns, g, bf):
         np.testing.assert_array_equal(a.cpu().numpy(), c.cpu().numpy())
         np.testing.assert_array_equal(a.cpu().numpy(), oracle.ball_query(r, s, xyz, new_xyz))
+
+
+@pytest.mark.parametrize("b,c,n,npoint,nsample", [(2, 7, 300, 64, 5), (3, 64, 4096, 1024, 32), (1, 5, 50, 200, 16), (2, 16, 1000, 1, 1)])
+def test_deterministic_backward_matches_atomics_and_repeats(oracle, monkeypatch, b, c, n, npoint, nsample):
+    """SPSK_DETERMINISTIC_GRAD=1: gather / group / three_interpolate backward through the sorted segment reduction
+    (spsk_scatter_grad): equal to the oracle's scatter (reference :46-63, :14-31, :127-149) up to summation order, equal to
+    the atomic path, and BIT-identical from run to run (heavily repeated indices included)."""
+    from spsnet_b200 import pointnet2_utils as pu
+
+    rng = np.random.default_rng(b * 1000 + n)
+    f_np = rng.standard_normal((b, c, n)).astype(np.float32)
+    gi = rng.integers(0, n, (b, npoint)).astype(np.int32)
+    gi[:, : max(1, npoint // 4)] = 3 % n                    # a hot target: long runs in the segment reduction
+    qi = rng.integers(0, n, (b, npoint, nsample)).astype(np.int32)
+    qi[:, :, 0] = qi[:, :1, 0]                              # every centre shares one neighbour
+    g1 = rng.standard_normal((b, c, npoint)).astype(np.float32)
+    g2 = rng.standard_normal((b, c, npoint, nsample)).astype(np.float32)
+    ti = rng.integers(0, n, (b, npoint, 3)).astype(np.int32)
+    tw = rng.random((b, npoint, 3)).astype(np.float32)
+
+    def grads():
+        out = []
+        f = dev(f_np).requires_grad_(True)
+        pu.gather_operation(f, dev(gi)).backward(dev(g1))
+        out.append(f.grad.clone()); f.grad = None
+        pu.grouping_operation(f, dev(qi)).backward(dev(g2))
+        out.append(f.grad.clone()); f.grad = None
+        pu.three_interpolate(f, dev(ti), dev(tw)).backward(dev(g1))
+        out.append(f.grad.clone())
+        return out
+
+    monkeypatch.delenv("SPSK_DETERMINISTIC_GRAD", raising=False)
+    atomic = grads()
+    monkeypatch.setenv("SPSK_DETERMINISTIC_GRAD", "1")
+    assert pu.deterministic_grads()
+    det_a, det_b = grads(), grads()
+    want = [oracle.gather_grad(g1, gi, n), oracle.group_grad(g2, qi, n), oracle.three_interpolate_grad(g1, ti, tw, n)]
+    for a, d1, d2, w in zip(atomic, det_a, det_b, want):
+        assert torch.equal(d1, d2), "the sorted segment reduction must be bit-reproducible"
+        scale = max(1.0, float(np.abs(w).max()))
+        assert float((d1.cpu() - torch.from_numpy(w)).abs().max()) <= 2e-5 * scale
+        assert float((d1 - a).abs().max()) <= 2e-5 * scale
