@@ -169,7 +169,9 @@ __device__ __forceinline__ void st_cluster_v4(const void *local_ptr, uint32_t ct
     asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <int P, bool CL, int LADDER>
+// PROF: compile the phase counters in (spsk_fps_set_profile).  They are predicated instructions, but on this latency chain
+// every issue slot counts: 16 warps x ~40 predicated-off instructions per iteration were ~10 % of the iteration.
+template <int P, bool CL, int LADDER, bool PROF>
 __global__ void __launch_bounds__(512, 1)
 fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__restrict__ temp, int *__restrict__ idx,
                   unsigned long long *__restrict__ prof) {
@@ -301,8 +303,11 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
     //      slot, so the next iteration reads its coordinates directly (no index -> position lookup on the chain).
     // Ties are rare: each arg-max first reduces the value alone and only falls back to the second (rank) reduction
     // when the maximum is not unique.
-    __shared__ uint2 slots2[2][W];            // single CTA: one (value, ~rank) slot per warp
+    __shared__ uint2 slots2[2][32];           // single CTA: one (value, ~rank) slot per warp; entries >= W stay zero so the
+                                              // read-back needs no lane guard (a divergent load costs a BSSY/BSYNC pair)
     __shared__ uint4 crec[CL ? 2 : 1][CL ? 16 * W : 1][2];   // cluster: [parity][cta * W + warp] = {value, ~rank, x, y | z, -, -, -}
+    if (tid < 64) slots2[tid >> 5][tid & 31] = make_uint2(0u, 0u);
+    __syncthreads();
     uint32_t bpos = 0u;   // lane p: sorted position of sub-bucket p's best point
     // The picks are written 32 at a time: lane (j & 31) of warp 0 keeps pick j in a register and the warp stores one
     // coalesced 128-byte line every 32 iterations.  A store per iteration sits on the latency chain: the CTA barrier of the
@@ -312,7 +317,7 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
     float qx = __ldg(scene_base), qy = __ldg(scene_base + 1), qz = __ldg(scene_base + 2);
     if (CL) cluster_sync_all();      // every CTA of the cluster is resident before the first remote store
     // optional profiling (spsk_fps_set_profile): cycles of warp 0 per phase + sub-buckets visited by all warps
-    const bool pf = prof != nullptr && tid == 0 && !CL;
+    const bool pf = PROF && prof != nullptr && tid == 0 && !CL;
     unsigned long long pc[6] = {0, 0, 0, 0, 0, 0};
     unsigned long long visited = 0;
 
@@ -336,7 +341,7 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
         break;
 
     for (int j = 1; j < m; ++j) {
-        long long t0 = pf ? clock64() : 0;
+        long long t0 = (PROF && pf) ? clock64() : 0;
         const float x1 = CL ? qx : sx[qpos], y1 = CL ? qy : sy[qpos], z1 = CL ? qz : sz[qpos];
         // box lower bound with the distance's own expression (monotone => rigorous in fp32)
         const float lx = fmaxf(fmaxf(__fsub_rn(bx0, x1), __fsub_rn(x1, bx1)), 0.f);
@@ -345,8 +350,8 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
         const float lb = __fmaf_rn(lz, lz, __fmaf_rn(lx, lx, __fmul_rn(ly, ly)));
         const bool act = (lane < P) && (lb < __uint_as_float(bmax_bits));
         uint32_t mask = __ballot_sync(0xFFFFFFFFu, act);
-        if (pf) { const long long t1 = clock64(); pc[0] += t1 - t0; t0 = t1; }
-        if (prof != nullptr && lane == 0) visited += __popc(mask);
+        if (PROF && pf) { const long long t1 = clock64(); pc[0] += t1 - t0; t0 = t1; }
+        if (PROF && prof != nullptr && lane == 0) visited += __popc(mask);
 #define SPSK_FPS_ALL_BUCKETS                                                                                              \
     SPSK_FPS_BUCKET(0) SPSK_FPS_BUCKET(1) SPSK_FPS_BUCKET(2) SPSK_FPS_BUCKET(3) SPSK_FPS_BUCKET(4) SPSK_FPS_BUCKET(5)        \
     SPSK_FPS_BUCKET(6) SPSK_FPS_BUCKET(7) SPSK_FPS_BUCKET(8) SPSK_FPS_BUCKET(9) SPSK_FPS_BUCKET(10) SPSK_FPS_BUCKET(11)      \
@@ -386,7 +391,7 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
             }
         }
 #undef SPSK_FPS_ALL_BUCKETS
-        if (pf) { const long long t1 = clock64(); pc[1] += t1 - t0; t0 = t1; }
+        if (PROF && pf) { const long long t1 = clock64(); pc[1] += t1 - t0; t0 = t1; }
         // warp best over its P sub-buckets
         const uint32_t wv = (lane < P) ? bmax_bits : 0u;
         const uint32_t wm = __reduce_max_sync(0xFFFFFFFFu, wv);
@@ -398,13 +403,13 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
         if (!CL) {
             uint2 *sl = slots2[j & 1];
             if (lane == 0) sl[warp] = make_uint2(wm, wr);
-            if (pf) { const long long t1 = clock64(); pc[2] += t1 - t0; t0 = t1; }
+            if (PROF && pf) { const long long t1 = clock64(); pc[2] += t1 - t0; t0 = t1; }
             __syncthreads();
-            if (pf) { const long long t1 = clock64(); pc[3] += t1 - t0; t0 = t1; }
+            if (PROF && pf) { const long long t1 = clock64(); pc[3] += t1 - t0; t0 = t1; }
             // block best over the W warp slots
-            const uint2 v = (lane < W) ? sl[lane] : make_uint2(0u, 0u);
+            const uint2 v = sl[lane];
             const uint32_t m2 = __reduce_max_sync(0xFFFFFFFFu, v.x);
-            const uint32_t r2 = __reduce_max_sync(0xFFFFFFFFu, (lane < W && v.x == m2) ? v.y : 0u);
+            const uint32_t r2 = __reduce_max_sync(0xFFFFFFFFu, (v.x == m2) ? v.y : 0u);
             // the sample's original index: rank(k) = brev(k & s_mask) | (k >> s_log2); its sorted position through the map
             const uint32_t rank = ~r2;
             const int old = (int)((__brev(rank) & s_mask) | ((rank & ((1u << (32u - s_log2)) - 1u)) << s_log2));
@@ -413,7 +418,7 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
                 if (lane == (j & 31)) keep = old;
                 if ((j & 31) == 31) idx[j - 31 + lane] = keep;
             }
-            if (pf) { const long long t1 = clock64(); pc[4] += t1 - t0; t0 = t1; }
+            if (PROF && pf) { const long long t1 = clock64(); pc[4] += t1 - t0; t0 = t1; }
         } else {
             // this warp's record -> the record table of every CTA of the cluster
             const uint32_t rv = wm, rr = wr, rp = wpos;
@@ -449,7 +454,7 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
     }
 #undef SPSK_FPS_BUCKET
     if (crank == 0 && warp == 0 && (m & 31) != 0 && lane < (m & 31)) idx[(m & ~31) + lane] = keep;   // the last partial line
-    if (prof != nullptr) {
+    if (PROF && prof != nullptr) {
         if (pf) for (int i = 0; i < 5; ++i) atomicAdd(prof + i, pc[i]);
         if (lane == 0) atomicAdd(prof + 5, visited);
     }
@@ -463,10 +468,10 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
 static unsigned long long *g_fps_prof = nullptr;
 constexpr int SPSK_FPS_NO_CLUSTER = 1;   // internal: the requested cluster size cannot run here, use the streaming kernel
 
-template <int P, bool CL, int LADDER>
+template <int P, bool CL, int LADDER, bool PROF = false>
 static int launch_fps_pruned_v(int b, int n, int m, int csize, const float *src, float *temp, int *idx, cudaStream_t st) {
     const size_t smem = sizeof(float) * 3 * 512 * P + (CL ? 0 : sizeof(unsigned short) * 512 * P);   // xyz (+ index -> position map)
-    auto kern = fps_pruned_kernel<P, CL, LADDER>;
+    auto kern = fps_pruned_kernel<P, CL, LADDER, PROF>;
     if (smem + 8192 > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fps_pruned_kernel)");
@@ -510,6 +515,7 @@ static int launch_fps_pruned(int b, int n, int m, int csize, const float *src, f
     int mode = 2;   // 1 = ladder, 2 = two-level ladder (fastest at every P on B200), 0 = switch over set bits
     if (const char *e = getenv("SPSK_FPS_DISPATCH")) mode = e[0] == 'l' ? 1 : (e[0] == 'g' ? 2 : 0);
     if (mode == 1) return launch_fps_pruned_v<P, CL, 1>(b, n, m, csize, src, temp, idx, st);
+    if (mode == 2 && g_fps_prof != nullptr) return launch_fps_pruned_v<P, CL, 2, true>(b, n, m, csize, src, temp, idx, st);
     if (mode == 2) return launch_fps_pruned_v<P, CL, 2>(b, n, m, csize, src, temp, idx, st);
     return launch_fps_pruned_v<P, CL, 0>(b, n, m, csize, src, temp, idx, st);
 }
