@@ -41,7 +41,7 @@ namespace spsk {
 // G = epilogue warpgroups.  G = 1 (192 threads, up to 3 CTAs per SM) for chains whose concurrency comes from co-resident
 // CTAs; G = 2 (320 threads, one CTA per SM) for the wide chains: the two warpgroups take alternate jobs, so two
 // accumulators drain concurrently and every scheduler holds two epilogue warps to hide TMEM / shared-memory latency.
-template <int G>
+template <int G, bool PROF>
 __global__ void __launch_bounds__(128 * G + 64, G == 1 ? 3 : 1)
 sa_mma_kernel(const __grid_constant__ SaArgs a) {
     constexpr int W_PROD = 4 * G, W_MMA = 4 * G + 1;
@@ -99,7 +99,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                 }
             }
         } else {
-            Prof pf;
+            ProfT<PROF> pf;
             pf.init(a.prof != nullptr && leader);
             uint32_t tcount = 0;
             int ws = 0, ls = 0;
@@ -237,7 +237,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                 }
             }
             __syncwarp();
-            Prof pf;
+            ProfT<PROF> pf;
             pf.init(a.prof != nullptr && leader);
             const long long t_start = pf.now();
             uint32_t job = 0;
@@ -310,7 +310,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
             pf.flush(a.prof);
         } else {
             const bool leader = elect_one();
-            Prof pf;
+            ProfT<PROF> pf;
             pf.init(a.prof != nullptr && leader);
             const long long t_start = pf.now();
             uint32_t job = 0;
@@ -412,7 +412,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
         }
     } else {
         // ================= gather + epilogue (threads 0..127; thread = row / TMEM lane) =================
-        Prof pf;
+        ProfT<PROF> pf;
         pf.init(a.prof != nullptr && tid == 0);
         const long long t_start = pf.now();
         uint32_t job = 0;
@@ -889,11 +889,23 @@ extern "C" int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stre
     const bool two_groups = P.ctas == 1 && !getenv("SPSK_SA_ONE_GROUP");
     static SmemAttrOnce attr1, attr2;
     if (two_groups) {
-        if (int rc = attr2.ensure(reinterpret_cast<const void *>(sa_mma_kernel<2>), 227 * 1024, "sa_mma_kernel<2>")) return rc;
-        sa_mma_kernel<2><<<grid, 320, P.smem, as_stream(stream)>>>(a);
+        if (a.prof) {
+            static SmemAttrOnce attr2p;
+            if (int rc = attr2p.ensure(reinterpret_cast<const void *>(sa_mma_kernel<2, true>), 227 * 1024, "sa_mma_kernel<2,prof>")) return rc;
+            sa_mma_kernel<2, true><<<grid, 320, P.smem, as_stream(stream)>>>(a);
+        } else {
+            if (int rc = attr2.ensure(reinterpret_cast<const void *>(sa_mma_kernel<2, false>), 227 * 1024, "sa_mma_kernel<2>")) return rc;
+            sa_mma_kernel<2, false><<<grid, 320, P.smem, as_stream(stream)>>>(a);
+        }
     } else {
-        if (int rc = attr1.ensure(reinterpret_cast<const void *>(sa_mma_kernel<1>), 227 * 1024, "sa_mma_kernel<1>")) return rc;
-        sa_mma_kernel<1><<<grid, 192, P.smem, as_stream(stream)>>>(a);
+        if (a.prof) {
+            static SmemAttrOnce attr1p;
+            if (int rc = attr1p.ensure(reinterpret_cast<const void *>(sa_mma_kernel<1, true>), 227 * 1024, "sa_mma_kernel<1,prof>")) return rc;
+            sa_mma_kernel<1, true><<<grid, 192, P.smem, as_stream(stream)>>>(a);
+        } else {
+            if (int rc = attr1.ensure(reinterpret_cast<const void *>(sa_mma_kernel<1, false>), 227 * 1024, "sa_mma_kernel<1>")) return rc;
+            sa_mma_kernel<1, false><<<grid, 192, P.smem, as_stream(stream)>>>(a);
+        }
     }
     SPSK_LAUNCH_CHECK("sa_mma_kernel");
     return SPSK_OK;

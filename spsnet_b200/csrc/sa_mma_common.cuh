@@ -164,7 +164,11 @@ static __device__ __noinline__ void pool_chunk_any(uint32_t taddr, PoolOut &o, i
 // ---- optional role profiling: cycles spent per wait / work category, summed over CTAs ------------------------
 enum { PF_MMA_TOTAL = 0, PF_MMA_ACC_EMPTY, PF_MMA_W_FULL, PF_MMA_XR, PF_PROD_W_EMPTY, PF_PROD_HID, PF_EPI_TOTAL, PF_EPI_GATHER,
        PF_EPI_WAIT_HID, PF_EPI_WORK_HID, PF_EPI_WAIT_POOL, PF_EPI_WORK_POOL, PF_MMA_ISSUE, PF_MMA_COMMIT, PF_COUNT };
-struct Prof {
+// Phase counters.  ON = false compiles to nothing: the MMA-issue and epilogue loops are issue-bound, and even predicated-off
+// clock reads and adds cost their slots (the same lesson as in fps.cu: -23 % there).  The kernels are instantiated both ways
+// and the counting variant is launched only while spsk_sa_mma_set_profile() has a buffer installed.
+template <bool ON>
+struct ProfT {
     unsigned long long acc[PF_COUNT];
     bool on;
     __device__ __forceinline__ void init(bool enable) {
@@ -180,6 +184,14 @@ struct Prof {
             if (acc[i]) atomicAdd(dst + i, acc[i]);
     }
 };
+template <>
+struct ProfT<false> {
+    __device__ __forceinline__ void init(bool) {}
+    __device__ __forceinline__ long long now() const { return 0ll; }
+    __device__ __forceinline__ void add(int, long long) {}
+    __device__ __forceinline__ void flush(unsigned long long *) const {}
+};
+using Prof = ProfT<true>;
 
 
 }  // namespace spsk
