@@ -575,8 +575,8 @@ def load_reference_backbone(state_dict):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cpu"])
     ap.add_argument("--depth", type=int, default=8, help="pipeline slots (streams) of BackbonePipeline: batches in flight; hides the\n                    latency-bound FPS (16 of 148 SMs for 3.6 ms per batch) behind the GEMM-heavy kernels of other batches")
     ap.add_argument("--no-graph", action="store_true")
