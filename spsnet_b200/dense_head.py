@@ -33,7 +33,7 @@ from . import pointnet2_utils as pu
 from ._lib import DetectDesc, check, lib
 from .backbone import Cfg
 
-__all__ = ["PointResidual_BinOri_Coder", "IASSD_Head", "MLT_SSD_Head", "detections_padded", "Detections", "class_agnostic_nms", "post_processing",
+__all__ = ["PointResidual_BinOri_Coder", "IASSD_Head", "MLT_SSD_Head", "detections_padded", "Detections", "class_agnostic_nms", "multi_classes_nms", "post_processing",
            "kitti_iassd_head_cfg", "waymo_iassd_head_cfg", "waymo_post_processing", "KITTI_POST_PROCESSING"]
 
 
@@ -443,6 +443,27 @@ def class_agnostic_nms(box_scores, box_preds, nms_config, score_thresh=None):
     return selected, src_box_scores[selected]
 
 
+def multi_classes_nms(cls_scores, box_preds, nms_config, score_thresh=None):
+    """reference model_nms_utils.py:30-66: NMS per class on the device kernels (one count read per class).
+    cls_scores (N, num_class), box_preds (N, 7 + C) -> (pred_scores, pred_labels, pred_boxes), classes concatenated."""
+    nms_fn = getattr(iou3d_nms_utils, nms_config.NMS_TYPE)
+    out_scores, out_labels, out_boxes = [], [], []
+    for k in range(cls_scores.shape[1]):
+        scores_k, boxes_k = cls_scores[:, k], box_preds
+        if score_thresh is not None:
+            keep_mask = scores_k >= score_thresh
+            scores_k, boxes_k = scores_k[keep_mask], box_preds[keep_mask]
+        picked = scores_k.new_zeros((0,), dtype=torch.long)
+        if scores_k.shape[0] > 0:
+            top_scores, top_idx = torch.topk(scores_k, k=min(nms_config.NMS_PRE_MAXSIZE, scores_k.shape[0]))
+            keep_idx, _ = nms_fn(boxes_k[top_idx][:, 0:7].contiguous(), top_scores, nms_config.NMS_THRESH, **nms_config)
+            picked = top_idx[keep_idx[:nms_config.NMS_POST_MAXSIZE]]
+        out_scores.append(scores_k[picked])
+        out_labels.append(torch.full((picked.shape[0],), k, dtype=torch.long, device=cls_scores.device))
+        out_boxes.append(boxes_k[picked])
+    return torch.cat(out_scores, dim=0), torch.cat(out_labels, dim=0), torch.cat(out_boxes, dim=0)
+
+
 def detections_padded(batch_dict, post_process_cfg) -> Detections:
     """Sync-free post-processing of a whole batch (class-agnostic NMS): reuses what IASSD_Head.forward already computed
     for the same configuration, else runs the fused kernels on batch_cls_preds / batch_box_preds."""
@@ -472,7 +493,17 @@ def post_processing(batch_dict, post_process_cfg, num_class: Optional[int] = Non
     bookkeeping needs ground truth and is evaluation code (out of scope): recall_dict is returned empty."""
     cfg = post_process_cfg if isinstance(post_process_cfg, Cfg) else Cfg(post_process_cfg)
     if cfg.NMS_CONFIG.get("MULTI_CLASSES_NMS", False):
-        raise NotImplementedError("MULTI_CLASSES_NMS post-processing is not provided (IA-SSD / SPSNet-IA configs use class-agnostic NMS)")
+        # reference detector3d_template.py:232-257 (single head): per scene, per class NMS; labels are 1-based
+        B = int(batch_dict["batch_size"])
+        cls = batch_dict["batch_cls_preds"].reshape(B, -1, batch_dict["batch_cls_preds"].shape[-1])
+        boxes = batch_dict["batch_box_preds"].reshape(B, cls.shape[1], -1)
+        if not batch_dict.get("cls_preds_normalized", False):
+            cls = torch.sigmoid(cls)
+        pred_dicts = []
+        for b in range(B):
+            sc, lab, bx = multi_classes_nms(cls[b], boxes[b], cfg.NMS_CONFIG, cfg.get("SCORE_THRESH", None))
+            pred_dicts.append({"pred_boxes": bx, "pred_scores": sc, "pred_labels": lab + 1})
+        return pred_dicts, {}
     det = detections_padded(batch_dict, cfg)
     counts = det.count.tolist()  # the one host read of the batch
     raw = None

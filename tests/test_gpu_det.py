@@ -292,3 +292,22 @@ def test_backbone_to_detections_end_to_end(oracle):
         assert d["pred_boxes"].shape[1] == 7 and d["pred_scores"].shape[0] == d["pred_boxes"].shape[0]
         assert (d["pred_scores"] >= 0.1).all() and ((d["pred_labels"] >= 1) & (d["pred_labels"] <= 3)).all()
         assert (d["pred_scores"][:-1] >= d["pred_scores"][1:]).all()
+
+
+def test_multi_classes_nms_dropin(ref_det):
+    """MULTI_CLASSES_NMS branch (not used by the IA-SSD / SPSNet configs): per-class device NMS == the reference function."""
+    from spsnet_b200 import dense_head as H
+
+    torch.manual_seed(3)
+    boxes = _boxes(21, 400)
+    scores = torch.rand(400, 3, device="cuda")
+    cfg = H.Cfg({**H.KITTI_POST_PROCESSING["NMS_CONFIG"], "NMS_THRESH": 0.1, "NMS_POST_MAXSIZE": 50})
+    sc, lab, bx = H.multi_classes_nms(scores, boxes, cfg, score_thresh=0.2)
+    assert sc.shape[0] == lab.shape[0] == bx.shape[0] and (sc >= 0.2).all() and set(lab.tolist()) <= {0, 1, 2}
+    if ref_det is not None:
+        rsc, rlab, rbx = ref_det.nms_utils.multi_classes_nms(scores, boxes, cfg, score_thresh=0.2)
+        assert torch.equal(sc, rsc) and torch.equal(lab, rlab) and torch.equal(bx, rbx)
+    pp = {**H.KITTI_POST_PROCESSING, "NMS_CONFIG": {**H.KITTI_POST_PROCESSING["NMS_CONFIG"], "MULTI_CLASSES_NMS": True, "NMS_THRESH": 0.1}}
+    logits = torch.randn(2 * 200, 3, device="cuda")
+    pd, _ = H.post_processing({"batch_size": 2, "batch_cls_preds": logits, "batch_box_preds": boxes, "cls_preds_normalized": False}, pp)
+    assert len(pd) == 2 and all(((d["pred_labels"] >= 1) & (d["pred_labels"] <= 3)).all() for d in pd)
