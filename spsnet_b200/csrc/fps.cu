@@ -152,15 +152,42 @@ fps_kernel_1024(int n, int m, const float *__restrict__ src, float *__restrict__
 // minima / original indices in registers, orig->sorted position map (u16) in shared memory.
 // CL = true: a thread-block CLUSTER per scene (n > 16384, e.g. Waymo's 65536 points): CTA r of the cluster owns the
 // contiguous index range [r*chunk, (r+1)*chunk), prunes and updates it exactly like the single-CTA kernel, and the
-// per-iteration arg-max is completed across the cluster through distributed shared memory: every warp stores its
-// (value, ~rank, x, y, z) record into the record table of EVERY CTA of the cluster (st.shared::cluster), one
-// barrier.cluster arrive/wait per iteration, then each warp reduces the csize*16 records locally.  The winner's
-// coordinates travel with the record, so no CTA ever reads another CTA's points.
+// per-iteration arg-max is completed across the cluster through distributed shared memory: each CTA reduces its 16 warp
+// summaries locally, warp 0 sends ONE (value, ~rank, x, y, z) record to every CTA of the cluster with st.async -- the
+// store itself completes transaction bytes on the receiver's mbarrier, so there is no cluster barrier and no fence on the
+// chain -- and every warp picks the winner among the csize records.  The winner's coordinates travel with the record, so
+// no CTA ever reads another CTA's points.
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// st.async: the store itself completes `16` transaction bytes on the consumer CTA's mbarrier -- data and signal in one
+// message, no fence and no cluster barrier on the per-iteration chain (measured: barrier.cluster arrive.release +
+// wait.acquire costs 518 cycles at 4 x 512 threads and compiles to MEMBAR.ALL.GPU + CCTL.IVALL around it).
+__device__ __forceinline__ void st_async_v4(const void *local_rec, const void *local_bar, uint32_t cta, uint4 v) {
+    const uint32_t la = (uint32_t)__cvta_generic_to_shared(local_rec), lb = (uint32_t)__cvta_generic_to_shared(local_bar);
+    uint32_t ra, rb;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(cta));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(lb), "r"(cta));
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(ra), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rb) : "memory");
+}
+__device__ __forceinline__ void xbar_init(uint64_t *bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void xbar_arm(uint64_t *bar, uint32_t bytes) {   // the one local arrival + the bytes this phase will receive
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void xbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t done = 0;
+#pragma unroll 1
+    while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    }
 }
 __device__ __forceinline__ void st_cluster_v4(const void *local_ptr, uint32_t cta, uint4 v) {
     const uint32_t la = (uint32_t)__cvta_generic_to_shared(local_ptr);
@@ -305,8 +332,20 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
     // when the maximum is not unique.
     __shared__ uint2 slots2[2][32];           // single CTA: one (value, ~rank) slot per warp; entries >= W stay zero so the
                                               // read-back needs no lane guard (a divergent load costs a BSSY/BSYNC pair)
-    __shared__ uint4 crec[CL ? 2 : 1][CL ? 16 * W : 1][2];   // cluster: [parity][cta * W + warp] = {value, ~rank, x, y | z, -, -, -}
+    __shared__ uint4 crec[CL ? 2 : 1][CL ? 16 : 1][2];   // cluster: [parity][cta] = {value, ~rank, x, y | z, -, -, -}, one record per CTA
+    __shared__ uint4 cslot[CL ? 2 : 1][CL ? 32 : 1];       // cluster: per-warp {value, ~rank, sorted position, -}; entries >= W stay zero
+    __shared__ uint64_t xbar[2];                         // cluster: transaction barriers of the two record tables
     if (tid < 64) slots2[tid >> 5][tid & 31] = make_uint2(0u, 0u);
+    if (CL) {
+        if (tid < 64) cslot[tid >> 5][tid & 31] = make_uint4(0u, 0u, 0u, 0u);
+        if (tid == 0) {
+            xbar_init(&xbar[0]);
+            xbar_init(&xbar[1]);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            xbar_arm(&xbar[0], csize * 32u);   // each phase receives one 32-byte record from every CTA of the cluster
+            xbar_arm(&xbar[1], csize * 32u);
+        }
+    }
     __syncthreads();
     uint32_t bpos = 0u;   // lane p: sorted position of sub-bucket p's best point
     // The picks are written 32 at a time: lane (j & 31) of warp 0 keeps pick j in a register and the warp stores one
@@ -420,31 +459,39 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
             }
             if (PROF && pf) { const long long t1 = clock64(); pc[4] += t1 - t0; t0 = t1; }
         } else {
-            // this warp's record -> the record table of every CTA of the cluster
-            const uint32_t rv = wm, rr = wr, rp = wpos;
-            const float rx = sx[rp], ry = sy[rp], rz = sz[rp];
+            // 1. CTA-local arg-max over the W warp slots (same as the single-CTA kernel, the winner's sorted position rides along)
+            uint4 *cs_ = cslot[j & 1];
+            if (lane == 0) cs_[warp] = make_uint4(wm, wr, wpos, 0u);
+            __syncthreads();
+            const uint4 sv = cs_[lane];
+            const uint32_t cm = __reduce_max_sync(0xFFFFFFFFu, sv.x);
+            const uint32_t cr = __reduce_max_sync(0xFFFFFFFFu, (sv.x == cm) ? sv.y : 0u);
             uint4(*tab)[2] = crec[j & 1];
-            if (lane < csize) {
-                uint4 *dst = tab[crank * W + warp];
-                st_cluster_v4(dst, lane, make_uint4(rv, rr, __float_as_uint(rx), __float_as_uint(ry)));
-                st_cluster_v4(dst + 1, lane, make_uint4(__float_as_uint(rz), 0u, 0u, 0u));
+            uint64_t *xb = &xbar[j & 1];
+            // 2. warp 0 sends this CTA's record {value, ~rank, x, y | z} to every CTA of the cluster; the stores themselves
+            //    complete the transaction bytes the receivers' barriers were armed with (2 x 16 bytes per sender)
+            if (warp == 0) {
+                const int wl = __ffs(__ballot_sync(0xFFFFFFFFu, sv.x == cm && sv.y == cr)) - 1;
+                const uint32_t rp = __shfl_sync(0xFFFFFFFFu, sv.z, wl);
+                if (lane < csize) {
+                    const float rx = sx[rp], ry = sy[rp], rz = sz[rp];
+                    st_async_v4(&tab[crank][0], xb, lane, make_uint4(cm, cr, __float_as_uint(rx), __float_as_uint(ry)));
+                    st_async_v4(&tab[crank][1], xb, lane, make_uint4(__float_as_uint(rz), 0u, 0u, 0u));
+                }
             }
-            cluster_sync_all();
-            // arg-max over the csize * W records (<= 4 per lane)
-            const int nrec = (int)csize * W;
+            // 3. wait for the csize records of this iteration: table (j & 1) is in its ((j - 1) / 2)-th phase
+            xbar_wait(xb, (uint32_t)((j - 1) >> 1) & 1u);
             uint32_t bv = 0u, br = 0u;
-            int bi = -1;
-            for (int i = lane; i < nrec; i += 32) {
-                const uint4 a = tab[i][0];
-                if (bi < 0 || a.x > bv || (a.x == bv && a.y > br)) { bv = a.x; br = a.y; bi = i; }
-            }
-            const uint32_t m2 = __reduce_max_sync(0xFFFFFFFFu, bi >= 0 ? bv : 0u);
-            const uint32_t c2 = (bi >= 0 && bv == m2) ? br : 0u;
-            const uint32_t r2 = __reduce_max_sync(0xFFFFFFFFu, c2);
-            const int bl = __ffs(__ballot_sync(0xFFFFFFFFu, bi >= 0 && bv == m2 && br == r2)) - 1;
-            const int wi = __shfl_sync(0xFFFFFFFFu, bi, bl);
+            if (lane < csize) { const uint4 a0 = tab[lane][0]; bv = a0.x; br = a0.y; }
+            const uint32_t m2 = __reduce_max_sync(0xFFFFFFFFu, bv);
+            const uint32_t r2 = __reduce_max_sync(0xFFFFFFFFu, (lane < csize && bv == m2) ? br : 0u);
+            const int wi = __ffs(__ballot_sync(0xFFFFFFFFu, lane < csize && bv == m2 && br == r2)) - 1;
             const uint4 w0 = tab[wi][0], w1 = tab[wi][1];
             qx = __uint_as_float(w0.z); qy = __uint_as_float(w0.w); qz = __uint_as_float(w1.x);
+            // 4. re-arm this table's barrier for its next phase (iteration j + 2).  Safe to do as soon as this thread has passed
+            //    the wait: no CTA can send iteration j + 2 before it has received OUR record of iteration j + 1, which is sent
+            //    after this point; a slower warp of this CTA still waiting on the old parity sees it as completed.
+            if (tid == 0) xbar_arm(xb, csize * 32u);
             if (crank == 0 && warp == 0) {
                 const uint32_t rank = ~w0.y;
                 if (lane == (j & 31)) keep = (int)((__brev(rank) & s_mask) | ((rank & ((1u << (32u - s_log2)) - 1u)) << s_log2));
