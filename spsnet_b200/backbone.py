@@ -143,6 +143,48 @@ class IASSD_Backbone(nn.Module):
             channel_out_list.append(channel_out)
         self.num_point_features = channel_out
 
+    # ---- FPS prefetch ----------------------------------------------------------------------------------------------
+    # The D-FPS of layer i+1 needs only the CENTRES of layer i, which exist long before layer i's ball query, MLPs and
+    # aggregation have run.  It is a latency chain on 16 of 148 SMs, so it is launched on a side stream at that moment and
+    # joined when layer i+1 starts (also inside CUDA-graph capture: the fork/join becomes graph edges).  Same kernels, same
+    # inputs, same results; SPSK_FPS_PREFETCH=0 disables it.
+    def _prefetchable(self, i: int) -> int:
+        """npoint of layer i+1's D-FPS if it can be started from layer i's centres, else 0."""
+        import os
+
+        if os.environ.get("SPSK_FPS_PREFETCH", "1") == "0" or self.training or torch.is_grad_enabled():
+            return 0
+        k = i + 1
+        if k >= len(self.SA_modules) or self.layer_types[k] != "SA_Layer" or self.layer_inputs[k] != k or self.ctr_idx_list[k] != -1:
+            return 0
+        m = self.SA_modules[k]
+        types, ranges, npoints = list(m.sample_type_list), list(m.sample_range_list), [n for n in m.npoint_list]
+        if len(types) != 1 or ranges[0] != -1 or not ("D-FPS" in types[0] or "DFS" in types[0]) or "S-FPS" in types[0]:
+            return 0
+        if any(t in types[0] for t in ("cls", "ctr", "ss")):   # the dispatch order of _sample_one: score samplers win
+            return 0
+        return int(npoints[0]) if npoints[0] > 0 else 0
+
+    def _prefetch_fps(self, new_xyz: torch.Tensor, npoint: int):
+        if new_xyz.shape[1] <= npoint or not new_xyz.is_cuda:
+            return None
+        main = torch.cuda.current_stream()
+        sides = self.__dict__.setdefault("_side_streams", {})
+        side = sides.get(main.cuda_stream)
+        if side is None:
+            side = sides[main.cuda_stream] = torch.cuda.Stream(device=new_xyz.device)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            idx = pointnet2_utils.furthest_point_sample(new_xyz, npoint)
+            done = torch.cuda.Event()
+            done.record(side)
+        if not torch.cuda.is_current_stream_capturing():
+            new_xyz.record_stream(side)
+            idx.record_stream(main)
+        return idx, done
+
     @staticmethod
     def break_up_pc(pc):
         batch_idx = pc[:, 0]
@@ -168,13 +210,22 @@ class IASSD_Backbone(nn.Module):
         li_cls_pred = None
         centers = centers_origin = ctr_offsets = None
         surface = None  # (B, n_i, 60) point-major surface features of the points kept so far
+        presampled = None
         for i, module in enumerate(self.SA_modules):
             xyz_input = encoder_xyz[self.layer_inputs[i]]
             feature_input = encoder_features[self.layer_inputs[i]]
             if self.layer_types[i] == "SA_Layer":
                 ctr_xyz = encoder_xyz[self.ctr_idx_list[i]] if self.ctr_idx_list[i] != -1 else None
                 kw = {"stds": stds} if self._pass_stds else {}
+                if presampled is not None:
+                    kw["_presampled"], presampled = presampled, None
+                nxt = self._prefetchable(i)
+                if nxt:
+                    box = []
+                    kw["_after_new_xyz"] = lambda c, n=nxt, b=box: b.append(self._prefetch_fps(c, n))
                 li_xyz, li_features, li_cls_pred, sampled_idx, stds_out = module(xyz_input, feature_input, li_cls_pred, ctr_xyz=ctr_xyz, **kw)
+                if nxt and box and box[0] is not None:
+                    presampled = box[0]
                 if self._pass_stds:
                     stds = stds_out
                 if self._use_surface and i <= 4:

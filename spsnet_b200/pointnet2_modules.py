@@ -576,13 +576,25 @@ class PointnetSAModuleMSG_WithSampling(_PointnetSAModuleBase):
         sampled_idx_list: object = []
         if ctr_xyz is None:
             xyz_flipped = None
-            sampled_idx_list, stds = self._sample(xyz, features, cls_features, stds, xyz_flipped)
+            pre = kwargs.get("_presampled")
+            if pre is not None:
+                # D-FPS of this layer was launched on a side stream as soon as the previous layer had its centres
+                # (backbone.IASSD_Backbone._prefetch_fps): join that stream, then proceed as if sampled here
+                torch.cuda.current_stream().wait_event(pre[1])
+                sampled_idx_list = pre[0]
+                if stds is not None:
+                    stds = _gather_stds(stds, sampled_idx_list)
+            else:
+                sampled_idx_list, stds = self._sample(xyz, features, cls_features, stds, xyz_flipped)
             if fused:
                 new_xyz = pu.gather_rows(xyz.contiguous(), sampled_idx_list)
             else:
                 new_xyz = pu.gather_operation(xyz.transpose(1, 2).contiguous(), sampled_idx_list).transpose(1, 2).contiguous()
         else:
             new_xyz = ctr_xyz
+        hook = kwargs.get("_after_new_xyz")
+        if hook is not None:
+            hook(new_xyz)
 
         if len(self.groupers) > 0:
             B_, M_ = new_xyz.shape[0], new_xyz.shape[1]
