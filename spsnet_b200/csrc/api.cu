@@ -25,5 +25,5 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 extern "C" unsigned long long spsk_launch_count(void) { return spsk::g_launches.load(std::memory_order_relaxed); }
 extern "C" const char *spsk_last_error(void) { return spsk::g_err; }
-extern "C" int spsk_abi_version(void) { return 1; }
+extern "C" int spsk_abi_version(void) { return 2; }  // 2: sections 3 (iou3d / NMS / detect), 4 (edge conv) and spsk_scatter_grad added
 extern "C" int spsk_built_for_sm(void) { return 100; }
