@@ -633,7 +633,7 @@ def main():
         e2e = world * BATCH * args.steps / (ms_e2e / 1e3)
         line.update(impl="reference", value=value, ms_per_step=ms / args.steps, clocks=clocks, gpu_launches=None,
                     e2e={"value": e2e, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes(), "d2h_bytes_per_step": pipe.d2h_bytes()},
-                    cpu_baseline={"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                    cpu_baseline={"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
                                   "sample": "not a CPU run: the reference's own CUDA ops (pointnet2_batch rebuilt for sm_100a) + its "
                                             "pointnet2_modules.py / IASSD_backbone.py on the same B200, cudnn.allow_tf32=True (stock); "
                                             "use --impl reference-cpu for the CPU oracle port"})
