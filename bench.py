@@ -273,6 +273,9 @@ def profile_kernels(net, dev_points, steps: int):
     for n in names:
         originals[n] = getattr(_lib.lib, n)
         setattr(_lib.lib, n, wrap(n, originals[n]))
+    # per-kernel durations must not include a concurrent kernel: keep the layer-1 FPS prefetch (side stream) off in this pass
+    prev_prefetch = os.environ.get("SPSK_FPS_PREFETCH")
+    os.environ["SPSK_FPS_PREFETCH"] = "0"
     try:
         with torch.no_grad():
             for i in range(steps):
@@ -283,6 +286,10 @@ def profile_kernels(net, dev_points, steps: int):
     finally:
         for n in names:
             setattr(_lib.lib, n, originals[n])
+        if prev_prefetch is None:
+            os.environ.pop("SPSK_FPS_PREFETCH", None)
+        else:
+            os.environ["SPSK_FPS_PREFETCH"] = prev_prefetch
     table = {}
     for name, a, e0, e1 in records:
         key = name

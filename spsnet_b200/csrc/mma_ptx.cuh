@@ -147,6 +147,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// relu(a), relu(b) -> packed fp16x2 in ONE conversion (cvt.rn.relu): saves the two FMNMX of fmaxf(x, 0) per pair in the
+// hidden-layer epilogue.  First source operand = upper half.
+__device__ __forceinline__ uint32_t pack_h2_relu(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&h);

@@ -67,8 +67,8 @@ __device__ __forceinline__ void store_hidden16(const float *v, const float *bias
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const float4 bb = __ldg(b4 + i);
-        h[2 * i] = pack_h2(fmaxf(v[4 * i] + bb.x, 0.f), fmaxf(v[4 * i + 1] + bb.y, 0.f));
-        h[2 * i + 1] = pack_h2(fmaxf(v[4 * i + 2] + bb.z, 0.f), fmaxf(v[4 * i + 3] + bb.w, 0.f));
+        h[2 * i] = pack_h2_relu(v[4 * i] + bb.x, v[4 * i + 1] + bb.y);
+        h[2 * i + 1] = pack_h2_relu(v[4 * i + 2] + bb.z, v[4 * i + 3] + bb.w);
     }
     *reinterpret_cast<uint4 *>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4 *>(dst + 128) = make_uint4(h[4], h[5], h[6], h[7]);
