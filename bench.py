@@ -585,7 +585,7 @@ def main():
     ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cpu"])
-    ap.add_argument("--depth", type=int, default=8, help="pipeline slots (streams) of BackbonePipeline: batches in flight; hides the\n                    latency-bound FPS (16 of 148 SMs for 3.6 ms per batch) behind the GEMM-heavy kernels of other batches")
+    ap.add_argument("--depth", type=int, default=8, help="pipeline slots (streams) of BackbonePipeline: batches in flight; hides the\n                    latency-bound FPS (16 of 148 SMs for 2.5 ms per batch) behind the GEMM-heavy kernels of other batches")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--pool", type=int, default=0, help="distinct input batches (0 = enough to exceed L2)")
     ap.add_argument("--cpu-sample", type=int, default=64, help="scenes in the cpu_baseline sample (0 = skip): 64 scenes = 10-15 s of host work")
