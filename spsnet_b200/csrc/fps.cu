@@ -259,7 +259,9 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
             const uint32_t cz = min(15, max(0, (int)((z - org[2]) * scl[2])));
             cx = (cx | (cx << 4)) & 0x0F0Fu; cx = (cx | (cx << 2)) & 0x3333u; cx = (cx | (cx << 1)) & 0x5555u;
             cy = (cy | (cy << 4)) & 0x0F0Fu; cy = (cy | (cy << 2)) & 0x3333u; cy = (cy | (cy << 1)) & 0x5555u;
-            const uint32_t code = (((cx | (cy << 1)) & 0x3FFFu) << 4) | cz;
+            // the top cell's last z slice is merged into its neighbour so that no real key equals the padding key
+            // 0xFFFFFFFF (code 0x3FFFF with local index 16383 would); cells only decide how much is pruned, never the result
+            const uint32_t code = min((((cx | (cy << 1)) & 0x3FFFu) << 4) | cz, 0x3FFFEu);
             key = (code << 14) | (uint32_t)i;
         }
         keys[i] = key;

@@ -31,7 +31,10 @@ score_topk_kernel(int n, int n_pad, int num_class, int npoint, const float *__re
         unsigned long long key = 0ull;
         if (i < n) {
             float mx = __ldg(cb + (size_t)i * num_class);
-            for (int c = 1; c < num_class; ++c) mx = fmaxf(mx, __ldg(cb + (size_t)i * num_class + c));
+            for (int c = 1; c < num_class; ++c) {   // torch.max propagates NaN (fmaxf would drop it); a NaN score sorts first, as in torch.topk
+                const float v = __ldg(cb + (size_t)i * num_class + c);
+                mx = (v != v || v > mx) ? v : mx;
+            }
             float score = sigmoid_like_torch(mx);
             if (sb) {
                 const float t = __fsub_rn(__fmul_rn(__ldg(sb + i), 0.125f), 3.0f);

@@ -25,6 +25,7 @@ __all__ = [
     "score_topk", "gather_rows", "ball_query_msg",
 ]
 
+FPS_DISTMAT_ONCHIP_MAX_N = 16384  # distance-matrix mode (F-FPS) and the forced dense kernels keep 16 minima per thread on chip, no clusters
 FPS_ONCHIP_MAX_N = 131072  # <= 16384: one CTA per scene; <= 131072: one 2/4/8-CTA cluster per scene; above: a 16-CTA cluster
 # (<= 262144) where the device can schedule one, else the streaming kernel over the `temp` scratch, which is allocated from here on
 
@@ -79,7 +80,8 @@ class FarthestPointSampling(Function):
             raise RuntimeError("xyz must be (B, N, 3)")
         output = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
         temp = None
-        if N > FPS_ONCHIP_MAX_N:
+        dense = os.environ.get("SPSK_FPS", "")[:1] == "d"   # cross-check mode: the unpruned kernels, no clusters
+        if N > (FPS_DISTMAT_ONCHIP_MAX_N if dense else FPS_ONCHIP_MAX_N):
             temp = torch.full((B, N), 1e10, dtype=torch.float32, device=xyz.device)
         with torch.cuda.device(xyz.device):
             check(lib.spsk_farthest_point_sampling(B, N, npoint, xyz.data_ptr(), temp.data_ptr() if temp is not None else None,
@@ -105,7 +107,7 @@ class FurthestPointSamplingWithDist(Function):
             raise RuntimeError("distance matrix must be (B, N, N)")
         output = torch.empty((B, npoint), dtype=torch.int32, device=xyz.device)
         temp = None
-        if N > FPS_ONCHIP_MAX_N:
+        if N > FPS_DISTMAT_ONCHIP_MAX_N:
             temp = torch.full((B, N), 1e10, dtype=torch.float32, device=xyz.device)
         with torch.cuda.device(xyz.device):
             check(lib.spsk_furthest_point_sampling_with_dist(B, N, npoint, xyz.data_ptr(),
@@ -398,7 +400,10 @@ def ball_query_msg(radii, nsamples, xyz: torch.Tensor, new_xyz: torch.Tensor, gr
     r = (C.c_float * S)(*[float(x) for x in radii])
     n = (C.c_int * S)(*[int(x) for x in nsamples])
     ptrs = (C.c_void_p * S)(*[o.data_ptr() for o in outs])
-    use_grid = GRID_MIN_N <= N <= 65536 if grid is None else bool(grid)
+    # the grid kernel keeps 8 per-warp hit bitmaps of S * ceil(N / 32) words in shared memory (ball_query_grid.cu): auto-select it
+    # only while they fit its 200 KB budget, else the brute-force scan (same results)
+    grid_fits = 8 * S * ((N + 31) // 32) * 4 <= 200 * 1024
+    use_grid = (GRID_MIN_N <= N <= 65536 and grid_fits) if grid is None else bool(grid)
     with torch.cuda.device(xyz.device):
         if use_grid:
             nbytes = int(lib.spsk_ball_query_grid_workspace_bytes(B, N))

@@ -365,3 +365,75 @@ def test_deterministic_backward_matches_atomics_and_repeats(oracle, monkeypatch,
         scale = max(1.0, float(np.abs(w).max()))
         assert float((d1.cpu() - torch.from_numpy(w)).abs().max()) <= 2e-5 * scale
         assert float((d1 - a).abs().max()) <= 2e-5 * scale
+
+
+# ---- round-2 regressions -------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n,chunks", [(16384, 1), (65536, 4), (32768, 2)])
+def test_fps_top_corner_point_is_not_padding(oracle, ref_ops, n, chunks):
+    """A CTA that owns exactly 16384 points has no padding slot; the LAST point of every 16384-point chunk sits in the top
+    Morton cell of that chunk (max x, y and z), which used to produce the padding sort key 0xFFFFFFFF and was silently
+    dropped.  Such an extreme corner is one of the first picks."""
+    from spsnet_b200 import pointnet2_utils as pu
+
+    xyz = _xyz(2, n, seed=77, kind="waymo" if n > 16384 else "kitti")
+    per = n // chunks
+    for c in range(chunks):
+        blk = xyz[:, c * per:(c + 1) * per]
+        xyz[:, (c + 1) * per - 1] = blk.max(axis=1) + np.float32(1.0 + c)   # strict maximum of the chunk in all three axes
+    m = 64
+    got = pu.furthest_point_sample(dev(xyz), m).cpu().numpy()
+    want = oracle.fps(xyz, m)
+    np.testing.assert_array_equal(got, want)
+    assert (n - 1) in want[0] and (n - 1) in got[0], "the global corner point must be sampled early"
+    for c in range(chunks):
+        assert ((c + 1) * per - 1) in got[0], f"corner point of chunk {c} was dropped"
+    np.testing.assert_array_equal(ref_ops.utils.furthest_point_sample(dev(xyz), m).cpu().numpy(), want)
+
+
+def test_fps_with_dist_above_16384(oracle, monkeypatch):
+    """F-FPS on a distance matrix with 16384 < N <= 131072 (no cluster variant in that mode): the wrapper must hand the
+    streaming kernel its `temp` scratch instead of raising; same for D-FPS with the dense kernels forced."""
+    from spsnet_b200 import pointnet2_utils as pu
+
+    n, m = 16500, 24
+    f = torch.randn(1, n, 4, generator=torch.Generator().manual_seed(3)).cuda()
+    d = torch.cdist(f, f).pow(2).contiguous()
+    got = pu.furthest_point_sample_with_dist(d, m).cpu().numpy()
+    np.testing.assert_array_equal(got, oracle.fps_with_dist(d.cpu().numpy(), m))
+    del d
+    xyz = _xyz(1, 20000, seed=5, kind="waymo")
+    monkeypatch.setenv("SPSK_FPS", "dense")
+    a = pu.furthest_point_sample(dev(xyz), 100).cpu().numpy()
+    monkeypatch.delenv("SPSK_FPS")
+    np.testing.assert_array_equal(a, oracle.fps(xyz, 100))
+
+
+def test_ball_query_msg_four_scales_large_n_falls_back(oracle):
+    """4 scales x 60000 points: the grid kernel's per-warp bitmaps exceed its shared-memory budget -> the automatic choice
+    must be the brute-force scan (same lists), not SPSK_ERR_UNSUPPORTED."""
+    from spsnet_b200 import pointnet2_utils as pu
+
+    xyz = _xyz(1, 60000, seed=8, kind="waymo")
+    new_xyz = np.ascontiguousarray(xyz[:, ::600])
+    radii, ns = [0.4, 0.8, 1.6, 3.2], [8, 16, 16, 32]
+    outs = pu.ball_query_msg(radii, ns, dev(xyz), dev(new_xyz))
+    for r, s, o in zip(radii, ns, outs):
+        np.testing.assert_array_equal(o.cpu().numpy(), pu.ball_query(r, s, dev(xyz), dev(new_xyz)).cpu().numpy())
+
+
+def test_score_topk_nan_ranks_first_like_torch():
+    """torch.max propagates NaN and torch.topk ranks NaN first; so does the fused kernel."""
+    from spsnet_b200 import pointnet2_utils as pu
+
+    cls = scenes.make_cls_logits(3, 2, 1024)
+    cls[0, 17, 1] = np.nan
+    cls[1, 900, 0] = np.nan
+    cls[1, 5, 2] = np.nan
+    idx = pu.score_topk(dev(cls), 256).cpu().numpy()
+    t = torch.sigmoid(dev(cls).max(dim=-1)[0])
+    ti = torch.topk(t, 256, dim=-1)[1].cpu().numpy()
+    assert idx[0, 0] == 17 and set(idx[1, :2]) == {5, 900}
+    assert set(ti[0, :1]) == {17} and set(ti[1, :2]) == {5, 900}
+    np.testing.assert_array_equal(idx[0, 1:], ti[0, 1:])
+    np.testing.assert_array_equal(idx[1, 2:], ti[1, 2:])
