@@ -31,7 +31,7 @@ import torch.nn as nn
 from . import iou3d_nms_utils
 from . import pointnet2_utils as pu
 from ._lib import DetectDesc, check, lib
-from .backbone import Cfg
+from .configs import Cfg
 
 __all__ = ["PointResidual_BinOri_Coder", "IASSD_Head", "MLT_SSD_Head", "detections_padded", "Detections", "class_agnostic_nms", "multi_classes_nms", "post_processing",
            "kitti_iassd_head_cfg", "waymo_iassd_head_cfg", "waymo_post_processing", "KITTI_POST_PROCESSING"]
@@ -45,49 +45,8 @@ def _ceil(a: int, b: int) -> int:
     return (a + b - 1) // b * b
 
 
-# reference: tools/cfgs/kitti_models/IA-SSD.yaml:59-84,108-121
-KITTI_IASSD_HEAD = {
-    "NAME": "IASSD_Head",
-    "CLS_FC": [256, 256],
-    "REG_FC": [256, 256],
-    "CLASS_AGNOSTIC": False,
-    "TARGET_CONFIG": {
-        "BOX_CODER": "PointResidual_BinOri_Coder",
-        "BOX_CODER_CONFIG": {"angle_bin_num": 12, "use_mean_size": True,
-                             "mean_size": [[3.9, 1.6, 1.56], [0.8, 0.6, 1.73], [1.76, 0.6, 1.73]]},
-    },
-}
-KITTI_POST_PROCESSING = {
-    "RECALL_THRESH_LIST": [0.3, 0.5, 0.7],
-    "SCORE_THRESH": 0.1,
-    "OUTPUT_RAW_SCORE": False,
-    "NMS_CONFIG": {"MULTI_CLASSES_NMS": False, "NMS_TYPE": "nms_gpu", "NMS_THRESH": 0.01, "NMS_PRE_MAXSIZE": 4096,
-                   "NMS_POST_MAXSIZE": 500},
-}
-
-
-def waymo_iassd_head_cfg() -> Cfg:
-    """reference tools/cfgs/waymo_models/IA-SSD.yaml:69-93: same stacks, Waymo mean sizes."""
-    import copy
-
-    c = copy.deepcopy(KITTI_IASSD_HEAD)
-    c["TARGET_CONFIG"]["BOX_CODER_CONFIG"]["mean_size"] = [[4.7, 2.1, 1.7], [0.91, 0.86, 1.73], [1.78, 0.84, 1.78]]
-    return Cfg(c)
-
-
-def waymo_post_processing() -> dict:
-    """reference tools/cfgs/waymo_models/IA-SSD.yaml:118-130 (NMS_THRESH 0.1)."""
-    import copy
-
-    c = copy.deepcopy(KITTI_POST_PROCESSING)
-    c["NMS_CONFIG"]["NMS_THRESH"] = 0.1
-    return c
-
-
-def kitti_iassd_head_cfg() -> Cfg:
-    import copy
-
-    return Cfg(copy.deepcopy(KITTI_IASSD_HEAD))
+from .configs import (KITTI_IASSD_HEAD, KITTI_POST_PROCESSING, kitti_iassd_head_cfg, waymo_iassd_head_cfg,  # noqa: F401,E402  (re-exported)
+                      waymo_post_processing)
 
 
 class Detections(NamedTuple):

@@ -168,3 +168,57 @@ def test_stability_generator_state_dict_layout():
     assert gen.feature_encoder.fc2.weight.shape == (8, 64) and gen.obj_encoder.fc1.weight.shape == (64, 72)
     with __import__("pytest").raises(NotImplementedError):
         gen.train()({"batch_size": 1, "points": None})
+
+
+def test_torch_library_ops_registered_with_fake_impls():
+    """every op of the thin custom-op layer is visible to the dispatcher (torch.ops.spsk.*), infers its
+    output shapes/dtypes on meta tensors (what torch.compile / FakeTensor tracing use) and refuses CPU tensors loudly."""
+    import pytest
+    import torch
+
+    import spsnet_b200.torch_ops as T
+
+    for name in T.OPS:
+        assert hasattr(torch.ops.spsk, name), name
+    xyz = torch.empty(2, 100, 3, device="meta")
+    ctr = torch.empty(2, 10, 3, device="meta")
+    f = torch.empty(2, 8, 100, device="meta")
+    i2 = torch.empty(2, 10, dtype=torch.int32, device="meta")
+    i3 = torch.empty(2, 10, 16, dtype=torch.int32, device="meta")
+    o = torch.ops.spsk.furthest_point_sample(xyz, 10)
+    assert o.shape == (2, 10) and o.dtype == torch.int32
+    assert torch.ops.spsk.gather_points(f, i2).shape == (2, 8, 10)
+    assert torch.ops.spsk.gather_rows(xyz, i2).shape == (2, 10, 3)
+    assert torch.ops.spsk.group_points(f, i3).shape == (2, 8, 10, 16)
+    assert torch.ops.spsk.ball_query(0.5, 16, xyz, ctr).shape == (2, 10, 16)
+    assert torch.ops.spsk.ball_query_dilated(0.5, 0.1, 16, xyz, ctr).shape == (2, 10, 16)
+    d, i = torch.ops.spsk.three_nn(ctr, xyz)
+    assert d.shape == (2, 10, 3) and i.dtype == torch.int32
+    assert torch.ops.spsk.three_interpolate(f, torch.empty(2, 10, 3, dtype=torch.int32, device="meta"), d).shape == (2, 8, 10)
+    assert torch.ops.spsk.score_topk(torch.empty(2, 100, 3, device="meta"), 5).shape == (2, 5)
+    with pytest.raises(RuntimeError):
+        torch.ops.spsk.furthest_point_sample(torch.zeros(2, 100, 3), 10)   # no CPU fallback
+
+
+def test_shims_export_the_reference_pybind_names():
+    """spsnet_b200/shims: exactly the names of pointnet2_api.cpp:10-26 and the GPU names of iou3d_nms_api.cpp:12-15."""
+    from spsnet_b200.shims import iou3d_nms_cuda, pointnet2_batch_cuda
+
+    want = {"ball_query_wrapper", "ball_query_dilated_wrapper", "group_points_wrapper", "group_points_grad_wrapper", "gather_points_wrapper",
+            "gather_points_grad_wrapper", "farthest_point_sampling_wrapper", "furthest_point_sampling_with_dist_wrapper", "three_nn_wrapper",
+            "three_interpolate_wrapper", "three_interpolate_grad_wrapper"}
+    assert {n for n in dir(pointnet2_batch_cuda) if n.endswith("_wrapper")} == want
+    for n in ("boxes_overlap_bev_gpu", "boxes_iou_bev_gpu", "nms_gpu", "nms_normal_gpu"):
+        assert callable(getattr(iou3d_nms_cuda, n))
+
+
+def test_configs_module_does_not_load_the_library():
+    """bench.py's reference arm imports spsnet_b200.configs / scenes only: neither may dlopen libspsk.so."""
+    import subprocess
+    import sys as _sys
+
+    code = ("import sys; sys.path.insert(0, %r); import spsnet_b200.configs, spsnet_b200.scenes; "
+            "assert 'spsnet_b200._lib' not in sys.modules; "
+            "assert not any('libspsk' in l for l in open('/proc/self/maps')); print('clean')" % str(ROOT))
+    r = subprocess.run([_sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 0 and "clean" in r.stdout, r.stderr
