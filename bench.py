@@ -1,25 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- IA-SSD set-abstraction backbone throughput (BASELINE.json metric) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-cpu]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-cpu] [--workload kitti|spsnet|waymo|...]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-        --master-port P bench.py --gpus N --steps K --warmup W
+        --master-port P bench.py --gpus N --steps K --warmup W [--scaling strong]
 
 A step = one forward of the full KITTI IA-SSD SA stack (BASELINE.json configs[1]: D-FPS 16384->4096->1024,
 ctr-aware top-k ->512->256, vote layer, MSG ball query + shared MLP) over one batch of 16 synthetic
 16384-point scenes, eval mode.  Scenes are independent: with N > 1 every rank runs its own batches
-(weak scaling, no data-path collective); NCCL carries only the timing reduction.
+(weak scaling, no data-path collective); NCCL carries only the timing reduction.  `--scaling strong` instead cuts ONE
+host batch of 128 scenes per step into contiguous per-rank shards (spsnet_b200.sharding.shard_range).
 
 Prints ONE JSON line (rank 0).  `value` = whole-job scenes/s with inputs resident in HBM (a pool of
 distinct batches larger than L2 is cycled); `e2e` = the same metric through `BackbonePipeline.submit_host`
-(pinned host input -> H2D -> forward -> D2H of the centre features, every step); `roofline` describes the
-dominant kernel of the step (CUDA-event timed in an instrumented eager pass of the same run);
-`cpu_baseline` = the CPU oracle port (oracle/) timed on a bounded sample on the host cores.
+(pinned host input -> H2D -> forward -> D2H of the centre features, every step); `depth1` = the same with ONE batch in
+flight (latency view); `roofline` describes the dominant kernel of the step (CUDA-event timed in an instrumented eager pass
+of the same run); `cpu_baseline` = the CPU oracle port (oracle/) timed on a bounded sample on the host cores;
+`verified` = verdict of the parity gate: before anything is timed, a helper process (`bench.py --verify-only`) runs one
+full-size batch through this arm (eager and graph replay) and through the unmodified reference (oracle/_ref, TF32 off) with
+the bars of tests/test_gpu_timed_path.py -- D-FPS layers bit-exact, every layer teacher-forced, features / logits <= 1e-3.
 
---impl reference runs the UNMODIFIED reference (its pointnet2_batch CUDA ops rebuilt for sm_100a +
-its own pointnet2_modules.py + IASSD_backbone.py, installed by oracle/build_ref.sh into oracle/_ref) on the
-same GPU, same weights, same inputs; when that module is unavailable it falls back to the CPU oracle port
-(--impl reference-cpu forces the CPU port).
+--impl reference runs the UNMODIFIED reference (its pointnet2_batch CUDA ops rebuilt for sm_100a + its own
+pointnet2_modules.py + IASSD_backbone.py, installed by oracle/build_ref.sh into oracle/_ref) on the same GPU, the same
+seeded weights, the same inputs; that process imports spsnet_b200.configs / scenes only and maps none of this repo's
+kernels (`native_so_loaded` lists what it did map).  When oracle/_ref is unavailable it falls back to the CPU oracle
+port (--impl reference-cpu forces the CPU port).
 """
 from __future__ import annotations
 
@@ -39,6 +44,11 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 METRIC = "IA-SSD SA-backbone scenes/s (16k pts)"
+# what the path computes in (a label, not a precision claim): shared-MLP chains of layers 1/2/5 multiply fp32 values rounded to
+# fp16 (11-bit significand, like the TF32 the reference's cuDNN convolutions use) and accumulate in fp32; narrow chains (K <= 64)
+# and every Conv1d GEMM carry hi + lo fp16 halves (fp32-grade); sampling / ball query / top-k are exact fp32 + int32
+DTYPE = "fp16 operands / fp32 accumulate (split-fp16 hi+lo for K <= 64 chains and all Conv1d GEMMs); fp32 + int32 sampling"
+DTYPE_REF = "fp32 storage, cuDNN TF32 convolutions (stock cudnn.allow_tf32=True), fp32 + int32 sampling"
 UNIT = "scenes/s"
 BATCH = 16
 NPTS = 16384
@@ -381,8 +391,9 @@ def _roof_entry(key, t, peaks, traffic):
     e["frac"] = (e["achieved"] / e["peak"]) if e.get("achieved") else None
     e["sms_used"] = sms
     e["sm_time_ms_per_step"] = None
-    tr = traffic.get(key.split("[")[0]) if traffic else None
-    e["traffic"] = tr
+    # DRAM bytes of THIS kernel instance (one launch) from the committed ncu --set full capture; null when that instance
+    # was not captured (never the number of a sibling instance of the same kernel class)
+    e["traffic"] = traffic.get(key) if traffic else None
     e["peak_source"] = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
     return e
 
@@ -393,7 +404,7 @@ def roofline_from_table(table, steps, peaks):
     latency-bound FPS (16 of 148 SMs) would otherwise hide the kernels that actually fill the GPU."""
     total = sum(t["ms"] for t in table.values())
     traffic = {}
-    tp = ROOT / "profiles" / "traffic.json"
+    tp = ROOT / "profiles" / "traffic_r02.json"   # {kernel key incl. its shape: dram bytes per launch}, scripts/ncu_traffic.py
     if tp.exists():
         try:
             traffic = json.loads(tp.read_text())
@@ -425,13 +436,16 @@ def load_peaks():
 # arms
 # --------------------------------------------------------------------------------------------------
 
-def timed_region(pipe, inputs, steps, warmup, host: bool, world: int):
-    """W warm-up steps, then EXACTLY K steps bracketed by barrier + synchronize; device-side events."""
+def timed_region(pipe, inputs, steps, warmup, host: bool, world: int, per_step: int = 1):
+    """W warm-up steps, then EXACTLY K steps bracketed by barrier + synchronize; device-side events.  A step submits `per_step`
+    batches (1 in weak scaling; this rank's share of the host batch in strong scaling)."""
     import torch.distributed as dist
 
     submit = pipe.submit_host if host else pipe.submit_device
-    for i in range(warmup):
-        submit(inputs[i % len(inputs)])
+    k = 0
+    for _ in range(warmup * per_step):
+        submit(inputs[k % len(inputs)])
+        k += 1
     pipe.sync()
     torch.cuda.synchronize()
     if world > 1:
@@ -442,8 +456,9 @@ def timed_region(pipe, inputs, steps, warmup, host: bool, world: int):
     e0.record(main)
     pipe.fork(main)
     t0 = time.perf_counter()
-    for i in range(steps):
-        submit(inputs[(warmup + i) % len(inputs)])
+    for _ in range(steps * per_step):
+        submit(inputs[k % len(inputs)])
+        k += 1
     pipe.join(main)
     e1.record(main)
     torch.cuda.synchronize()
@@ -453,7 +468,7 @@ def timed_region(pipe, inputs, steps, warmup, host: bool, world: int):
     from spsnet_b200 import sharding
 
     # the only communication of the path: SUM of scenes, MAX of the device-timed milliseconds (spsnet_b200/sharding.py)
-    _, ms = sharding.reduce_report(BATCH * steps, e0.elapsed_time(e1), device="cuda")
+    _, ms = sharding.reduce_report(BATCH * steps * per_step, e0.elapsed_time(e1), device="cuda")
     return ms, wall
 
 
@@ -532,148 +547,295 @@ class RefDetector(torch.nn.Module):
                 "det_count": counts}
 
 
-def load_reference_detector(state_dict):
+# --------------------------------------------------------------------------------------------------
+# the reference arm's model: built from the SEED alone, through spsnet_b200.configs (which does not load libspsk.so)
+# and oracle/_ref only -- no product module is imported, so the arm's process maps none of this repo's kernels.
+# Same torch seed + same constructor order + configs.randomize_bn_stats == the very weights of our arm
+# (tests/test_gpu_timed_path.py::test_same_seed_gives_reference_identical_weights; `bench.py --verify-only` re-checks it).
+# --------------------------------------------------------------------------------------------------
+
+def _ref_import(name):
     import importlib
     import types
     import warnings
 
-    from spsnet_b200 import backbone as bb
-    from spsnet_b200 import dense_head as dh
-
-    backbone = load_reference_backbone({k[len("backbone_3d."):]: v for k, v in state_dict.items() if k.startswith("backbone_3d.")})
-    sys.modules.setdefault("SharedArray", types.ModuleType("SharedArray"))  # absent dependency of pcdet.utils.common_utils, unused here
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        hm = importlib.import_module("pcdet.models.dense_heads.IASSD_head")
-        nu = importlib.import_module("pcdet.models.model_utils.model_nms_utils")
-    import copy
-
-    hcfg = copy.deepcopy(dict(dh.waymo_iassd_head_cfg()) if KIND == "waymo" else dh.KITTI_IASSD_HEAD)
-    hcfg["LOSS_CONFIG"] = {"LOSS_CLS": "WeightedCrossEntropy", "LOSS_REG": "WeightedSmoothL1Loss", "LOSS_INS": "WeightedCrossEntropy",
-                           "CORNER_LOSS_REGULARIZATION": False, "CENTERNESS_REGULARIZATION": False, "IOU3D_REGULARIZATION": False,
-                           "LOSS_WEIGHTS": {"code_weights": [1.0] * 6}}
-    head = hm.IASSD_Head(3, 512, bb.Cfg(hcfg))
-    head.load_state_dict({k[len("point_head."):]: v for k, v in state_dict.items() if k.startswith("point_head.")}, strict=False)
-    return RefDetector(backbone, head.eval(), bb.Cfg(dh.waymo_post_processing() if KIND == "waymo" else dh.KITTI_POST_PROCESSING), nu).eval()
-
-
-def load_reference_backbone(state_dict):
     ref_root = ROOT / "oracle" / "_ref"
     so = ref_root / "pcdet" / "ops" / "pointnet2" / "pointnet2_batch" / "pointnet2_batch_cuda.so"
     if not so.exists():
         raise RuntimeError("oracle/_ref not built (run oracle/build_ref.sh where /root/reference exists)")
-    import importlib
-    import warnings
-
-    sys.path.insert(0, str(ref_root))
-    from spsnet_b200 import backbone as bb
-
-    if _WL["bb"] not in ("IASSD_Backbone", "IASSD_DET", "PAGNet_Backbone"):
-        raise RuntimeError("the reference arm runs the IASSD_Backbone / PAGNet_Backbone workloads (kitti, waymo, kitti_det, spsnet, spsnet_sf)")
-    cls_name = "PAGNet_Backbone" if _WL["bb"] == "PAGNet_Backbone" else "IASSD_Backbone"
+    if str(ref_root) not in sys.path:
+        sys.path.insert(0, str(ref_root))
+    sys.modules.setdefault("SharedArray", types.ModuleType("SharedArray"))  # absent dependency of pcdet.utils.common_utils, unused here
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        mod = importlib.import_module("pcdet.models.backbones_3d." + cls_name.replace("_Backbone", "_backbone"))
-    net = getattr(mod, cls_name)(getattr(bb, _WL["cfg"])(), num_class=3, input_channels=NCOLS - 1)
-    net.load_state_dict(state_dict)
-    return net.eval()
+        return importlib.import_module(name)
 
 
-def main():
+def build_reference_from_seed(seed=0):
+    import copy
+
+    from spsnet_b200 import configs as cf
+
+    if _WL["bb"] not in ("IASSD_Backbone", "IASSD_DET", "PAGNet_Backbone"):
+        raise RuntimeError("the reference arm runs the IASSD_Backbone / PAGNet_Backbone workloads (kitti, waymo, kitti_det, waymo_det, spsnet, spsnet_sf)")
+    cls_name = "PAGNet_Backbone" if _WL["bb"] == "PAGNet_Backbone" else "IASSD_Backbone"
+    mod = _ref_import("pcdet.models.backbones_3d." + cls_name.replace("_Backbone", "_backbone"))
+    torch.manual_seed(seed)
+    backbone = getattr(mod, cls_name)(getattr(cf, _WL["cfg"])(), num_class=3, input_channels=NCOLS - 1)
+    if _WL["bb"] != "IASSD_DET":
+        cf.randomize_bn_stats(backbone, seed=seed)
+        return backbone.eval()
+    hm = _ref_import("pcdet.models.dense_heads.IASSD_head")
+    nu = _ref_import("pcdet.models.model_utils.model_nms_utils")
+    hcfg = copy.deepcopy(dict(cf.waymo_iassd_head_cfg()) if KIND == "waymo" else cf.KITTI_IASSD_HEAD)
+    hcfg["LOSS_CONFIG"] = {"LOSS_CLS": "WeightedCrossEntropy", "LOSS_REG": "WeightedSmoothL1Loss", "LOSS_INS": "WeightedCrossEntropy",
+                           "CORNER_LOSS_REGULARIZATION": False, "CENTERNESS_REGULARIZATION": False, "IOU3D_REGULARIZATION": False,
+                           "LOSS_WEIGHTS": {"code_weights": [1.0] * 6}}
+    head = hm.IASSD_Head(3, 512, cf.Cfg(hcfg))
+    det = RefDetector(backbone, head, cf.Cfg(cf.waymo_post_processing() if KIND == "waymo" else cf.KITTI_POST_PROCESSING), nu)
+    cf.randomize_bn_stats(det, seed=seed)
+    return det.eval()
+
+
+def loaded_repo_libraries():
+    """Which of this repo's shared objects are mapped into this process (the arm's own evidence for `native_so_loaded`)."""
+    out = set()
+    try:
+        for ln in open("/proc/self/maps"):
+            path = ln.rstrip().split(" ")[-1]
+            if path.endswith(".so") and str(ROOT) in path:
+                out.add(os.path.relpath(path, ROOT))
+    except OSError:
+        pass
+    return sorted(out)
+
+
+def pin_rank_to_cores(local: int, world: int):
+    """One block of host cores per rank (8 submit loops + 8 clock samplers otherwise migrate over the same NUMA node)."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // max(world, 1))
+        mine = cores[local * per:(local + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return f"{mine[0]}-{mine[-1]}"
+    except (AttributeError, OSError):
+        return None
+
+
+def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cpu"])
-    ap.add_argument("--depth", type=int, default=8, help="pipeline slots (streams) of BackbonePipeline: batches in flight; hides the\n                    latency-bound FPS (16 of 148 SMs for 2.5 ms per batch) behind the GEMM-heavy kernels of other batches")
+    ap.add_argument("--depth", type=int, default=8, help="pipeline slots (streams) of BackbonePipeline: batches in flight; hides the\n                    latency-bound FPS (16 of 148 SMs per batch) behind the GEMM-heavy kernels of other batches")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--pool", type=int, default=0, help="distinct input batches (0 = enough to exceed L2)")
     ap.add_argument("--cpu-sample", type=int, default=64, help="scenes in the cpu_baseline sample (0 = skip): 64 scenes = 10-15 s of host work")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-depth1", action="store_true", help="skip the extra single-batch-in-flight (latency) measurement")
+    ap.add_argument("--no-verify", action="store_true", help="skip the parity gate (a helper process: this arm vs oracle/_ref on one full-size batch)")
+    ap.add_argument("--verify-only", action="store_true", help="run the parity gate alone and print its JSON verdict")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank runs its own batches of 16 scenes (default, the driver's scaling run); strong: ONE host batch of "
+                         "--total-scenes scenes per step is cut into contiguous shards by spsnet_b200.sharding.shard_range")
+    ap.add_argument("--total-scenes", type=int, default=128, help="strong scaling: scenes in the host batch of one step")
+    ap.add_argument("--no-pin", action="store_true", help="do not pin each rank to its own block of host cores")
+    ap.add_argument("--out16", action="store_true", help="e2e: return centre features as fp16 (halves the D2H bytes; opt-in, default fp32 like the reference)")
+    ap.add_argument("--timeline", action="store_true", help="e2e: CUDA-event timeline of H2D / forward / D2H per step (rank 0), printed in `e2e.timeline`")
     ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS), help="kitti = BASELINE.json configs[1] (headline)")
-    args = ap.parse_args()
+    return ap.parse_args()
+
+
+def strong_plan(args, rank, world):
+    """(first scene of this rank inside the host batch, batches this rank runs per step)."""
+    from spsnet_b200 import sharding
+
+    lo, hi = sharding.shard_range(args.total_scenes, rank, world)
+    if (hi - lo) % BATCH != 0 or hi == lo:
+        raise SystemExit(f"strong scaling: the shard of rank {rank} ({hi - lo} scenes) must be a positive multiple of {BATCH}")
+    return lo, (hi - lo) // BATCH
+
+
+def make_pool_for(args, rank, world):
+    """Pinned host batches this rank cycles through; together larger than L2."""
+    from spsnet_b200 import scenes
+
+    if args.scaling == "weak":
+        n_pool = args.pool or (L2_BYTES // (BATCH * NPTS * NCOLS * 4) + 2)
+        return make_pool(rank, n_pool), 1, n_pool
+    lo, per_step = strong_plan(args, rank, world)
+    n_host = args.pool or max(2, (L2_BYTES // (args.total_scenes // world * NPTS * NCOLS * 4)) + 2)
+    pool = []
+    for i in range(n_host):           # host batch i = scenes [i * total, (i + 1) * total); this rank owns [lo, hi) of each
+        for b in range(per_step):
+            arr = scenes.to_points(scenes.make_batch(i * args.total_scenes + lo + b * BATCH, BATCH, NPTS, KIND))
+            pool.append(torch.from_numpy(arr).pin_memory())
+    return pool, per_step, n_host * per_step
+
+
+def run_verify_only(args):
+    """The parity gate: one full-size batch through this arm (eager AND the graph-replay pipeline) and through the unmodified
+    reference (oracle/_ref, TF32 off), with the bars of tests/test_gpu_timed_path.py.  Prints {"verified": true|false, ...}."""
+    verdict = {"verified": False, "workload": args.workload}
+    try:
+        from oracle import parity
+        from spsnet_b200.runtime import BackbonePipeline
+
+        torch.cuda.set_device(0)
+        net = build_net().cuda()
+        ref = build_reference_from_seed().cuda()
+        mine_bb = net.backbone_3d if hasattr(net, "backbone_3d") else net
+        ref_bb = ref.backbone_3d if hasattr(ref, "backbone_3d") else ref
+        a, b = net.state_dict(), ref.state_dict()
+        same = set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in a)
+        verdict["weights_identical_from_seed"] = bool(same)
+        assert same, "the reference arm's seed-built weights differ from this arm's"
+        from spsnet_b200 import scenes
+
+        pts = torch.from_numpy(scenes.to_points(scenes.make_batch(4242, BATCH, NPTS, KIND))).cuda()
+        extra = extra_inputs("cuda") or {}
+        rep = parity.teacher_forced_check(mine_bb, ref_bb, BATCH, pts, extra=extra)
+        verdict["fps_layers_bit_exact"] = rep["fps_layers_bit_exact"]
+        verdict["sampled_set_overlap"] = rep["sampled_set_overlap"]
+        worst_f = worst_l = 0.0
+        for rec in rep["layers"].values():
+            for k, v in rec.items():
+                if isinstance(v, dict):
+                    if k.endswith("logits"):
+                        worst_l = max(worst_l, v["range_rel"])
+                    else:
+                        worst_f = max(worst_f, v["range_rel"])
+        verdict["max_feature_err_range_rel"] = worst_f
+        verdict["max_logit_err_range_rel"] = worst_l
+        verdict["tolerance"] = parity.REL_TOL
+        if not hasattr(net, "forward_padded"):
+            # the timed API: graph replay on a slot stream == eager forward of the same batch
+            pipe = BackbonePipeline(net, BATCH, NPTS, NCOLS, depth=2, use_graph=True, extra_inputs=extra or None)
+            pipe.prepare(pts)
+            pts2 = torch.from_numpy(scenes.to_points(scenes.make_batch(777, BATCH, NPTS, KIND)))
+            for host in (pts.cpu().pin_memory(), pts2.pin_memory(), pts.cpu().pin_memory()):
+                slot = pipe.submit_host(host)
+                out = {k: v.clone() for k, v in pipe.host_out(slot).items()}
+                with torch.no_grad():
+                    want = net({"batch_size": BATCH, "points": host.cuda(), **extra})
+                for k in out:
+                    assert torch.equal(out[k], want[k].cpu()), f"pipeline output `{k}` differs from the eager forward"
+            verdict["pipeline_equals_eager"] = True
+        verdict["verified"] = True
+        verdict["against"] = "oracle/_ref: unmodified reference backbone + its CUDA ops (sm_100a), TF32 off, teacher-forced per layer"
+    except Exception as e:  # the verdict must always be printed
+        verdict["error"] = f"{type(e).__name__}: {e}"[:500]
+    print("VERIFY " + json.dumps(verdict), flush=True)
+
+
+def verify_in_helper_process(args, local):
+    """Run `bench.py --verify-only` in its own process BEFORE this one touches the GPU's timed state: the reference extension is
+    never mapped into the timed process."""
+    if _WL["bb"] not in ("IASSD_Backbone", "PAGNet_Backbone", "IASSD_DET"):
+        return {"verified": None, "reason": "no reference arm for this workload"}
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID", "GROUP_RANK", "LOCAL_WORLD_SIZE"):
+        env.pop(k, None)
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    env["CUDA_VISIBLE_DEVICES"] = vis.split(",")[local] if vis else str(local)
+    try:
+        r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--verify-only", "--workload", args.workload], env=env,
+                           capture_output=True, text=True, timeout=900)
+        for ln in r.stdout.splitlines():
+            if ln.startswith("VERIFY "):
+                return json.loads(ln[len("VERIFY "):])
+        return {"verified": False, "error": (r.stderr or r.stdout)[-400:]}
+    except Exception as e:
+        return {"verified": False, "error": f"{type(e).__name__}: {e}"[:400]}
+
+
+def main():
+    args = parse_args()
     set_workload(args.workload)
     rank, world, local = dist_env()
     args.warmup = max(args.warmup, 3)
 
+    if args.verify_only:
+        return run_verify_only(args)
     if args.impl == "reference-cpu" or (args.impl == "reference" and not torch.cuda.is_available()):
         return run_reference_cpu(args, rank, world)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    pinned = None if (args.no_pin or world == 1) else pin_rank_to_cores(local, world)
     if world > 1:
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     peaks = load_peaks()
-    net = build_net()
-    state = {k: v.clone() for k, v in net.state_dict().items()}
-    n_pool = args.pool or (L2_BYTES // (BATCH * NPTS * NCOLS * 4) + 2)
-    host_pool = make_pool(rank, n_pool)
-    dev_pool = [t.cuda() for t in host_pool]
 
     line = {"metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": DTYPE, "data": "synthetic"}
     cfg = {"workload": WORKLOAD, "batch_per_gpu": BATCH, "points_per_scene": NPTS,
-           "l2_policy": f"input pool of {n_pool} distinct batches ({n_pool * BATCH * NPTS * NCOLS * 4 / 2**20:.0f} MiB > 126 MiB L2) cycled",
            "parallelism": f"scene-sharded x{world}, no data-path collective"}
+    if args.scaling == "strong":
+        cfg["strong_scaling"] = (f"one host batch of {args.total_scenes} scenes per step, cut into contiguous shards by "
+                                 f"spsnet_b200.sharding.shard_range ({args.total_scenes // world} scenes = {args.total_scenes // world // BATCH} "
+                                 f"sub-batches of {BATCH} per rank)")
 
     if args.impl == "reference":
-        try:
-            ref = (load_reference_detector(state) if _WL["bb"] == "IASSD_DET" else load_reference_backbone(state)).cuda()
-        except Exception as e:  # fall back to the CPU port of the oracle
-            if rank == 0:
-                sys.stderr.write(f"[bench] reference CUDA module unavailable ({e}); using the CPU oracle port\n")
-            return run_reference_cpu(args, rank, world)
-        torch.backends.cudnn.allow_tf32 = True  # the reference's stock setting
-        pipe = EagerRef(ref, outputs=("det_boxes", "det_scores", "det_labels", "det_count") if _WL["bb"] == "IASSD_DET"
-                        else ("centers_features", "centers"), extra=extra_inputs("cuda"))
-        pipe.submit_device(dev_pool[0])
-        pipe.sync()
-        sampler = ClockSampler(local)
-        sampler.start()
-        ms, _ = timed_region(pipe, dev_pool, args.steps, args.warmup, host=False, world=world)
-        ms_e2e, _ = timed_region(pipe, host_pool, args.steps, args.warmup, host=True, world=world)
-        clocks = sampler.stop()
-        value = world * BATCH * args.steps / (ms / 1e3)
-        e2e = world * BATCH * args.steps / (ms_e2e / 1e3)
-        line.update(impl="reference", value=value, ms_per_step=ms / args.steps, clocks=clocks, gpu_launches=None,
-                    e2e={"value": e2e, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes(), "d2h_bytes_per_step": pipe.d2h_bytes()},
-                    cpu_baseline={"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
-                                  "sample": "not a CPU run: the reference's own CUDA ops (pointnet2_batch rebuilt for sm_100a) + its "
-                                            "pointnet2_modules.py / IASSD_backbone.py on the same B200, cudnn.allow_tf32=True (stock); "
-                                            "use --impl reference-cpu for the CPU oracle port"})
-        cfg["reference"] = "unmodified reference from oracle/_ref on GPU (eager, as shipped)"
-        line["config"] = cfg
-        if rank == 0:
-            print(json.dumps(line), flush=True)
-        if world > 1:
-            import torch.distributed as dist
-
-            dist.destroy_process_group()
-        return
+        return run_reference_gpu(args, rank, world, local, line, cfg)
 
     # ---- our arm
+    verdict = None
+    if rank == 0 and not args.no_verify:
+        verdict = verify_in_helper_process(args, local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
     from spsnet_b200 import _lib
     from spsnet_b200.runtime import BackbonePipeline
 
-    net = net.cuda()
+    net = build_net().cuda()
+    host_pool, per_step, n_pool = make_pool_for(args, rank, world)
+    dev_pool = [t.cuda() for t in host_pool]
+    cfg["l2_policy"] = f"input pool of {n_pool} distinct batches ({n_pool * BATCH * NPTS * NCOLS * 4 / 2**20:.0f} MiB > 126 MiB L2) cycled"
     outputs = ("det_boxes", "det_scores", "det_labels", "det_count") if _WL["bb"] in ("IASSD_DET", "SPSNET_DET") else ("centers_features", "centers")
     pipe = BackbonePipeline(net, BATCH, NPTS, NCOLS, depth=args.depth, use_graph=not args.no_graph, extra_inputs=extra_inputs("cuda"),
-                            outputs=outputs)
+                            outputs=outputs, out16=args.out16, timeline=args.timeline and rank == 0)
     pipe.prepare(dev_pool[0])
     sampler = ClockSampler(local)
     sampler.start()
-    ms, wall = timed_region(pipe, dev_pool, args.steps, args.warmup, host=False, world=world)
-    ms_e2e, _ = timed_region(pipe, host_pool, args.steps, args.warmup, host=True, world=world)
+    ms, wall = timed_region(pipe, dev_pool, args.steps, args.warmup, host=False, world=world, per_step=per_step)
+    pipe.reset_timeline()
+    ms_e2e, _ = timed_region(pipe, host_pool, args.steps, args.warmup, host=True, world=world, per_step=per_step)
     clocks = sampler.stop()
-    value = world * BATCH * args.steps / (ms / 1e3)
-    e2e = world * BATCH * args.steps / (ms_e2e / 1e3)
+    scenes_total = world * BATCH * args.steps * per_step
+    value = scenes_total / (ms / 1e3)
+    e2e = scenes_total / (ms_e2e / 1e3)
     line.update(impl="ours", value=value, ms_per_step=ms / args.steps, clocks=clocks,
-                gpu_launches=int(pipe.launches_per_step * args.steps),
-                e2e={"value": e2e, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes(), "d2h_bytes_per_step": pipe.d2h_bytes()})
-    cfg.update(pipeline_depth=args.depth, cuda_graph=not args.no_graph, launches_per_step=int(pipe.launches_per_step))
+                gpu_launches=int(pipe.launches_per_step * args.steps * per_step),
+                e2e={"value": e2e, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes() * per_step, "d2h_bytes_per_step": pipe.d2h_bytes() * per_step,
+                     "ms_per_step": ms_e2e / args.steps, "outputs_dtype": "fp16" if args.out16 else "fp32"})
+    if args.timeline and rank == 0:
+        line["e2e"]["timeline"] = pipe.timeline_summary()
+    cfg.update(pipeline_depth=args.depth, cuda_graph=not args.no_graph, launches_per_step=int(pipe.launches_per_step) * per_step)
+    if pinned:
+        cfg["host_cores_of_rank0"] = pinned
+    if verdict is not None:
+        line["verified"] = bool(verdict.get("verified"))
+        line["verify"] = verdict
+    line["native_so_loaded"] = loaded_repo_libraries()
+
+    if not args.no_depth1 and args.depth != 1 and args.scaling == "weak":
+        # latency view: ONE batch in flight (the pipeline cannot hide the FPS chain behind other batches)
+        pipe1 = BackbonePipeline(net, BATCH, NPTS, NCOLS, depth=1, use_graph=not args.no_graph, extra_inputs=extra_inputs("cuda"), outputs=outputs)
+        pipe1.prepare(dev_pool[0])
+        s1 = max(8, min(args.steps, 32))
+        ms1, _ = timed_region(pipe1, dev_pool, s1, 3, host=False, world=world)
+        ms1h, _ = timed_region(pipe1, host_pool, s1, 3, host=True, world=world)
+        line["depth1"] = {"value": world * BATCH * s1 / (ms1 / 1e3), "ms_per_step": ms1 / s1, "steps": s1, "unit": UNIT,
+                          "e2e": world * BATCH * s1 / (ms1h / 1e3),
+                          "note": "same workload with ONE batch in flight (pipeline_depth 1): ms_per_step here is the latency of a batch"}
+        del pipe1
 
     if rank == 0 and not args.no_profile:
         table, psteps = profile_kernels(net, dev_pool, steps=min(args.steps, 5))
@@ -694,6 +856,51 @@ def main():
         import torch.distributed as dist
 
         dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_reference_gpu(args, rank, world, local, line, cfg):
+    """The UNMODIFIED reference (oracle/_ref: its CUDA ops rebuilt for sm_100a + its own python modules) on the same GPU, same
+    seeded weights, same inputs.  Nothing of this repo's product is imported: the process maps oracle/_ref's libraries only."""
+    try:
+        ref = build_reference_from_seed().cuda()
+    except Exception as e:  # fall back to the CPU port of the oracle
+        if rank == 0:
+            sys.stderr.write(f"[bench] reference CUDA module unavailable ({e}); using the CPU oracle port\n")
+        return run_reference_cpu(args, rank, world)
+    host_pool, per_step, n_pool = make_pool_for(args, rank, world)
+    dev_pool = [t.cuda() for t in host_pool]
+    cfg["l2_policy"] = f"input pool of {n_pool} distinct batches ({n_pool * BATCH * NPTS * NCOLS * 4 / 2**20:.0f} MiB > 126 MiB L2) cycled"
+    torch.backends.cudnn.allow_tf32 = True  # the reference's stock setting (SURVEY.md A.5)
+    pipe = EagerRef(ref, outputs=("det_boxes", "det_scores", "det_labels", "det_count") if _WL["bb"] == "IASSD_DET"
+                    else ("centers_features", "centers"), extra=extra_inputs("cuda"))
+    pipe.submit_device(dev_pool[0])
+    pipe.sync()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, _ = timed_region(pipe, dev_pool, args.steps, args.warmup, host=False, world=world, per_step=per_step)
+    ms_e2e, _ = timed_region(pipe, host_pool, args.steps, args.warmup, host=True, world=world, per_step=per_step)
+    clocks = sampler.stop()
+    scenes_total = world * BATCH * args.steps * per_step
+    value = scenes_total / (ms / 1e3)
+    e2e = scenes_total / (ms_e2e / 1e3)
+    line.update(impl="reference", dtype=DTYPE_REF, value=value, ms_per_step=ms / args.steps, clocks=clocks, gpu_launches=None,
+                e2e={"value": e2e, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes() * per_step, "d2h_bytes_per_step": pipe.d2h_bytes() * per_step,
+                     "ms_per_step": ms_e2e / args.steps, "outputs_dtype": "fp32"},
+                depth1={"value": value, "ms_per_step": ms / args.steps / per_step, "steps": args.steps, "unit": UNIT, "e2e": e2e,
+                        "note": "the reference has no pipelining: one batch in flight is its only mode"},
+                cpu_baseline={"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
+                              "sample": "not a CPU run: the reference's own CUDA ops (pointnet2_batch rebuilt for sm_100a) + its "
+                                        "pointnet2_modules.py / IASSD_backbone.py on the same B200, cudnn.allow_tf32=True (stock); "
+                                        "use --impl reference-cpu for the CPU oracle port"},
+                native_so_loaded=loaded_repo_libraries())
+    cfg["reference"] = "unmodified reference from oracle/_ref on GPU (eager, as shipped), weights built from the same seed"
+    line["config"] = cfg
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+
         dist.destroy_process_group()
 
 
@@ -719,7 +926,7 @@ def run_reference_cpu(args, rank, world):
     cores = max(O.num_threads(), torch.get_num_threads())
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": min(args.warmup, 1), "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "fp32 (CPU oracle port)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sample": f"each step = {sample} scenes of the workload on the host CPU"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{sample} scenes per step x {steps} steps, oracle/oracle.c (OpenMP) + torch-CPU conv/BN"},

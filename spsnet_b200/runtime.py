@@ -25,10 +25,16 @@ class _Slot:
     __slots__ = ("stream", "static_in", "graph", "outs", "host_outs", "done")
 
 
+def _median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2] if xs else None
+
+
 class BackbonePipeline:
     def __init__(self, net: torch.nn.Module, batch_size: int, n_points: int, n_cols: int, depth: int = 2,
                  use_graph: bool = True, outputs: Sequence[str] = ("centers_features", "centers"),
-                 extra_inputs: Dict[str, torch.Tensor] | None = None, device: torch.device | None = None):
+                 extra_inputs: Dict[str, torch.Tensor] | None = None, device: torch.device | None = None,
+                 out16: bool = False, timeline: bool = False):
         self.net = net
         self.B, self.N, self.cols = batch_size, n_points, n_cols
         self.depth = depth
@@ -36,6 +42,12 @@ class BackbonePipeline:
         self.outputs = tuple(outputs)
         self.device = device or next(net.parameters()).device
         self.extra = extra_inputs or {}
+        # out16: hand `centers_features` back as fp16 -- the values half of the point-major fp16 rows the last SA layer already
+        # wrote for the head -- which halves the device->host bytes of a step (opt-in: the reference returns fp32)
+        self.out16 = out16
+        # timeline: four CUDA events per submit_host (before H2D, after H2D, after the forward, after D2H), see timeline_summary()
+        self.timeline = timeline
+        self._tl: list = []
         self.slots: List[_Slot] = []
         self._next = 0
         self.launches_per_step = 0
@@ -54,7 +66,15 @@ class BackbonePipeline:
         d.update(self.extra)
         # detectors expose a fixed-shape, sync-free forward (spsnet_b200.detector.IASSD.forward_padded)
         out = self.net.forward_padded(d) if hasattr(self.net, "forward_padded") else self.net(d)
-        return {k: out[k] for k in self.outputs}
+        res = {k: out[k] for k in self.outputs}
+        if self.out16 and "centers_features" in res:
+            cf = res["centers_features"]
+            rows = getattr(cf, "_spsk_rows16", None)
+            if rows is not None and rows[1] == cf._version:
+                res["centers_features"] = rows[0][:, :cf.shape[1]].contiguous()   # fp16 values, (B * M, C)
+            else:
+                res["centers_features"] = cf.half()
+        return res
 
     def prepare(self, example_points: torch.Tensor) -> None:
         """Warm up (fold BN, set kernel attributes, fill the allocator) and capture one graph per slot."""
@@ -98,13 +118,40 @@ class BackbonePipeline:
         i = self._next
         s = self.slots[i]
         with torch.cuda.stream(s.stream):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if self.timeline else None
+            if ev:
+                ev[0].record(s.stream)
             s.static_in.copy_(host_points, non_blocking=True)
+            if ev:
+                ev[1].record(s.stream)
             self._run(s)
+            if ev:
+                ev[2].record(s.stream)
             for k, v in s.outs.items():
                 s.host_outs[k].copy_(v, non_blocking=True)
+            if ev:
+                ev[3].record(s.stream)
+                self._tl.append(ev)
             s.done.record(s.stream)
         self._next = (i + 1) % self.depth
         return i
+
+    def reset_timeline(self) -> None:
+        self._tl = []
+
+    def timeline_summary(self) -> dict:
+        """Median milliseconds a step spends in its H2D copy, its forward (queueing behind other slots included) and its D2H
+        copy, and the copy rates they imply -- the evidence for what bounds the end-to-end number at 8 GPUs."""
+        self.sync()
+        h2d = [e[0].elapsed_time(e[1]) for e in self._tl]
+        fwd = [e[1].elapsed_time(e[2]) for e in self._tl]
+        d2h = [e[2].elapsed_time(e[3]) for e in self._tl]
+        if not h2d:
+            return {}
+        mh, mf, md = _median(h2d), _median(fwd), _median(d2h)
+        return {"steps": len(h2d), "h2d_ms_median": mh, "forward_ms_median": mf, "d2h_ms_median": md,
+                "h2d_ms_max": max(h2d), "d2h_ms_max": max(d2h),
+                "h2d_gbs_median": self.h2d_bytes() / 1e6 / mh if mh else None, "d2h_gbs_median": self.d2h_bytes() / 1e6 / md if md else None}
 
     def join(self, stream: torch.cuda.Stream) -> None:
         """Make `stream` wait for everything submitted so far (device-side, no host sync)."""

@@ -69,3 +69,21 @@ def test_gloo_world2_sharded_report():
 
 def test_reduce_report_without_group_is_identity():
     assert sharding.reduce_report(16, 2.5) == (16, 2.5)
+
+
+def test_strong_scaling_plan_partitions_the_host_batch():
+    """bench.py --scaling strong: the per-rank shards of one 128-scene host batch (shard_range) tile it exactly, in whole
+    sub-batches of 16 scenes, for every world size of the scaling run."""
+    import types
+
+    import bench
+
+    bench.set_workload("kitti")
+    for world in (1, 2, 4, 8):
+        seen = []
+        for rank in range(world):
+            lo, per_step = bench.strong_plan(types.SimpleNamespace(total_scenes=128), rank, world)
+            seen += list(range(lo, lo + per_step * bench.BATCH))
+        assert seen == list(range(128))
+    with pytest.raises(SystemExit):
+        bench.strong_plan(types.SimpleNamespace(total_scenes=100), 0, 8)
