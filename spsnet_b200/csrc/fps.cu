@@ -14,7 +14,7 @@
 //                                                 buffered) -> REDUX.MAX again in every warp
 //
 // FPS is latency bound: m-1 strictly sequential arg-max steps per scene.  One CTA per scene.
-#include "common.cuh"
+#include "mma_ptx.cuh"
 #include <stdlib.h>
 
 namespace spsk {
@@ -198,17 +198,33 @@ __device__ __forceinline__ void st_cluster_v4(const void *local_ptr, uint32_t ct
 
 // PROF: compile the phase counters in (spsk_fps_set_profile).  They are predicated instructions, but on this latency chain
 // every issue slot counts: 16 warps x ~40 predicated-off instructions per iteration were ~10 % of the iteration.
-template <int P, bool CL, int LADDER, bool PROF>
+//
+// TM: the running minima (and each point's tie-break key ~rank) live in TENSOR MEMORY instead of registers.  The minima of a
+// lane are private to it, which is exactly the access pattern tcgen05.ld/st offer (a warp reaches the 32 TMEM lanes of its
+// quarter; column = sub-bucket), and -- unlike registers -- the column index is DYNAMIC: a visited sub-bucket is one generic
+// loop body (ffs over the ballot mask, 12-cycle TMEM load, distance, TMEM store, two REDUX) instead of a 32-case ladder of
+// warp-uniform branches around 32 statically indexed copies of the body.  Measured with the phase counters (round 2): the
+// ladder + its reconvergence points cost ~400-500 cycles per visited sub-bucket on the critical warp of an iteration; the
+// generic body ~160.  Shared memory cannot take the minima (xyz 192 KB + index map 32 KB already fill it at 16384 points);
+// the 256 KB of TMEM are otherwise unused by this kernel.  Layout: warp w owns columns [(w / 4) * 2P, +2P) of lane quarter
+// w % 4; sub-bucket p = columns (2p, 2p + 1) = (running minimum bits, ~rank or 0 for padding).
+// ST (storage of the running minima): 0 = registers + ladder (the round-1 kernel), 1 = tensor memory (TM above), 2 = shared
+// memory (small scenes, P <= 8: the minima fit next to xyz, and a small CTA must not hold TMEM columns -- it shares its SM with
+// sa_mma CTAs that allocate all 512).  1 and 2 run the same generic visit loop.
+template <int P, bool CL, int LADDER, bool PROF, int ST>
 __global__ void __launch_bounds__(512, 1)
 fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__restrict__ temp, int *__restrict__ idx,
                   unsigned long long *__restrict__ prof) {
     constexpr int T = 512, W = 16, NP = T * P;
+    constexpr bool TM = ST == 1, SM = ST == 2, GEN = ST != 0;
     constexpr uint32_t s_mask = 1023u, s_log2 = 10u;   // reference block size is 1024 for n >= 1024
     extern __shared__ float smem[];
     __shared__ float red[6][W];
     float *sx = smem, *sy = smem + NP, *sz = smem + 2 * NP;
     uint32_t *keys = reinterpret_cast<uint32_t *>(smem);              // sort phase only (aliases sx)
     unsigned short *pos_of = reinterpret_cast<unsigned short *>(smem + 3 * NP);
+    float *stmp = smem + 3 * NP + (CL ? 0 : NP / 2);                   // ST == 2: running minima by sorted position ...
+    uint32_t *sir = reinterpret_cast<uint32_t *>(stmp + NP);          // ... and ~rank (0 = padding)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t crank = CL ? cluster_ctarank() : 0u, csize = CL ? cluster_nctarank() : 1u;
     const size_t scene = CL ? blockIdx.x / csize : blockIdx.x;
@@ -219,6 +235,9 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
     const float *base = scene_base + (size_t)gbase * 3;
     if (temp) temp += scene * (size_t)n_scene;   // indexed with scene indices
     idx += scene * (size_t)m;
+    constexpr uint32_t TM_COLS = 8 * P < 32 ? 32 : 8 * P;   // 4 warps per lane quarter x P sub-buckets x 2 columns (power of two)
+    __shared__ uint32_t tm_slot;
+    if (TM && warp == 0) tmem_alloc(smem_u32(&tm_slot), TM_COLS);
 
     // ---- bounding box of the owned points (only scales the Morton cells: any box gives the same samples)
     float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
@@ -282,10 +301,16 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
     }
     // ---- take ownership: slot p of this lane = sorted position ((p*W + warp)*32 + lane)
     uint32_t oidx[P];
-    float tmp[P];
+    float tmp[GEN ? 1 : P];
 #pragma unroll
     for (int p = 0; p < P; ++p) oidx[p] = keys[(p * W + warp) * 32 + lane];
+    if (TM) tc_fence_before();
     __syncthreads();   // keys consumed; the region becomes sx/sy/sz
+    uint32_t tbase = 0u;   // TM: this warp's first column in its lane quarter
+    if (TM) {
+        tc_fence_after();
+        tbase = tm_slot + ((uint32_t)(warp & 3) << 21) + (uint32_t)(warp >> 2) * (2u * P);   // lane field = bits 31:16
+    }
 #pragma unroll
     for (int p = 0; p < P; ++p) {
         const int pos = (p * W + warp) * 32 + lane;
@@ -295,9 +320,13 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
         sx[pos] = valid ? __ldg(base + (size_t)oi * 3) : 0.f;
         sy[pos] = valid ? __ldg(base + (size_t)oi * 3 + 1) : 0.f;
         sz[pos] = valid ? __ldg(base + (size_t)oi * 3 + 2) : 0.f;
-        tmp[p] = valid ? (temp ? temp[oidx[p]] : 1e10f) : -1.f;
+        const float t0 = valid ? (temp ? temp[oidx[p]] : 1e10f) : -1.f;
+        if (TM) tmem_st_x2(tbase + 2u * p, __float_as_uint(t0), valid ? ~fps_rank(oidx[p], s_mask, s_log2) : 0u);
+        else if (SM) { stmp[pos] = t0; sir[pos] = valid ? ~fps_rank(oidx[p], s_mask, s_log2) : 0u; }
+        else tmp[p] = t0;
         if (!CL && valid) pos_of[oi] = (unsigned short)pos;
     }
+    if (TM) tmem_wait_st();
     __syncthreads();
     // ---- sub-bucket boxes: lane p keeps the box / bmax / best-rank of slot p of this warp
     float bx0 = 3.0e38f, bx1 = -3.0e38f, by0 = 3.0e38f, by1 = -3.0e38f, bz0 = 3.0e38f, bz1 = -3.0e38f;
@@ -361,14 +390,15 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
     const bool pf = PROF && prof != nullptr && tid == 0 && !CL;
     unsigned long long pc[6] = {0, 0, 0, 0, 0, 0};
     unsigned long long visited = 0;
+    uint32_t wm = 0u, wr = 0u, wpos = 0u;   // this warp's best (value, ~rank, position): recomputed only after a visit
 
 #define SPSK_FPS_BUCKET(PP)                                                                                      \
     case PP:                                                                                                     \
         if (PP < P) {                                                                                            \
             const int pos = (PP * W + warp) * 32 + lane;                                                         \
             const float d = sqdist3(sx[pos], sy[pos], sz[pos], x1, y1, z1);                                      \
-            const float t = fminf(d, tmp[PP < P ? PP : 0]);                                                      \
-            tmp[PP < P ? PP : 0] = t;                                                                            \
+            const float t = fminf(d, tmp[(!GEN && PP < P) ? PP : 0]);                                            \
+            tmp[(!GEN && PP < P) ? PP : 0] = t;                                                                  \
             const uint32_t oi = oidx[PP < P ? PP : 0];                                                           \
             const bool valid = oi != 0xFFFFFFFFu;                                                                \
             const uint32_t u = (valid && t > 0.f) ? __float_as_uint(t) : 0u;                                     \
@@ -391,6 +421,7 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
         const float lb = __fmaf_rn(lz, lz, __fmaf_rn(lx, lx, __fmul_rn(ly, ly)));
         const bool act = (lane < P) && (lb < __uint_as_float(bmax_bits));
         uint32_t mask = __ballot_sync(0xFFFFFFFFu, act);
+        const uint32_t mask0 = mask;
         if (PROF && pf) { const long long t1 = clock64(); pc[0] += t1 - t0; t0 = t1; }
         if (PROF && prof != nullptr && lane == 0) visited += __popc(mask);
 #define SPSK_FPS_ALL_BUCKETS                                                                                              \
@@ -400,7 +431,31 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
     SPSK_FPS_BUCKET(18) SPSK_FPS_BUCKET(19) SPSK_FPS_BUCKET(20) SPSK_FPS_BUCKET(21) SPSK_FPS_BUCKET(22) SPSK_FPS_BUCKET(23)  \
     SPSK_FPS_BUCKET(24) SPSK_FPS_BUCKET(25) SPSK_FPS_BUCKET(26) SPSK_FPS_BUCKET(27) SPSK_FPS_BUCKET(28) SPSK_FPS_BUCKET(29)  \
     SPSK_FPS_BUCKET(30) SPSK_FPS_BUCKET(31)
-        if (LADDER == 2) {
+        if (GEN) {
+            // generic body, dynamic sub-bucket index: the running minimum and the point's tie-break key come from TMEM (or
+            // shared memory)
+            uint32_t mk = mask;
+            while (mk) {
+                const int pb = __ffs(mk) - 1;
+                mk &= mk - 1u;
+                const int pos = (pb * W + warp) * 32 + lane;
+                uint32_t tb, ir;
+                if (TM) tmem_ld_x2(tbase + 2u * (uint32_t)pb, tb, ir);
+                else { tb = __float_as_uint(stmp[pos]); ir = sir[pos]; }
+                const float d = sqdist3(sx[pos], sy[pos], sz[pos], x1, y1, z1);
+                const float t = fminf(d, __uint_as_float(tb));
+                if (TM) tmem_st_x1(tbase + 2u * (uint32_t)pb, __float_as_uint(t));
+                else stmp[pos] = t;
+                const uint32_t u = (t > 0.f) ? __float_as_uint(t) : 0u;   // padding keeps t = -1, ir = 0
+                const uint32_t mx = __reduce_max_sync(0xFFFFFFFFu, u);
+                const uint32_t cand = (u == mx) ? ir : 0u;
+                const uint32_t rr = __reduce_max_sync(0xFFFFFFFFu, cand);
+                uint32_t bp = 0u;   // cluster mode only: the best point's position travels with the summary
+                if (CL) bp = __reduce_max_sync(0xFFFFFFFFu, (ir != 0u && cand == rr) ? (uint32_t)pos : 0u);
+                if (lane == pb) { bmax_bits = mx; brank = rr; bpos = bp; }
+            }
+            if (TM && mask) tmem_wait_st();   // the next load of these columns (a later iteration) must see the stores
+        } else if (LADDER == 2) {
             // two-level ladder: groups of 8 sub-buckets, then the bits of a non-empty group
 #pragma unroll
             for (int g = 0; g < P; g += 8) {
@@ -433,22 +488,29 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
         }
 #undef SPSK_FPS_ALL_BUCKETS
         if (PROF && pf) { const long long t1 = clock64(); pc[1] += t1 - t0; t0 = t1; }
-        // warp best over its P sub-buckets
-        const uint32_t wv = (lane < P) ? bmax_bits : 0u;
-        const uint32_t wm = __reduce_max_sync(0xFFFFFFFFu, wv);
-        const uint32_t wc = (lane < P && bmax_bits == wm) ? brank : 0u;
-        const uint32_t wr = __reduce_max_sync(0xFFFFFFFFu, wc);
-        // (value, ~rank) identifies one point, so exactly one lane matches: a max-reduction moves its position
-        uint32_t wpos = 0u;
-        if (CL) wpos = __reduce_max_sync(0xFFFFFFFFu, (lane < P && bmax_bits == wm && brank == wr) ? bpos : 0u);
+        // warp best over its P sub-buckets: unchanged (cached) when this warp visited nothing -- most warps, most iterations;
+        // their REDUX would only compete with the critical warp's for the same unit
+        if (mask0) {
+            const uint32_t wv = (lane < P) ? bmax_bits : 0u;
+            wm = __reduce_max_sync(0xFFFFFFFFu, wv);
+            const uint32_t wc = (lane < P && bmax_bits == wm) ? brank : 0u;
+            wr = __reduce_max_sync(0xFFFFFFFFu, wc);
+            // (value, ~rank) identifies one point, so exactly one lane matches: a max-reduction moves its position
+            if (CL) wpos = __reduce_max_sync(0xFFFFFFFFu, (lane < P && bmax_bits == wm && brank == wr) ? bpos : 0u);
+        }
         if (!CL) {
             uint2 *sl = slots2[j & 1];
-            if (lane == 0) sl[warp] = make_uint2(wm, wr);
+            if (lane == 0) {
+                sl[warp] = make_uint2(wm, wr);
+            }
             if (PROF && pf) { const long long t1 = clock64(); pc[2] += t1 - t0; t0 = t1; }
             __syncthreads();
             if (PROF && pf) { const long long t1 = clock64(); pc[3] += t1 - t0; t0 = t1; }
             // block best over the W warp slots
             const uint2 v = sl[lane];
+            // (tried in round 2 and dropped: the block maximum of the value through a native shared-memory atomicMax + ballot /
+            // shuffle for the rank instead of the two REDUX below -- 1086 vs 895 cycles per iteration: the atomic sits in front of
+            // the barrier on every warp and VOTE + SHFL are no faster than one REDUX)
             const uint32_t m2 = __reduce_max_sync(0xFFFFFFFFu, v.x);
             const uint32_t r2 = __reduce_max_sync(0xFFFFFFFFu, (v.x == m2) ? v.y : 0u);
             // the sample's original index: rank(k) = brev(k & s_mask) | (k >> s_log2); its sorted position through the map
@@ -509,18 +571,33 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
     }
     if (temp) {
 #pragma unroll
-        for (int p = 0; p < P; ++p)
-            if (oidx[p] != 0xFFFFFFFFu) temp[oidx[p]] = tmp[p];
+        for (int p = 0; p < P; ++p) {
+            if (GEN) {
+                uint32_t tb, ir;
+                if (TM) tmem_ld_x2(tbase + 2u * p, tb, ir);
+                else { const int pos = (p * W + warp) * 32 + lane; tb = __float_as_uint(stmp[pos]); ir = sir[pos]; }
+                const uint32_t rank = ~ir;   // rank(k) = brev(k & s_mask) | (k >> s_log2): the point's scene index, recovered
+                if (ir != 0u) temp[(__brev(rank) & s_mask) | ((rank & ((1u << (32u - s_log2)) - 1u)) << s_log2)] = __uint_as_float(tb);
+            } else if (oidx[p] != 0xFFFFFFFFu) {
+                temp[oidx[p]] = tmp[(!GEN) ? p : 0];
+            }
+        }
+    }
+    if (TM) {
+        tc_fence_before();
+        __syncthreads();
+        if (warp == 0) { tc_fence_after(); tmem_dealloc(tm_slot, TM_COLS); }
     }
 }
 
 static unsigned long long *g_fps_prof = nullptr;
 constexpr int SPSK_FPS_NO_CLUSTER = 1;   // internal: the requested cluster size cannot run here, use the streaming kernel
 
-template <int P, bool CL, int LADDER, bool PROF = false>
+template <int P, bool CL, int LADDER, bool PROF = false, int ST = 0>
 static int launch_fps_pruned_v(int b, int n, int m, int csize, const float *src, float *temp, int *idx, cudaStream_t st) {
-    const size_t smem = sizeof(float) * 3 * 512 * P + (CL ? 0 : sizeof(unsigned short) * 512 * P);   // xyz (+ index -> position map)
-    auto kern = fps_pruned_kernel<P, CL, LADDER, PROF>;
+    const size_t smem = sizeof(float) * 3 * 512 * P + (CL ? 0 : sizeof(unsigned short) * 512 * P)   // xyz (+ index -> position map)
+                        + (ST == 2 ? 8 * 512 * P : 0);                                               // (+ minima and ~rank)
+    auto kern = fps_pruned_kernel<P, CL, LADDER, PROF, ST>;
     if (smem + 8192 > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fps_pruned_kernel)");
@@ -561,6 +638,15 @@ static int launch_fps_pruned_v(int b, int n, int m, int csize, const float *src,
 // (SPSK_FPS_DISPATCH=ladder|switch overrides, for A/B measurements)
 template <int P, bool CL>
 static int launch_fps_pruned(int b, int n, int m, int csize, const float *src, float *temp, int *idx, cudaStream_t st) {
+    // P >= 16 (n > 4096 points per CTA): running minima in tensor memory, generic visit loop (see the kernel).  These CTAs fill
+    // their SM's shared memory, so the TMEM columns they hold never compete with a co-resident tensor-core kernel; the smaller
+    // shapes (short ladders, CTAs that share their SM with sa_mma CTAs wanting all 512 columns) keep the register kernel.
+    static const bool no_tm = getenv("SPSK_FPS_NOTMEM") != nullptr;   // A/B and fallback: the round-1 register kernel everywhere
+    if (!no_tm) {
+        constexpr int ST = P >= 16 ? 1 : 2;
+        if (g_fps_prof != nullptr) return launch_fps_pruned_v<P, CL, 2, true, ST>(b, n, m, csize, src, temp, idx, st);
+        return launch_fps_pruned_v<P, CL, 2, false, ST>(b, n, m, csize, src, temp, idx, st);
+    }
     int mode = 2;   // 1 = ladder, 2 = two-level ladder (fastest at every P on B200), 0 = switch over set bits
     if (const char *e = getenv("SPSK_FPS_DISPATCH")) mode = e[0] == 'l' ? 1 : (e[0] == 'g' ? 2 : 0);
     if (mode == 1) return launch_fps_pruned_v<P, CL, 1>(b, n, m, csize, src, temp, idx, st);

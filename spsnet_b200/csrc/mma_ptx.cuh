@@ -147,6 +147,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- TMEM as a warp-private scratch array (fps.cu): one 32-bit word per (lane, column), DYNAMIC column index -------------
+// A warp reaches the 32 TMEM lanes of its quarter (warp % 4); `.32x32b.xN` moves N consecutive columns of every lane.
+__device__ __forceinline__ void tmem_ld_x2(uint32_t taddr, uint32_t &a, uint32_t &b) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st_x1(uint32_t taddr, uint32_t a) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(a) : "memory");
+}
+__device__ __forceinline__ void tmem_st_x2(uint32_t taddr, uint32_t a, uint32_t b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // relu(a), relu(b) -> packed fp16x2 in ONE conversion (cvt.rn.relu): saves the two FMNMX of fmaxf(x, 0) per pair in the
 // hidden-layer epilogue.  First source operand = upper half.
 __device__ __forceinline__ uint32_t pack_h2_relu(float a, float b) {

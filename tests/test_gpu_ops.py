@@ -378,9 +378,10 @@ def test_fps_top_corner_point_is_not_padding(oracle, ref_ops, n, chunks):
 
     xyz = _xyz(2, n, seed=77, kind="waymo" if n > 16384 else "kitti")
     per = n // chunks
+    top = xyz.max(axis=1)
     for c in range(chunks):
-        blk = xyz[:, c * per:(c + 1) * per]
-        xyz[:, (c + 1) * per - 1] = blk.max(axis=1) + np.float32(1.0 + c)   # strict maximum of the chunk in all three axes
+        # strict maximum of its chunk (and of the scene) in all three axes, and a far outlier: FPS must pick every one of them early
+        xyz[:, (c + 1) * per - 1] = top + np.float32(100.0 * (c + 1))
     m = 64
     got = pu.furthest_point_sample(dev(xyz), m).cpu().numpy()
     want = oracle.fps(xyz, m)
