@@ -110,12 +110,15 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, enabled: bool = True):
         self.gpu = gpu_index
+        self.enabled = enabled
         self.proc = None
         self.path = Path(f"/tmp/spsk_clocks_{os.getpid()}.csv")
 
     def start(self):
+        if not self.enabled:
+            return
         try:
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -640,7 +643,8 @@ def parse_args():
                     help="weak: every rank runs its own batches of 16 scenes (default, the driver's scaling run); strong: ONE host batch of "
                          "--total-scenes scenes per step is cut into contiguous shards by spsnet_b200.sharding.shard_range")
     ap.add_argument("--total-scenes", type=int, default=128, help="strong scaling: scenes in the host batch of one step")
-    ap.add_argument("--no-pin", action="store_true", help="do not pin each rank to its own block of host cores")
+    ap.add_argument("--pin", action="store_true", help="pin each rank to its own block of host cores (opt-in: on the 16-core / 8-GPU boxes of "
+                    "this pool two cores per rank starve the CUDA helper threads: e2e 70.6k vs 78.2k scenes/s at N = 8, profiles/r02_*)")
     ap.add_argument("--out16", action="store_true", help="e2e: return centre features as fp16 (halves the D2H bytes; opt-in, default fp32 like the reference)")
     ap.add_argument("--timeline", action="store_true", help="e2e: CUDA-event timeline of H2D / forward / D2H per step (rank 0), printed in `e2e.timeline`")
     ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS), help="kitti = BASELINE.json configs[1] (headline)")
@@ -764,7 +768,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
-    pinned = None if (args.no_pin or world == 1) else pin_rank_to_cores(local, world)
+    pinned = pin_rank_to_cores(local, world) if (args.pin and world > 1) else None
     if world > 1:
         import torch.distributed as dist
 
@@ -802,7 +806,7 @@ def main():
     pipe = BackbonePipeline(net, BATCH, NPTS, NCOLS, depth=args.depth, use_graph=not args.no_graph, extra_inputs=extra_inputs("cuda"),
                             outputs=outputs, out16=args.out16, timeline=args.timeline and rank == 0)
     pipe.prepare(dev_pool[0])
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, enabled=rank == 0)   # one nvidia-smi poller per job, not one per rank (8 pollers contend for the driver)
     sampler.start()
     ms, wall = timed_region(pipe, dev_pool, args.steps, args.warmup, host=False, world=world, per_step=per_step)
     pipe.reset_timeline()
@@ -876,7 +880,7 @@ def run_reference_gpu(args, rank, world, local, line, cfg):
                     else ("centers_features", "centers"), extra=extra_inputs("cuda"))
     pipe.submit_device(dev_pool[0])
     pipe.sync()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, enabled=rank == 0)
     sampler.start()
     ms, _ = timed_region(pipe, dev_pool, args.steps, args.warmup, host=False, world=world, per_step=per_step)
     ms_e2e, _ = timed_region(pipe, host_pool, args.steps, args.warmup, host=True, world=world, per_step=per_step)

@@ -256,6 +256,8 @@ typedef struct spsk_sa_mma_desc {
                                multiple of 256, and wtiles in the PAIR packing: per layer, 256-wide cout chunks; inside a chunk
                                the rows of pair rank 0 then rank 1 (hidden layers: half of the chunk each; last layer: 128
                                couts each), each as tiles of <= 64 k in the canonical layout */
+    int ovf_tag;            /* fp16 range guard: bit (ovf_tag & 31) of the per-device overflow word is set when a hidden activation or
+                               an fp16 output of this call exceeds 65504 (see spsk_fp16_overflow_poll); appended in ABI 3 */
 } spsk_sa_mma_desc;
 
 /* Launch shape the library picks for a chain (only nlayers / kpad / cpad / split are read): dynamic shared memory,
@@ -294,8 +296,17 @@ typedef struct spsk_pw_desc {
     void *out16; int ld16, n16;
     int o16lo;  /* > 0: out16 also receives the residuals fp16(y - fp16(y)) at columns [o16lo, o16lo + n16) */
     float *out_pm; int ldpm;
+    int ovf_tag;  /* fp16 range guard tag of this call (see spsk_sa_mma_desc.ovf_tag) */
 } spsk_pw_desc;
 SPSK_API int spsk_pw_mma_forward(const spsk_pw_desc *d, spsk_stream_t stream);
+
+/* fp16 range guard.  The tensor-core path stores inter-layer activations as fp16 (largest finite value 65504) where the
+ * reference's TF32 convolutions keep the fp32 exponent range (pointnet2_modules.py:203-211).  Every kernel that stores fp16
+ * (spsk_sa_mma_forward, spsk_pw_mma_forward, spsk_make_twin) ORs bit (ovf_tag & 31) into a per-device word when a value it
+ * stores exceeds that range.  This call SYNCHRONISES the device, returns the word and optionally clears it; the python
+ * modules poll it after an eager forward and re-run the tagged modules on the exact-fp32 kernels (spsk_grouped_linear /
+ * spsk_pointwise_linear), which have no range limit. */
+SPSK_API int spsk_fp16_overflow_poll(unsigned int *mask, int clear);
 
 /* ------------------------------------------------------------------------------------------------
  * Section 3 -- the consumer of the path: rotated IoU / NMS and the fused

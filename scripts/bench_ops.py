@@ -18,13 +18,37 @@ except Exception as e:  # pragma: no cover
     print("reference ops unavailable:", e); ref = None
 
 
-def timeit(fn, reps):
-    fn(); torch.cuda.synchronize()
+def timeit(fn, reps, warm=3):
+    """>= 3 warm-ups (kernel attributes, allocator blocks, caches), then `reps` timed launches between two CUDA events."""
+    for _ in range(warm):
+        out = fn()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps): out = fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps, out
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ours_group_into(feats, idx, out):
+    """spsk_group_points straight through the C-ABI into a PRE-ALLOCATED output (no allocator in the timed region)."""
+    from spsnet_b200._lib import check, lib
+    B, C, N = feats.shape
+    _, M, ns = idx.shape
+    check(lib.spsk_group_points(B, C, N, M, ns, feats.data_ptr(), idx.data_ptr(), out.data_ptr(), _stream()), "group_points")
+    return out
+
+
+def ref_group_into(feats, idx, out):
+    """the reference's pybind entry point (group_points_wrapper, group_points.cpp:30) into the same pre-allocated output."""
+    B, C, N = feats.shape
+    _, M, ns = idx.shape
+    ref.pointnet2.group_points_wrapper(B, C, N, M, ns, feats, idx, out)
+    return out
 
 
 def main():
@@ -39,10 +63,10 @@ def main():
         xyz = torch.from_numpy(np.ascontiguousarray(xyz_np)).cuda()
         for M in (512, 1024, 4096, 16384):
             if M >= N: continue
-            ms, idx = timeit(lambda: pu.furthest_point_sample(xyz, M), 2)
+            ms, idx = timeit(lambda: pu.furthest_point_sample(xyz, M), 2, warm=3 if N * M <= 65536 * 16384 else 1)
             r = {"op": "fps", "B": B, "N": N, "npoint": M, "ours_ms": ms, "us_per_iter": ms * 1e3 / (M - 1)}
-            if ref is not None and N * M <= 65536 * 16384:
-                rms, ridx = timeit(lambda: ref.furthest_point_sample(xyz, M), 1)
+            if ref is not None:
+                rms, ridx = timeit(lambda: ref.furthest_point_sample(xyz, M), 1, warm=1)
                 r.update(ref_ms=rms, speedup=rms / ms, bit_exact=bool(torch.equal(idx, ridx)))
             rows.append(r); print(r, flush=True)
     # ball query + grouping: KITTI layer shapes (N source points, M = N/4 centres)
@@ -54,12 +78,14 @@ def main():
         for radius in (0.2, 0.8, 1.6, 4.8):
             for ns in (16, 32, 64):
                 ms, idx = timeit(lambda: pu.ball_query_msg([radius], [ns], xyz, new_xyz)[0], 5)
-                gms, g = timeit(lambda: pu.grouping_operation(feats, idx), 5)
+                gout = torch.empty((16, 64, M, ns), dtype=torch.float32, device="cuda")
+                gms, g = timeit(lambda: ours_group_into(feats, idx, gout), 5)
+                g = g.clone()
                 r = {"op": "ball_query+group", "B": 16, "N": N, "M": M, "radius": radius, "nsample": ns, "ours_bq_ms": ms, "ours_group_ms": gms,
                      "group_GBps": (g.numel() * 4 + idx.numel() * 4) / gms / 1e6}
                 if ref is not None:
                     rms, ridx = timeit(lambda: ref.ball_query(radius, ns, xyz, new_xyz), 3)
-                    rgms, rg = timeit(lambda: ref.grouping_operation(feats, ridx), 3)
+                    rgms, rg = timeit(lambda: ref_group_into(feats, ridx, gout), 3)
                     r.update(ref_bq_ms=rms, ref_group_ms=rgms, bq_speedup=rms / ms, bit_exact=bool(torch.equal(idx, ridx) and torch.equal(g, rg)))
                 rows.append(r); print(r, flush=True)
     if out_path:

@@ -49,6 +49,7 @@ SIGNATURES = {
     "spsk_sa_mma_forward": [_p, _p],
     "spsk_sa_mma_set_profile": [_p],
     "spsk_pw_mma_forward": [_p, _p],
+    "spsk_fp16_overflow_poll": [C.POINTER(C.c_uint), _i],
     "spsk_boxes_overlap_bev": [_i, _p, _i, _p, _p, _p],
     "spsk_boxes_iou_bev": [_i, _p, _i, _p, _p, _p],
     "spsk_boxes_iou3d": [_i, _p, _i, _p, _p, _p],
@@ -86,7 +87,7 @@ class SaMmaDesc(C.Structure):
         ("nlayers", _i), ("kpad", _i * 4), ("cpad", _i * 4),
         ("wtiles", _p), ("bias", _p), ("cout_last", _i),
         ("out_cm", _p), ("c_total", _i), ("co_off", _i),
-        ("out16", _p), ("ld16", _i), ("co16", _i), ("n16", _i), ("o16lo", _i), ("l0_fused", _i), ("pair", _i),
+        ("out16", _p), ("ld16", _i), ("co16", _i), ("n16", _i), ("o16lo", _i), ("l0_fused", _i), ("pair", _i), ("ovf_tag", _i),
     ]
 
 
@@ -98,7 +99,7 @@ class PwDesc(C.Structure):
         ("x", _p), ("wtiles", _p), ("bias", _p),
         ("out_cm", _p), ("m", _i), ("c_total", _i), ("co_off", _i),
         ("out16", _p), ("ld16", _i), ("n16", _i), ("o16lo", _i),
-        ("out_pm", _p), ("ldpm", _i),
+        ("out_pm", _p), ("ldpm", _i), ("ovf_tag", _i),
     ]
 
 

@@ -77,6 +77,8 @@ class IASSD_Backbone(nn.Module):
                 channel_out += 60  # the vote layer also sees the 60 surface channels (PAGNet_backbone.py:91-92)
             channel_out_list.append(channel_out)
         self.num_point_features = channel_out
+        for k, m in enumerate(self.SA_modules):   # fp16 range guard: which module a flagged tensor-core launch belongs to
+            m._spsk_tag = (k % 31) + 1
 
     # ---- FPS prefetch ----------------------------------------------------------------------------------------------
     # The D-FPS of layer i+1 needs only the CENTRES of layer i, which exist long before layer i's ball query, MLPs and
@@ -128,7 +130,25 @@ class IASSD_Backbone(nn.Module):
         return batch_idx, xyz, features
 
     def forward(self, batch_dict):
-        """batch_dict['points']: (B*N, 1+3+C) rows [batch_idx, x, y, z, feat...], equal N per scene."""
+        """batch_dict['points']: (B*N, 1+3+C) rows [batch_idx, x, y, z, feat...], equal N per scene.
+
+        fp16 range guard (inference, eager): the tensor-core path stores inter-layer activations as fp16; a checkpoint whose
+        BN gains push them beyond 65504 would overflow where the reference's TF32 convolutions do not.  The kernels flag it,
+        this wrapper polls the flag once per forward (one device synchronisation; SPSK_FP16_GUARD=0 or `_spsk_guard = False`
+        turn it off, CUDA-graph capture skips it) and re-runs with the affected modules on the exact-fp32 kernels."""
+        guard = (not self.training and batch_dict["points"].is_cuda and getattr(self, "_spsk_guard", True)
+                 and pointnet2_modules.fp16_guard_enabled())
+        if not guard:
+            return self._forward_impl(batch_dict)
+        out = self._forward_impl(dict(batch_dict))
+        for _ in range(len(self.SA_modules)):
+            if not pointnet2_modules.fp16_guard_check(list(self.SA_modules)):
+                break
+            out = self._forward_impl(dict(batch_dict))
+        batch_dict.update(out)
+        return batch_dict
+
+    def _forward_impl(self, batch_dict):
         batch_size = batch_dict["batch_size"]
         points = batch_dict["points"]
         if points.shape[0] % batch_size != 0:

@@ -17,6 +17,8 @@ namespace spsk {
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);
 void count_launch();
+unsigned int *fp16_overflow_word();   // device address of this device's fp16 range-guard word (api.cu), or nullptr
+constexpr float FP16_MAX = 65504.f;
 
 #define SPSK_REQUIRE(cond, code, ...)            \
     do {                                         \

@@ -24,7 +24,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
 #pragma unroll 1
-    for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin) {   // ~1 s at ~100 cycles per probe
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"

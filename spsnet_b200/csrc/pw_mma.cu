@@ -39,6 +39,7 @@ struct PwArgs {
     float *out_cm; int m, c_total, co_off;
     __half *out16; int ld16, n16;
     float *out_pm; int ldpm;
+    unsigned int *ovf; unsigned int ovf_bit;   // fp16 range guard (api.cu)
 };
 
 template <int PW_STAGES, int PW_LAG, bool SPLIT>
@@ -157,6 +158,7 @@ pw_mma_kernel(const PwArgs a) {
         long long bb = 0;
         int p = 0;
         if (a.out_cm && ok) { bb = row / a.m; p = (int)(row - bb * a.m); }
+        float mx16 = 0.f;   // largest magnitude stored as fp16 by this thread
         for (int c0 = 0; c0 < ncols; c0 += 16) {
             float v[16];
             __syncwarp();
@@ -185,6 +187,7 @@ pw_mma_kernel(const PwArgs a) {
                         uint32_t h[4], l[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
+                            mx16 = fmaxf(fmaxf(mx16, fabsf(v[8 * q + 2 * i])), fabsf(v[8 * q + 2 * i + 1]));
                             const __half2 hh = __floats2half2_rn(v[8 * q + 2 * i], v[8 * q + 2 * i + 1]);
                             const float2 hf = __half22float2(hh);
                             h[i] = *reinterpret_cast<const uint32_t *>(&hh);
@@ -201,6 +204,7 @@ pw_mma_kernel(const PwArgs a) {
                     if (ch0 + c0 + i < a.n) o[i] = v[i];
             }
         }
+        if (mx16 > FP16_MAX && a.ovf) atomicOr(a.ovf, a.ovf_bit);
     }
 
     tc_fence_before();
@@ -248,6 +252,8 @@ extern "C" int spsk_pw_mma_forward(const spsk_pw_desc *d, spsk_stream_t stream) 
                          (reinterpret_cast<uintptr_t>(d->out16) & 15) == 0,
                      SPSK_ERR_INVALID_ARG, "pw_mma: fp16 output needs ld16, n16 multiples of 8, n <= n16 <= ld16, 16-byte alignment");
     a.out_pm = d->out_pm; a.ldpm = d->ldpm;
+    a.ovf = fp16_overflow_word();
+    a.ovf_bit = 1u << (d->ovf_tag & 31);
     if (a.out_pm) SPSK_REQUIRE(d->ldpm >= d->n, SPSK_ERR_INVALID_ARG, "pw_mma: ldpm < n");
     const bool deep = !a.split && a.n_kc >= 12;
     static SmemAttrOnce attr_s, attr_d, attr_x;

@@ -41,14 +41,17 @@ namespace spsk {
 // G = epilogue warpgroups.  G = 1 (192 threads, up to 3 CTAs per SM) for chains whose concurrency comes from co-resident
 // CTAs; G = 2 (320 threads, one CTA per SM) for the wide chains: the two warpgroups take alternate jobs, so two
 // accumulators drain concurrently and every scheduler holds two epilogue warps to hide TMEM / shared-memory latency.
-template <int G, bool PROF>
-__global__ void __launch_bounds__(128 * G + 64, G == 1 ? 3 : 1)
+// SC = the CTA carries a scout warp (streaming chains; see the tabulated issue loop).  Not for the 3-CTAs-per-SM shapes: a
+// seventh warp would round the register allocation up to eight and cap the epilogue warps at 80 registers.
+template <int G, bool PROF, bool SC>
+__global__ void __launch_bounds__(128 * G + 64 + (SC ? 32 : 0), G == 1 ? (SC ? 2 : 3) : 1)
 sa_mma_kernel(const __grid_constant__ SaArgs a) {
-    constexpr int W_PROD = 4 * G, W_MMA = 4 * G + 1;
+    constexpr int W_PROD = 4 * G, W_MMA = 4 * G + 1, W_SCOUT = 4 * G + 2;
     extern __shared__ __align__(128) uint8_t smem[];
     // carve: [header: barriers + tmem slot][XA][XB][weights]
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + MM_HDR - 16);
+    uint32_t *ready_cnt = reinterpret_cast<uint32_t *>(smem + MM_HDR - 32);   // scout -> issuer: schedule entries whose waits are over
     uint4 *sched = reinterpret_cast<uint4 *>(smem + MM_HDR);               // a.sched_n entries (streaming chains)
     uint8_t *xa = smem + MM_HDR + ((a.sched_n * 16 + 127) & ~127);
     uint8_t *xb = xa + a.xa_bytes;
@@ -79,6 +82,40 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
         for (int s = 0; s < MM_MAX_STAGES; ++s) { mbar_init(WL_FULL(s), 1); mbar_init(WL_EMPTY(s), 1); }
         mbar_init(HID_DONE, 1);
         mbar_init_fence();
+        *ready_cnt = 0u;
+    }
+    if (warp == W_MMA && a.sched_n > 0 && (tid & 31) == 0) {
+        // Streaming chains: the per-tile schedule (one entry per weight tile) is identical for every tile, so it is tabulated
+        // once in shared memory (read by the issuing warp and by the scout warp):
+        //   .x = activation descriptor lo of the tile's first K block   .y = instruction descriptor
+        //   .z = activation desc hi | weight desc hi << 16
+        //   .w = nk16[0:3) first_kc[3] last_kc[4] cc0[5] need_chunk[6:11) lring[11] hid_done[12] last_layer[13] xbuf[14] layer_start[15]
+        int e = 0;
+        for (int l = 0; l < nL; ++l) {
+            const SaLayer &Ly = a.L[l];
+            const bool last = (l == nL - 1);
+            const uint32_t x_lo0 = umma_desc_lo(smem_u32((l & 1) ? xb : xa), 128u);
+            const uint32_t x_hi = umma_desc_hi((uint32_t)Ly.xw * 16u);
+            for (int cci = 0; cci < Ly.n_cc; ++cci) {
+                const int cc = chunk_of(l, cci, Ly.n_cc);
+                const int ncols = min(128, Ly.cpad - cc * 128);
+                for (int kc = 0; kc < Ly.n_kc; ++kc, ++e) {
+                    const int kw = min(64, Ly.vk - kc * 64);
+                    const int nk16 = kw >> 4;
+                    uint32_t f = (uint32_t)nk16;
+                    if (kc == 0) f |= 1u << 3;
+                    if (kc == Ly.n_kc - 1) f |= 1u << 4;
+                    if (cci == 0) f |= (1u << 5) | ((uint32_t)((kc * 4 + nk16 - 1) >> 2) << 6);
+                    if (a.lstages > 0 && last) f |= 1u << 11;
+                    if (a.lstages > 0 && l == nL - 2 && cci == Ly.n_cc - 1 && kc == Ly.n_kc - 1) f |= 1u << 12;
+                    if (last) f |= 1u << 13;
+                    f |= (uint32_t)(l & 1) << 14;
+                    if (cci == 0 && kc == 0) f |= 1u << 15;
+                    const uint32_t idesc = last ? umma_idesc(128, MM_ROWS) : umma_idesc(128, ncols);
+                    sched[e] = make_uint4(x_lo0 + (uint32_t)kc * 64u, idesc, x_hi | (umma_desc_hi((uint32_t)kw * 16u) << 16), f);
+                }
+            }
+        }
     }
     if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
     tc_fence_before();
@@ -200,43 +237,17 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                 }
             }
         } else if (a.sched_n > 0) {
-            // Streaming chains: the per-tile schedule (one entry per weight tile) is identical for every tile, so it is
-            // tabulated once in shared memory and the issue loop does no address arithmetic or parameter loads: per entry
-            // one 16-byte read, the waits, <= 4 MMAs, the commits.  (The general loop below executes ~120 instructions
-            // per weight tile on ONE warp -- ~2x the duration of the four 128x128x16 MMAs it issues.)
-            //   .x = activation descriptor lo of the tile's first K block   .y = instruction descriptor
-            //   .z = activation desc hi | weight desc hi << 16
-            //   .w = nk16[0:3) first_kc[3] last_kc[4] cc0[5] need_chunk[6:11) lring[11] hid_done[12] last_layer[13] xbuf[14] layer_start[15]
+            // Streaming chains: the issue loop reads the tabulated schedule (built above): per entry one 16-byte read, <= 4 MMAs,
+            // the commits -- no address arithmetic, no parameter loads.
+            //
+            // It also does NO mbarrier wait when the scout warp is on (default).  Measured on this GPU (round 2,
+            // scripts/dev/issue_loop_probe.cu): one mbarrier.try_wait on an ALREADY COMPLETED barrier costs the issuing thread
+            // ~220 cycles -- almost the 264 cycles of the four 128x128x16 MMAs it guards -- and the loop needs one per weight tile
+            // plus one per accumulator and per activation chunk.  The scout warp walks the same schedule, takes every wait in
+            // program order (accumulator free, activation chunks landed, weight stage landed) and publishes the number of
+            // entries that are clear with a release store; the issuer compares a cached copy and re-reads the counter with an
+            // acquire load (one shared-memory load, which usually clears several tiles at once) only when it catches up.
             const bool leader = elect_one();
-            if ((tid & 31) == 0) {
-                int e = 0;
-                for (int l = 0; l < nL; ++l) {
-                    const SaLayer &Ly = a.L[l];
-                    const bool last = (l == nL - 1);
-                    const uint32_t x_lo0 = umma_desc_lo(smem_u32((l & 1) ? xb : xa), 128u);
-                    const uint32_t x_hi = umma_desc_hi((uint32_t)Ly.xw * 16u);
-                    for (int cci = 0; cci < Ly.n_cc; ++cci) {
-                        const int cc = chunk_of(l, cci, Ly.n_cc);
-                        const int ncols = min(128, Ly.cpad - cc * 128);
-                        for (int kc = 0; kc < Ly.n_kc; ++kc, ++e) {
-                            const int kw = min(64, Ly.vk - kc * 64);
-                            const int nk16 = kw >> 4;
-                            uint32_t f = (uint32_t)nk16;
-                            if (kc == 0) f |= 1u << 3;
-                            if (kc == Ly.n_kc - 1) f |= 1u << 4;
-                            if (cci == 0) f |= (1u << 5) | ((uint32_t)((kc * 4 + nk16 - 1) >> 2) << 6);
-                            if (a.lstages > 0 && last) f |= 1u << 11;
-                            if (a.lstages > 0 && l == nL - 2 && cci == Ly.n_cc - 1 && kc == Ly.n_kc - 1) f |= 1u << 12;
-                            if (last) f |= 1u << 13;
-                            f |= (uint32_t)(l & 1) << 14;
-                            if (cci == 0 && kc == 0) f |= 1u << 15;
-                            const uint32_t idesc = last ? umma_idesc(128, MM_ROWS) : umma_idesc(128, ncols);
-                            sched[e] = make_uint4(x_lo0 + (uint32_t)kc * 64u, idesc, x_hi | (umma_desc_hi((uint32_t)kw * 16u) << 16), f);
-                        }
-                    }
-                }
-            }
-            __syncwarp();
             ProfT<PROF> pf;
             pf.init(a.prof != nullptr && leader);
             const long long t_start = pf.now();
@@ -247,6 +258,9 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
             uint8_t *lst = ((nL - 2) & 1) ? xb : xa;
             const uint32_t nbmask = (uint32_t)a.nbuf - 1u;
             const int nent = a.sched_n;
+            const bool scout = SC && a.scout != 0;
+            const uint32_t ready_addr = smem_u32(ready_cnt);
+            uint32_t done = 0u, avail = 0u;   // entries issued so far / entries known to be clear
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 int xwait = 0, buf = 0;
                 uint32_t d_tmem = tmem_base;
@@ -257,22 +271,22 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                     if (f & (1u << 3)) {
                         buf = (int)(job & nbmask);
                         const uint32_t use = job >> a.nbuf_log2;
-                        if (use > 0) { const long long t0 = pf.now(); mbar_wait(ACC_EMPTY(buf), (use - 1) & 1u); pf.add(PF_MMA_ACC_EMPTY, t0); }
+                        if (!scout && use > 0) { const long long t0 = pf.now(); mbar_wait(ACC_EMPTY(buf), (use - 1) & 1u); pf.add(PF_MMA_ACC_EMPTY, t0); }
                         d_tmem = tmem_base + (uint32_t)(buf * 128);
                     }
                     uint32_t wbase, wempty;
                     if (f & (1u << 11)) {
-                        { const long long t0 = pf.now(); mbar_wait(WL_FULL(ls), lph); pf.add(PF_MMA_ISSUE, t0); }   // (profile slot "mma_issue" = last-layer ring waits in this path)
+                        if (!scout) { const long long t0 = pf.now(); mbar_wait(WL_FULL(ls), lph); pf.add(PF_MMA_ISSUE, t0); }   // (profile slot "mma_issue" = last-layer ring waits in this path)
                         wbase = smem_u32(lst + (size_t)ls * MM_STAGE_BYTES);
                         wempty = WL_EMPTY(ls);
                         if (++ls == a.lstages) { ls = 0; lph ^= 1u; }
                     } else {
-                        { const long long t0 = pf.now(); mbar_wait(W_FULL(ws), wph); pf.add(PF_MMA_W_FULL, t0); }
+                        if (!scout) { const long long t0 = pf.now(); mbar_wait(W_FULL(ws), wph); pf.add(PF_MMA_W_FULL, t0); }
                         wbase = smem_u32(wst + (size_t)ws * MM_STAGE_BYTES);
                         wempty = W_EMPTY(ws);
                         if (++ws == a.nstages) { ws = 0; wph ^= 1u; }
                     }
-                    if (f & (1u << 5)) {
+                    if (!scout && (f & (1u << 5))) {
                         const int need = (int)((f >> 6) & 31u);
                         const int xbuf = (int)((f >> 14) & 1u);
                         while (xwait <= need) {
@@ -282,6 +296,16 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                             xph[xbuf] ^= (1u << xwait);
                             ++xwait;
                         }
+                    }
+                    ++done;
+                    if (scout && avail < done) {
+                        const long long t0 = pf.now();
+                        uint32_t spin = 0u;
+                        do {
+                            asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(avail) : "r"(ready_addr) : "memory");
+                            if (++spin > (1u << 26)) __trap();   // a protocol bug traps instead of hanging the GPU
+                        } while (avail < done);
+                        pf.add(PF_MMA_W_FULL, t0);
                     }
                     tc_fence_after();
                     if (leader) {
@@ -409,6 +433,52 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
             }
             pf.add(PF_MMA_TOTAL, t_start);
             pf.flush(a.prof);
+        }
+    } else if (SC && warp == W_SCOUT) {
+        // ================= scout: every wait of the tabulated issue loop, taken ahead of the issuer =================
+        // Same schedule, same order, same phase bookkeeping as the issuer; after the waits of entry e are over it publishes
+        // e + 1 (release store: the bulk copies and epilogue stores it observed through the barriers are visible to whoever
+        // acquires the counter).  It can never run more than one barrier phase ahead: a stage / accumulator / activation chunk
+        // is only refilled after the ISSUER has consumed it, and the issuer consumes nothing the scout has not cleared.
+        if (a.sched_n > 0 && a.scout && !a.narrow) {
+            uint32_t job = 0, count = 0u;
+            int ws = 0, ls = 0;
+            uint32_t wph = 0u, lph = 0u;
+            uint32_t xph[2] = {0u, 0u};
+            const uint32_t nbmask = (uint32_t)a.nbuf - 1u;
+            const int nent = a.sched_n;
+            const uint32_t ready_addr = smem_u32(ready_cnt);
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                int xwait = 0;
+                for (int e = 0; e < nent; ++e) {
+                    const uint32_t f = sched[e].w;
+                    if (f & (1u << 15)) xwait = 0;
+                    if (f & (1u << 3)) {
+                        const int buf = (int)(job & nbmask);
+                        const uint32_t use = job >> a.nbuf_log2;
+                        if (use > 0) mbar_wait(ACC_EMPTY(buf), (use - 1) & 1u);
+                    }
+                    if (f & (1u << 5)) {
+                        const int need = (int)((f >> 6) & 31u);
+                        const int xbuf = (int)((f >> 14) & 1u);
+                        while (xwait <= need) {
+                            mbar_wait(XR(xbuf, xwait), (xph[xbuf] >> xwait) & 1u);
+                            xph[xbuf] ^= (1u << xwait);
+                            ++xwait;
+                        }
+                    }
+                    if (f & (1u << 11)) {
+                        mbar_wait(WL_FULL(ls), lph);
+                        if (++ls == a.lstages) { ls = 0; lph ^= 1u; }
+                    } else {
+                        mbar_wait(W_FULL(ws), wph);
+                        if (++ws == a.nstages) { ws = 0; wph ^= 1u; }
+                    }
+                    ++count;
+                    if ((tid & 31) == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(ready_addr), "r"(count) : "memory");
+                    if (f & (1u << 4)) ++job;
+                }
+            }
         }
     } else {
         // ================= gather + epilogue (threads 0..127; thread = row / TMEM lane) =================
@@ -571,6 +641,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                     tc_fence_after();
                     const long long t_w = pf.now();
                     const uint32_t taddr = tmem_base + lane_field + (uint32_t)(buf * 128);
+                    float hmx = 0.f;   // fp16 range guard: largest hidden activation this thread stores in this job
                     if (!a.split) {
                         for (int h0 = 0; h0 < ncols; h0 += 64) {   // one 64-wide K chunk of the next operand at a time
                             const int hend = min(ncols, h0 + 64);
@@ -579,14 +650,14 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                                 float v[32];
                                 tmem_ld32(taddr + (uint32_t)c0, v);
                                 const int col = cc * 128 + c0;
-                                store_hidden16(v, bias + col, xrow + (size_t)(col >> 3) * 128);
-                                store_hidden16(v + 16, bias + col + 16, xrow + (size_t)((col >> 3) + 2) * 128);
+                                store_hidden16(v, bias + col, xrow + (size_t)(col >> 3) * 128, hmx);
+                                store_hidden16(v + 16, bias + col + 16, xrow + (size_t)((col >> 3) + 2) * 128, hmx);
                             }
                             if (c0 < hend) {
                                 float v[16];
                                 tmem_ld16(taddr + (uint32_t)c0, v);
                                 const int col = cc * 128 + c0;
-                                store_hidden16(v, bias + col, xrow + (size_t)(col >> 3) * 128);
+                                store_hidden16(v, bias + col, xrow + (size_t)(col >> 3) * 128, hmx);
                             }
                             fence_proxy_async();
                             mbar_arrive(XR(obuf, (cc * 128 + h0) >> 6));
@@ -597,17 +668,18 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                         for (; c0 + 32 <= ncols; c0 += 32) {
                             float v[32];
                             tmem_ld32(taddr + (uint32_t)c0, v);
-                            store_hidden16_split(v, bias + c0, xrow + (size_t)(c0 >> 3) * 128, xlo + (size_t)(c0 >> 3) * 128);
-                            store_hidden16_split(v + 16, bias + c0 + 16, xrow + (size_t)((c0 >> 3) + 2) * 128, xlo + (size_t)((c0 >> 3) + 2) * 128);
+                            store_hidden16_split(v, bias + c0, xrow + (size_t)(c0 >> 3) * 128, xlo + (size_t)(c0 >> 3) * 128, hmx);
+                            store_hidden16_split(v + 16, bias + c0 + 16, xrow + (size_t)((c0 >> 3) + 2) * 128, xlo + (size_t)((c0 >> 3) + 2) * 128, hmx);
                         }
                         if (c0 < ncols) {
                             float v[16];
                             tmem_ld16(taddr + (uint32_t)c0, v);
-                            store_hidden16_split(v, bias + c0, xrow + (size_t)(c0 >> 3) * 128, xlo + (size_t)(c0 >> 3) * 128);
+                            store_hidden16_split(v, bias + c0, xrow + (size_t)(c0 >> 3) * 128, xlo + (size_t)(c0 >> 3) * 128, hmx);
                         }
                         fence_proxy_async();
                         for (int c = 0; c < Ln.n_xc; ++c) mbar_arrive(XR(obuf, c));
                     }
+                    if (hmx > FP16_MAX && a.ovf) atomicOr(a.ovf, a.ovf_bit);
                     tc_fence_before();
                     mbar_arrive(ACC_EMPTY(buf));
                     pf.add(PF_EPI_WORK_HID, t_w);
@@ -643,6 +715,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                     if (ns == 32) pool_chunk<32>(taddr, o);
                     else if (ns == 16) pool_chunk<16>(taddr, o);
                     else pool_chunk_any(taddr, o, ns);
+                    if (o.mx16 > FP16_MAX && a.ovf) atomicOr(a.ovf, a.ovf_bit);
                     tc_fence_before();
                     mbar_arrive(ACC_EMPTY(buf));
                     pf.add(PF_EPI_WORK_POOL, t_w);
@@ -665,7 +738,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
 
 // ---- feature twin: (b, c, n) f32 channel-major -> (b, n, ld) fp16 point-major (zero padded) -------------
 __global__ void __launch_bounds__(256)
-make_twin_kernel(int c, int n, int cpad8, const float *__restrict__ in, __half *__restrict__ out) {
+make_twin_kernel(int c, int n, int cpad8, const float *__restrict__ in, __half *__restrict__ out, unsigned int *ovf) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -677,7 +750,10 @@ make_twin_kernel(int c, int n, int cpad8, const float *__restrict__ in, __half *
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
         const int ni = n0 + i, ci = c0 + tx;
-        if (ni < n && ci < cpad8) out[((size_t)b * n + ni) * cpad8 + ci] = __float2half_rn(tile[tx][i]);
+        if (ni < n && ci < cpad8) {
+            out[((size_t)b * n + ni) * cpad8 + ci] = __float2half_rn(tile[tx][i]);
+            if (fabsf(tile[tx][i]) > FP16_MAX && ovf) atomicOr(ovf, 1u);   // untagged (bit 0): the caller's input does not fit fp16
+        }
     }
 }
 
@@ -737,7 +813,9 @@ static int sa_plan(const spsk_sa_mma_desc *d, SaPlan *P) {
         if (xtot + P->w_total <= per) { *resident = 1; *nstages = 1; *smem = xtot + P->w_total; return true; }
         const int st = (per - xtot) / MM_STAGE_BYTES;
         if (st < 2) return false;
-        *resident = 0; *nstages = st > MM_MAX_STAGES ? MM_MAX_STAGES : st; *smem = xtot + *nstages * MM_STAGE_BYTES;
+        int cap = MM_MAX_STAGES;
+        if (const char *e = getenv("SPSK_SA_MAX_STAGES")) cap = max(2, min(MM_MAX_STAGES, atoi(e)));   // tuning / sensitivity measurements
+        *resident = 0; *nstages = st > cap ? cap : st; *smem = xtot + *nstages * MM_STAGE_BYTES;
         return true;
     };
     int ctas = 0, cmax = pair ? 1 : 3;
@@ -791,7 +869,7 @@ extern "C" int spsk_make_twin(int b, int c, int n, int cpad8, const float *featu
     if (b == 0 || n == 0) return SPSK_OK;
     SPSK_REQUIRE(features && twin, SPSK_ERR_INVALID_ARG, "make_twin: null pointer");
     dim3 grid((n + 31) / 32, (cpad8 + 31) / 32, b);
-    make_twin_kernel<<<grid, 256, 0, as_stream(stream)>>>(c, n, cpad8, features, reinterpret_cast<__half *>(twin));
+    make_twin_kernel<<<grid, 256, 0, as_stream(stream)>>>(c, n, cpad8, features, reinterpret_cast<__half *>(twin), fp16_overflow_word());
     SPSK_LAUNCH_CHECK("make_twin_kernel");
     return SPSK_OK;
 }
@@ -853,6 +931,8 @@ extern "C" int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stre
     a.ntiles = (int)ntiles;
     a.lstages = P.lstages;
     a.sched_n = P.sched_n;
+    static const bool no_scout = getenv("SPSK_SA_NO_SCOUT") != nullptr;   // A/B knob: the issuer takes its own waits (round-1 loop)
+    a.scout = no_scout ? 0 : 1;
     a.rot_last = (P.L[d->nlayers - 1].n_cc > 1 && getenv("SPSK_SA_ROT")) ? 1 : 0;   // opt-in: measured neutral on B200 (the weight stream is not L2 hot-line bound)
     a.l0_fused = d->l0_fused ? 1 : 0;
     a.l0_off = P.l0_off;
@@ -877,7 +957,8 @@ extern "C" int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stre
         SPSK_REQUIRE(d->n16 >= d->cout_last && d->n16 <= d->cpad[d->nlayers - 1] && d->co16 >= 0 && d->co16 + d->n16 <= d->ld16, SPSK_ERR_INVALID_ARG,
                      "sa_mma: fp16 output window [co16, co16 + n16) outside ld16 or wider than the last layer");
     a.prof = g_sa_prof;
-    a.prof = g_sa_prof;
+    a.ovf = fp16_overflow_word();
+    a.ovf_bit = 1u << (d->ovf_tag & 31);
     if (d->pair) {
         a.ntiles = (int)((a.rows + 255) / 256);   // 256-row tiles, one per CTA pair
         return spsk_sa_mma_pair_launch(a, P.smem, as_stream(stream));
@@ -887,26 +968,22 @@ extern "C" int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stre
     const int slots = SPSK_NUM_SMS * P.ctas * mult;
     const int grid = a.ntiles < slots ? a.ntiles : slots;
     const bool two_groups = P.ctas == 1 && !getenv("SPSK_SA_ONE_GROUP");
-    static SmemAttrOnce attr1, attr2;
+    const bool sc = a.scout && a.sched_n > 0 && !a.narrow && (two_groups || P.ctas <= 2);
+    a.scout = sc ? 1 : 0;
+#define SPSK_SA_LAUNCH(GV, PV, SCV)                                                                                          \
+    do {                                                                                                                    \
+        static SmemAttrOnce attr;                                                                                           \
+        if (int rc = attr.ensure(reinterpret_cast<const void *>(sa_mma_kernel<GV, PV, SCV>), 227 * 1024, "sa_mma_kernel")) return rc; \
+        sa_mma_kernel<GV, PV, SCV><<<grid, 128 * GV + 64 + (SCV ? 32 : 0), P.smem, as_stream(stream)>>>(a);                   \
+    } while (0)
     if (two_groups) {
-        if (a.prof) {
-            static SmemAttrOnce attr2p;
-            if (int rc = attr2p.ensure(reinterpret_cast<const void *>(sa_mma_kernel<2, true>), 227 * 1024, "sa_mma_kernel<2,prof>")) return rc;
-            sa_mma_kernel<2, true><<<grid, 320, P.smem, as_stream(stream)>>>(a);
-        } else {
-            if (int rc = attr2.ensure(reinterpret_cast<const void *>(sa_mma_kernel<2, false>), 227 * 1024, "sa_mma_kernel<2>")) return rc;
-            sa_mma_kernel<2, false><<<grid, 320, P.smem, as_stream(stream)>>>(a);
-        }
+        if (a.prof) { if (sc) SPSK_SA_LAUNCH(2, true, true); else SPSK_SA_LAUNCH(2, true, false); }
+        else { if (sc) SPSK_SA_LAUNCH(2, false, true); else SPSK_SA_LAUNCH(2, false, false); }
     } else {
-        if (a.prof) {
-            static SmemAttrOnce attr1p;
-            if (int rc = attr1p.ensure(reinterpret_cast<const void *>(sa_mma_kernel<1, true>), 227 * 1024, "sa_mma_kernel<1,prof>")) return rc;
-            sa_mma_kernel<1, true><<<grid, 192, P.smem, as_stream(stream)>>>(a);
-        } else {
-            if (int rc = attr1.ensure(reinterpret_cast<const void *>(sa_mma_kernel<1, false>), 227 * 1024, "sa_mma_kernel<1>")) return rc;
-            sa_mma_kernel<1, false><<<grid, 192, P.smem, as_stream(stream)>>>(a);
-        }
+        if (a.prof) { if (sc) SPSK_SA_LAUNCH(1, true, true); else SPSK_SA_LAUNCH(1, true, false); }
+        else { if (sc) SPSK_SA_LAUNCH(1, false, true); else SPSK_SA_LAUNCH(1, false, false); }
     }
+#undef SPSK_SA_LAUNCH
     SPSK_LAUNCH_CHECK("sa_mma_kernel");
     return SPSK_OK;
 }

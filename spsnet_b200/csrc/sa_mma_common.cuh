@@ -6,7 +6,7 @@
 namespace spsk {
 
 constexpr int MM_ROWS = 128;          // grouped rows per tile
-constexpr int MM_THREADS = 192;       // G = 1: 4 gather/epilogue warps + producer + mma;  G = 2: 8 + 2 = 320 threads
+constexpr int MM_THREADS = 224;       // G = 1: 4 gather/epilogue warps + producer + mma + scout;  G = 2: 8 + 3 = 352 threads
 constexpr int MM_STAGE_BYTES = 16384; // largest weight tile: [128 cout][64 k] fp16
 constexpr int MM_MAX_LAYERS = 4;
 constexpr int MM_MAX_STAGES = 8;
@@ -36,6 +36,7 @@ struct SaArgs {
     int nstages, resident, w_total, tmem_cols, nbuf, nbuf_log2;
     int l0_fused, l0_off;   // split chains: layer 0 (K <= 11 real inputs) is evaluated in fp32 by the gather threads from the
                             // [16][cpad0] fp32 weights + bias appended to the resident weights at byte l0_off; the MMA chain starts at layer 1
+    int scout;       // tabulated issue loop: the scout warp takes every mbarrier wait and publishes a ready counter
     int rot_last;    // rotate the last layer's cout-chunk order by blockIdx (de-synchronises the CTAs' weight streams)
     int sched_n;     // > 0: streaming chain whose per-tile MMA schedule (sched_n weight tiles) is tabulated in shared memory
     int narrow;      // resident chain with one job per layer: the MMA warp runs the register-resident fast loop
@@ -52,6 +53,8 @@ struct SaArgs {
     __half *out16;        // (b*m, ld16) or null
     int ld16, co16, n16, o16lo;
     unsigned long long *prof;   // optional per-role wait/work cycle counters (spsk_sa_mma_set_profile), null = off
+    unsigned int *ovf;          // fp16 range guard word of this device (may be null) and this call's tag bit
+    unsigned int ovf_bit;
 };
 
 // byte offset of weight tile (cc, kc) inside a layer: chunks of 128 couts are contiguous (cc-major), inside a chunk
@@ -60,15 +63,20 @@ __device__ __forceinline__ int wtile_off(const SaLayer &Ly, int cc, int kc, int 
     return Ly.w_off + (128 * cc * Ly.vk + ncols * 64 * kc) * 2;
 }
 
-// 16 accumulator columns -> + bias -> ReLU -> fp16 -> two 16-byte stores into the next operand (K-major)
-__device__ __forceinline__ void store_hidden16(const float *v, const float *bias16, uint8_t *dst) {
+// 16 accumulator columns -> + bias -> ReLU -> fp16 -> two 16-byte stores into the next operand (K-major).
+// `mx` collects the largest value seen (fp16 range guard: the caller flags > 65504 once per job; 3-input FMNMX, half an
+// instruction per value).
+__device__ __forceinline__ void store_hidden16(const float *v, const float *bias16, uint8_t *dst, float &mx) {
     const float4 *b4 = reinterpret_cast<const float4 *>(bias16);
     uint32_t h[8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const float4 bb = __ldg(b4 + i);
-        h[2 * i] = pack_h2_relu(v[4 * i] + bb.x, v[4 * i + 1] + bb.y);
-        h[2 * i + 1] = pack_h2_relu(v[4 * i + 2] + bb.z, v[4 * i + 3] + bb.w);
+        const float s0 = v[4 * i] + bb.x, s1 = v[4 * i + 1] + bb.y, s2 = v[4 * i + 2] + bb.z, s3 = v[4 * i + 3] + bb.w;
+        mx = fmaxf(fmaxf(mx, s0), s1);
+        mx = fmaxf(fmaxf(mx, s2), s3);
+        h[2 * i] = pack_h2_relu(s0, s1);
+        h[2 * i + 1] = pack_h2_relu(s2, s3);
     }
     *reinterpret_cast<uint4 *>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4 *>(dst + 128) = make_uint4(h[4], h[5], h[6], h[7]);
@@ -86,7 +94,7 @@ __device__ __forceinline__ void split8(const float *y, uint4 &hi, uint4 &lo) {
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
-__device__ __forceinline__ void store_hidden16_split(const float *v, const float *bias16, uint8_t *dst_hi, uint8_t *dst_lo) {
+__device__ __forceinline__ void store_hidden16_split(const float *v, const float *bias16, uint8_t *dst_hi, uint8_t *dst_lo, float &mx) {
     const float4 *b4 = reinterpret_cast<const float4 *>(bias16);
     float y[16];
 #pragma unroll
@@ -94,6 +102,8 @@ __device__ __forceinline__ void store_hidden16_split(const float *v, const float
         const float4 bb = __ldg(b4 + i);
         y[4 * i] = fmaxf(v[4 * i] + bb.x, 0.f); y[4 * i + 1] = fmaxf(v[4 * i + 1] + bb.y, 0.f);
         y[4 * i + 2] = fmaxf(v[4 * i + 2] + bb.z, 0.f); y[4 * i + 3] = fmaxf(v[4 * i + 3] + bb.w, 0.f);
+        mx = fmaxf(fmaxf(mx, y[4 * i]), y[4 * i + 1]);
+        mx = fmaxf(fmaxf(mx, y[4 * i + 2]), y[4 * i + 3]);
     }
     uint4 h0, l0, h1, l1;
     split8(y, h0, l0);
@@ -107,6 +117,7 @@ __device__ __forceinline__ void store_hidden16_split(const float *v, const float
 // Last-layer epilogue of one 128-cout chunk: thread = cout; max over each centre's NS consecutive columns,
 // + bias, ReLU, store.  The output cursors advance incrementally with the centre.
 struct PoolOut {
+    float mx16 = 0.f;   // largest value written as fp16 (range guard)
     float bv;
     bool w32, w16;
     float *outc;
@@ -120,6 +131,7 @@ struct PoolOut {
         if (q < qmax) {
             if (w32) *outc = y;
             if (w16) {
+                mx16 = fmaxf(mx16, y);
                 const __half h = __float2half_rn(y);
                 *out16 = h;
                 if (o16lo > 0) out16[o16lo] = __float2half_rn(y - __half2float(h));

@@ -343,6 +343,7 @@ sa_mma_pair_kernel(const __grid_constant__ SaArgs a) {
                     tc_fence_after();
                     const long long t_w = pf.now();
                     const uint32_t taddr = tmem_base + lane_field + (uint32_t)(buf * 256);
+                    float hmx = 0.f;   // fp16 range guard (see sa_mma.cu)
                     for (int h0 = 0; h0 < cw; h0 += 64) {
                         const int hend = min(cw, h0 + 64);
                         int c0 = h0;
@@ -350,18 +351,19 @@ sa_mma_pair_kernel(const __grid_constant__ SaArgs a) {
                             float v[32];
                             tmem_ld32(taddr + (uint32_t)c0, v);
                             const int col = cc * 256 + c0;
-                            store_hidden16(v, bias + col, xrow + (size_t)(col >> 3) * 128);
-                            store_hidden16(v + 16, bias + col + 16, xrow + (size_t)((col >> 3) + 2) * 128);
+                            store_hidden16(v, bias + col, xrow + (size_t)(col >> 3) * 128, hmx);
+                            store_hidden16(v + 16, bias + col + 16, xrow + (size_t)((col >> 3) + 2) * 128, hmx);
                         }
                         if (c0 < hend) {
                             float v[16];
                             tmem_ld16(taddr + (uint32_t)c0, v);
                             const int col = cc * 256 + c0;
-                            store_hidden16(v, bias + col, xrow + (size_t)(col >> 3) * 128);
+                            store_hidden16(v, bias + col, xrow + (size_t)(col >> 3) * 128, hmx);
                         }
                         fence_proxy_async();
                         mbar_arrive(XR(obuf, (cc * 256 + h0) >> 6));
                     }
+                    if (hmx > FP16_MAX && a.ovf) atomicOr(a.ovf, a.ovf_bit);
                     tc_fence_before();
                     mbar_arrive(ACC_EMPTY(buf));
                     pf.add(PF_EPI_WORK_HID, t_w);
@@ -395,6 +397,7 @@ sa_mma_pair_kernel(const __grid_constant__ SaArgs a) {
                     if (ns == 32) pool_chunk<32, PR_ROWS>(taddr, o);
                     else if (ns == 16) pool_chunk<16, PR_ROWS>(taddr, o);
                     else pool_chunk_any(taddr, o, ns, PR_ROWS);
+                    if (o.mx16 > FP16_MAX && a.ovf) atomicOr(a.ovf, a.ovf_bit);
                     tc_fence_before();
                     mbar_arrive(ACC_EMPTY(buf));
                     pf.add(PF_EPI_WORK_POOL, t_w);

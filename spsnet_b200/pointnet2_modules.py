@@ -105,10 +105,50 @@ class _Folded:
         return out
 
 
-def mlp_backend() -> str:
+def mlp_backend(module: nn.Module | None = None) -> str:
     """'mma' (default): grouped shared MLPs on the tcgen05 tensor cores (fp16 operands, fp32 accumulate);
-    'ffma': the exact-fp32 CUDA-core kernels.  Set SPSK_MLP=ffma to force the latter."""
+    'ffma': the exact-fp32 CUDA-core kernels.  Set SPSK_MLP=ffma to force the latter everywhere; a module whose
+    `_spsk_exact` attribute is set (the fp16 range guard found its activations beyond 65504, see
+    `fp16_guard_check`) uses the exact kernels on its own."""
+    if module is not None and getattr(module, "_spsk_exact", False):
+        return "ffma"
     return os.environ.get("SPSK_MLP", "mma").lower()
+
+
+def _tag(module: nn.Module) -> None:
+    """Every tensor-core launch issued from here on carries this module's fp16-range-guard tag (pointnet2_utils)."""
+    pu.current_ovf_tag = int(getattr(module, "_spsk_tag", 0)) & 31
+
+
+def fp16_guard_enabled() -> bool:
+    """The eager, inference-mode forward of the backbones polls the fp16 range-guard word once (ONE device synchronisation
+    per forward).  Off inside CUDA-graph capture (BackbonePipeline checks while it warms up, before it captures) and with
+    SPSK_FP16_GUARD=0."""
+    return os.environ.get("SPSK_FP16_GUARD", "1") != "0" and not torch.cuda.is_current_stream_capturing()
+
+
+def fp16_guard_check(modules) -> bool:
+    """Poll the fp16 range-guard word (synchronises).  When a tensor-core kernel stored a value beyond the fp16 range since
+    the last poll, switch the modules whose tag bit is set (all of them if the untagged bit 0 is set) to the exact-fp32
+    kernels for good and return True: the caller re-runs its forward, which then reproduces the reference's finite fp32
+    result (pointnet2_modules.py:203-211 of the reference keeps the fp32 exponent range under TF32)."""
+    mask = pu.fp16_overflow(clear=True)
+    if not mask:
+        return False
+    hit = False
+    for m in modules:
+        t = int(getattr(m, "_spsk_tag", 0)) & 31
+        if (mask >> t) & 1 or (mask & 1):
+            if not getattr(m, "_spsk_exact", False):
+                m._spsk_exact = True
+                hit = True
+    if not hit:   # every flagged module is already exact: the flag came from somewhere else (e.g. a stale word)
+        return False
+    import warnings
+
+    warnings.warn("spsnet_b200: activations beyond the fp16 range (65504) on the tensor-core path; the affected set-abstraction "
+                  "modules now run on the exact-fp32 kernels", RuntimeWarning)
+    return True
 
 
 def _fused_ok(module: nn.Module, *tensors) -> bool:
@@ -275,7 +315,8 @@ class _PointnetSAModuleBase(nn.Module):
                     idxs.append(pu.ball_query(g.radius, g.nsample, xyz, new_xyz))
         c_feat = features.shape[1] if features is not None else 0
         packs = [None] * len(chains)
-        if mlp_backend() == "mma" and pool == 1:
+        _tag(self)
+        if mlp_backend(self) == "mma" and pool == 1:
             for si, (g, chain, idx) in enumerate(zip(self.groupers, chains, idxs)):
                 ns = idx.shape[2]
                 if ns <= 128 and (ns & (ns - 1)) == 0:
@@ -334,7 +375,7 @@ class _PointnetSAModuleBase(nn.Module):
         """aggregation_layer over the pooled MSG features (reference :447-449).  Tensor-core path: fp16 rows (values +
         residuals) in, (B, C, M) fp32 + its fp16 point-major twin out (the twin feeds the confidence GEMMs and the next
         layer's gather); hi + lo arithmetic keeps this layer fp32-grade."""
-        if _fused_ok(self, out_cm) and mlp_backend() == "mma":
+        if _fused_ok(self, out_cm) and mlp_backend(self) == "mma":
             if out16 is not None:
                 xlo = out16.shape[1] // 2
             else:
@@ -347,7 +388,7 @@ class _PointnetSAModuleBase(nn.Module):
 
     def _confidence(self, new_features):
         """confidence_layers -> (B, npoint, num_class) (reference :454-455, incl. the transpose)."""
-        if _fused_ok(self, new_features) and mlp_backend() == "mma":
+        if _fused_ok(self, new_features) and mlp_backend(self) == "mma":
             B, _, M = new_features.shape
             tw, lo = _get_twin(new_features, 16)
             layers = self._pw_layers("confidence_layers", self.confidence_layers, split=lo > 0)
@@ -646,12 +687,15 @@ class Vote_layer(nn.Module):
         if hasattr(self, "center_surface_futures"):
             features_select = torch.cat([self.center_surface_futures, features_select], dim=1)
 
-        if _fused_ok(self, features_select) and mlp_backend() == "mma":
+        _tag(self)
+        if _fused_ok(self, features_select) and mlp_backend(self) == "mma":
             B_, _, M_ = features_select.shape
             caches = self.__dict__.setdefault("_pw_cache", {"mlp_modules": _PwCache(), "ctr_reg": _PwCache()})
             tw, lo = _get_twin(features_select.contiguous(), 16)
-            if lo == 0 and hasattr(self, "center_surface_futures"):
-                tw, lo = _split_rows(features_select)  # concatenated input: no producer twin, keep fp32-grade arithmetic
+            if lo == 0:
+                # no producer rows with residuals (concatenated surface features, a producer on the exact-fp32 kernels, a
+                # caller-supplied tensor): build [values | residuals] here so the offsets stay fp32-grade
+                tw, lo = _split_rows(features_select)
             layers = caches["mlp_modules"].get(self._folded("mlp_modules", self.mlp_modules), lo > 0) + \
                 caches["ctr_reg"].get(self._folded("ctr_reg", nn.Sequential(self.ctr_reg)), lo > 0)
             ctr_offsets = _pw_stack(layers, tw.view(B_ * M_, -1), lo, B_, M_, "pm")  # (B, npoint, 3 [+ extra])

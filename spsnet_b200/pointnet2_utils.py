@@ -25,6 +25,17 @@ __all__ = [
     "score_topk", "gather_rows", "ball_query_msg",
 ]
 
+current_ovf_tag = 0   # fp16 range-guard tag stamped on the tensor-core launches (set by the calling module, 0 = untagged)
+
+
+def fp16_overflow(clear: bool = True) -> int:
+    """Bit mask of the modules (tags) whose tensor-core kernels stored a value beyond the fp16 range since the last clear.
+    SYNCHRONISES the current device (include/spsk.h: spsk_fp16_overflow_poll)."""
+    m = C.c_uint(0)
+    check(lib.spsk_fp16_overflow_poll(C.byref(m), 1 if clear else 0), "fp16_overflow_poll")
+    return int(m.value)
+
+
 FPS_DISTMAT_ONCHIP_MAX_N = 16384  # distance-matrix mode (F-FPS) and the forced dense kernels keep 16 minima per thread on chip, no clusters
 FPS_ONCHIP_MAX_N = 131072  # <= 16384: one CTA per scene; <= 131072: one 2/4/8-CTA cluster per scene; above: a 16-CTA cluster
 # (<= 262144) where the device can schedule one, else the streaming kernel over the `temp` scratch, which is allocated from here on
@@ -583,6 +594,7 @@ class MmaChain:
             d.kpad[l] = self.kpad[l]
             d.cpad[l] = self.cpad[l]
         d.split = 1 if self.split else 0
+        d.ovf_tag = current_ovf_tag
         d.pair = 1 if self.pair else 0
         d.l0_fused = 1 if self.l0_fused else 0
         d.c_feat = self.c_feat
@@ -676,6 +688,7 @@ def pw_mma_forward(x16: torch.Tensor, layer: PwLayer, *, xlo=0, out_cm=None, m=0
     d = PwDesc()
     d.rows, d.k, d.ldx, d.n, d.relu = rows, layer.k, ldx, layer.c_out, 1 if layer.relu else 0
     d.split, d.xlo = (1, int(xlo)) if layer.split else (0, 0)
+    d.ovf_tag = current_ovf_tag
     d.x, d.wtiles, d.bias = x16.data_ptr(), layer.wtiles.data_ptr(), layer.bias.data_ptr()
     if out_cm is not None:
         d.out_cm, d.m, d.c_total, d.co_off = out_cm.data_ptr(), m, out_cm.shape[1], co_off

@@ -87,6 +87,11 @@ class BackbonePipeline:
                         s.outs = self._forward(s)
                     self.launches_per_step = (lib.spsk_launch_count() - c0) // 2
                 s.stream.synchronize()
+                # the warm-up forwards above ran eagerly WITH the fp16 range guard (backbone.forward): modules whose activations
+                # overflow fp16 are on the exact kernels from here on, before anything is captured.  Replays do not poll.
+                for mod in self.net.modules():
+                    if hasattr(mod, "SA_modules"):
+                        mod._spsk_guard = False
                 if self.use_graph:
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, stream=s.stream):
@@ -168,6 +173,15 @@ class BackbonePipeline:
     def sync(self) -> None:
         for s in self.slots:
             s.stream.synchronize()
+
+    def check_overflow(self) -> None:
+        """Raise if a replayed batch pushed an activation beyond the fp16 range (data-dependent: the weights were checked in
+        prepare()).  Synchronises the device; call it where the results of a batch are consumed if the inputs are untrusted."""
+        from . import pointnet2_utils as pu
+
+        if pu.fp16_overflow(clear=True):
+            raise RuntimeError("BackbonePipeline: an activation exceeded the fp16 range during replay; call prepare() again on a "
+                               "representative batch (it moves the affected modules to the exact-fp32 kernels) and resubmit")
 
     def host_out(self, slot: int) -> Dict[str, torch.Tensor]:
         self.slots[slot].done.synchronize()

@@ -187,3 +187,70 @@ def test_pw_mma_many_rows_vs_oracle():
     e = rel_err(out_pm.cpu().double().reshape(rows, c_out).numpy(), want.numpy())
     print(f"[pw many rows] {rows} x {c_in} -> {c_out}: {e:.2e}")
     assert e <= 2e-5
+
+
+def test_fp16_range_guard_falls_back_to_exact_kernels(ref_ops):
+    """VERDICT round 1, task 9.  BN gains that push the hidden activations of SA layers 1, 2 and 5 far beyond 65504 (the
+    largest fp16 value) while the reference's fp32 / TF32 result stays finite: the tensor-core kernels flag the overflow, the
+    backbone's eager forward polls the flag, moves the affected modules to the exact-fp32 kernels and re-runs -- same sampled
+    points, features within 1e-3 of the UNMODIFIED reference (TF32 off).  Without the guard the fp16 path returns non-finite /
+    wrong features, which the test demonstrates first."""
+    import os
+    import warnings
+
+    from oracle import parity
+    from spsnet_b200 import backbone as bb
+    from spsnet_b200 import pointnet2_utils as pu
+
+    cfg = bb.Cfg({"SA_CONFIG": {**bb.KITTI_IASSD_SA_CONFIG, "NPOINT_LIST": [[1024], [256], [128], [64], [-1], [64]]}})
+    torch.manual_seed(6)
+    net = bb.IASSD_Backbone(cfg, num_class=3, input_channels=4)
+    bb.randomize_bn_stats(net, seed=6)
+    gain = 3.0e5
+    with torch.no_grad():
+        for li in (1, 2, 5):
+            for mlp in net.SA_modules[li].mlps:
+                mlp[1].weight.mul_(gain)      # BN after the first conv: hidden activations ~1e5..1e6
+                mlp[1].bias.mul_(gain)
+                mlp[3].weight.div_(gain)      # the next conv undoes the scale: everything downstream stays O(1)
+    net = net.cuda().eval()
+    ref = parity.reference_backbone("IASSD_Backbone", cfg, 4).cuda().eval()
+    ref.load_state_dict(net.state_dict())
+    B, N = 2, 4096
+    pts = torch.from_numpy(scenes.to_points(scenes.make_batch(31, B, N))).cuda()
+    pu.fp16_overflow(clear=True)
+    # (1) guard off: the overflow is real
+    os.environ["SPSK_FP16_GUARD"] = "0"
+    try:
+        with torch.no_grad():
+            bad = net({"batch_size": B, "points": pts.clone()})
+        assert pu.fp16_overflow(clear=True) != 0, "the kernels did not flag the fp16 overflow"
+        f = bad["encoder_features"][2]
+        with torch.no_grad():
+            f_ref = ref({"batch_size": B, "points": pts.clone()})["encoder_features"][2]
+        assert not torch.isfinite(f).all() or parity.rel_err(f.cpu().numpy(), f_ref.cpu().numpy()) > 1e-2
+    finally:
+        del os.environ["SPSK_FP16_GUARD"]
+    # (2) guard on (default): detected, exact fallback, reference-grade results
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        rep = parity.teacher_forced_check(net, ref, B, pts, fps_layers=(1, 2))
+    assert any("fp16 range" in str(x.message) for x in w), "the guard did not report the fallback"
+    assert [bool(getattr(m, "_spsk_exact", False)) for m in net.SA_modules] == [False, True, True, False, False, True]
+    with torch.no_grad():
+        out = net({"batch_size": B, "points": pts.clone()})
+    assert torch.isfinite(out["centers_features"]).all()
+    print(f"[fp16 guard] teacher-forced after fallback: {rep['layers']}")
+    # the pipeline checks while it warms up, BEFORE it captures: a fresh copy of the same weights ends up on the exact kernels too
+    from spsnet_b200.runtime import BackbonePipeline
+
+    net2 = bb.IASSD_Backbone(cfg, num_class=3, input_channels=4).cuda().eval()
+    net2.load_state_dict(net.state_dict())
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        pipe = BackbonePipeline(net2, B, N, 5, depth=2, use_graph=True)
+        pipe.prepare(pts)
+    slot = pipe.submit_device(pts)
+    pipe.sync()
+    pipe.check_overflow()
+    assert torch.equal(pipe.slots[slot].outs["centers_features"], out["centers_features"])
