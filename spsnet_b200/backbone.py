@@ -22,6 +22,29 @@ from .configs import (Cfg, KITTI_IASSD_SA_CONFIG, kitti_iassd_cfg, kitti_spsnet_
                       randomize_bn_stats, waymo_iassd_cfg)
 
 
+class LazyList(list):
+    """A list whose entries are built on first access.  `encoder_coords` and `sa_ins_preds` (reference IASSD_backbone.py:
+    113,139-148) are read by the heads' target assignment and losses only -- training code -- yet cost ten small cat / cast
+    kernels per forward; at inference they are materialised only if somebody looks.  Entries are either values or zero-argument
+    callables; everything the callables capture (encoder_xyz, the class logits) is a regular output of the forward, so a
+    later access -- also after a CUDA-graph replay -- sees the current contents."""
+
+    def _get(self, i):
+        v = list.__getitem__(self, i)
+        if callable(v):
+            v = v()
+            list.__setitem__(self, i, v)
+        return v
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._get(j) for j in range(*i.indices(len(self)))]
+        return self._get(i if i >= 0 else len(self) + i)
+
+    def __iter__(self):
+        return (self._get(i) for i in range(len(self)))
+
+
 class IASSD_Backbone(nn.Module):
     """Backbone for IA-SSD (reference IASSD_backbone.py:7-212)."""
 
@@ -160,8 +183,19 @@ class IASSD_Backbone(nn.Module):
             features = features.view(batch_size, -1, features.shape[-1]).permute(0, 2, 1).contiguous()
         bidx2d = batch_idx.view(batch_size, -1)
 
-        encoder_xyz, encoder_features, sa_ins_preds = [xyz], [features], []
-        encoder_coords = [torch.cat([bidx2d.unsqueeze(-1), xyz], dim=-1)]
+        # eager materialisation of the training-only extras when training or under autograd (reference behaviour), lazy otherwise
+        lazy = (not self.training) and not torch.is_grad_enabled()
+
+        def coords_of(t):
+            f = lambda: torch.cat([bidx2d[:, :t.shape[1], None].float(), t.view(batch_size, -1, 3)], dim=-1)  # noqa: E731
+            return f if lazy else f()
+
+        def preds_of(t):
+            f = lambda: torch.cat([bidx2d[:, :t.shape[1], None].float(), t.reshape(batch_size, -1, t.shape[-1])], dim=-1)  # noqa: E731
+            return f if lazy else f()
+
+        encoder_xyz, encoder_features, sa_ins_preds = [xyz], [features], LazyList()
+        encoder_coords = LazyList([coords_of(xyz)])
         li_cls_pred = None
         centers = centers_origin = ctr_offsets = None
         surface = None  # (B, n_i, 60) point-major surface features of the points kept so far
@@ -193,14 +227,12 @@ class IASSD_Backbone(nn.Module):
                 kw = {"center_surface_futures": surface.permute(0, 2, 1).contiguous()} if surface is not None else {}
                 li_xyz, li_features, xyz_select, ctr_offsets = module(xyz_input, feature_input, **kw)
                 centers, centers_origin = li_xyz, xyz_select
-                encoder_coords.append(torch.cat([bidx2d[:, :centers_origin.shape[1], None].float(),
-                                                 centers_origin.view(batch_size, -1, 3)], dim=-1))
+                encoder_coords.append(coords_of(centers_origin))
             encoder_xyz.append(li_xyz)
-            encoder_coords.append(torch.cat([bidx2d[:, :li_xyz.shape[1], None].float(), li_xyz.view(batch_size, -1, 3)], dim=-1))
+            encoder_coords.append(coords_of(li_xyz))
             encoder_features.append(li_features)
             if li_cls_pred is not None:
-                sa_ins_preds.append(torch.cat([bidx2d[:, :li_cls_pred.shape[1], None].float(),
-                                               li_cls_pred.reshape(batch_size, -1, li_cls_pred.shape[-1])], dim=-1))
+                sa_ins_preds.append(preds_of(li_cls_pred))
             else:
                 sa_ins_preds.append([])
 

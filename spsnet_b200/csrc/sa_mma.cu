@@ -534,16 +534,26 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                 if (!a.split) {
                     const int nch = L0.kpad >> 3;
                     const int fch = a.cpad8 >> 3;
-                    const uint4 *trow = (ok && fch) ? reinterpret_cast<const uint4 *>(a.twin + ((size_t)bb * a.n + j) * a.ldtwin) : nullptr;
+                    // the row's feature channels go global -> shared with 16-byte cp.async (LDGSTS): every load of the row is in
+                    // flight at once and no register is staged (the register version moved them in batches of 8, one L2 round
+                    // trip per batch: 4 round trips for the 256-channel rows of layer 5); rows past the end are zero-filled
+                    // (rows of <= 8 loads -- one batch either way -- keep the register path: cp.async + wait + proxy fence measured
+                    // 5-8 % slower on the 64-channel chains of layer 1)
+                    const uint4 *trow = fch ? reinterpret_cast<const uint4 *>(a.twin + (ok ? ((size_t)bb * a.n + j) * a.ldtwin : 0)) : nullptr;
                     int c = 0;
-                    for (; c + 8 <= fch; c += 8) {   // 8 independent 16-byte loads in flight
+                    if (fch > 8) {
+                        const uint32_t xdst = smem_u32(xrow);
+                        for (; c < fch; ++c) cp_async16(xdst + (uint32_t)c * 128u, trow + c, ok ? 16u : 0u);
+                        cp_async_commit();
+                    } else {
                         uint4 t[8];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) t[u] = ok ? __ldg(trow + c + u) : zero;
+                        for (int u = 0; u < 8; ++u) t[u] = (ok && u < fch) ? __ldg(trow + u) : zero;
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) *reinterpret_cast<uint4 *>(xrow + (size_t)(c + u) * 128) = t[u];
+                        for (int u = 0; u < 8; ++u)
+                            if (u < fch) *reinterpret_cast<uint4 *>(xrow + (size_t)u * 128) = t[u];
+                        c = fch;
                     }
-                    for (; c < fch; ++c) *reinterpret_cast<uint4 *>(xrow + (size_t)c * 128) = ok ? __ldg(trow + c) : zero;
                     if (a.use_xyz) {
                         *reinterpret_cast<uint4 *>(xrow + (size_t)c * 128) = make_uint4(pack_h2(dx, dy), pack_h2(dz, 0.f), 0u, 0u);
                         ++c;
@@ -619,6 +629,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                     }
                 }
                 if (!a.l0_fused) {
+                    if (!a.split && (a.cpad8 >> 3) > 8) cp_async_wait<0>();
                     fence_proxy_async();
                     for (int c = 0; c < L0.n_xc; ++c) mbar_arrive(XR(0, c));
                 }
@@ -931,8 +942,8 @@ extern "C" int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stre
     a.ntiles = (int)ntiles;
     a.lstages = P.lstages;
     a.sched_n = P.sched_n;
-    static const bool no_scout = getenv("SPSK_SA_NO_SCOUT") != nullptr;   // A/B knob: the issuer takes its own waits (round-1 loop)
-    a.scout = no_scout ? 0 : 1;
+    static const bool want_scout = getenv("SPSK_SA_SCOUT") != nullptr;   // opt-in (A/B knob): measured neutral on B200 (292 vs 280-290 us on layer 5 scale 2) -- the waits it removes are real stalls, not overhead
+    a.scout = want_scout ? 1 : 0;
     a.rot_last = (P.L[d->nlayers - 1].n_cc > 1 && getenv("SPSK_SA_ROT")) ? 1 : 0;   // opt-in: measured neutral on B200 (the weight stream is not L2 hot-line bound)
     a.l0_fused = d->l0_fused ? 1 : 0;
     a.l0_off = P.l0_off;

@@ -718,9 +718,17 @@ class Vote_layer(nn.Module):
                 cached = self.max_offset_limit.to(xyz_select.device).view(1, 1, 3)
                 self.__dict__["_limit_dev"] = cached
             limit = cached
-            limited = torch.where(ctr_offsets > limit, limit, ctr_offsets)
-            limited = torch.where(limited < -limit, -limit, limited)
-            vote_xyz = xyz_select + limited
+            if _fused_ok(self, ctr_offsets):
+                # one clamp kernel instead of the reference's compare / where / neg / compare / where chain (:504-513): same
+                # values (NaN passes through both), `limited` is only an intermediate
+                neg = self.__dict__.get("_neg_limit_dev")
+                if neg is None or neg.device != limit.device:
+                    neg = self.__dict__["_neg_limit_dev"] = -limit
+                vote_xyz = xyz_select + torch.clamp(ctr_offsets, min=neg, max=limit)
+            else:
+                limited = torch.where(ctr_offsets > limit, limit, ctr_offsets)
+                limited = torch.where(limited < -limit, -limit, limited)
+                vote_xyz = xyz_select + limited
         else:
             vote_xyz = xyz_select + ctr_offsets
         return vote_xyz, new_features, xyz_select, ctr_offsets
