@@ -43,10 +43,13 @@ namespace spsk {
 // accumulators drain concurrently and every scheduler holds two epilogue warps to hide TMEM / shared-memory latency.
 // SC = the CTA carries a scout warp (streaming chains; see the tabulated issue loop).  Not for the 3-CTAs-per-SM shapes: a
 // seventh warp would round the register allocation up to eight and cap the epilogue warps at 80 registers.
-template <int G, bool PROF, bool SC>
-__global__ void __launch_bounds__(128 * G + 64 + (SC ? 32 : 0), G == 1 ? (SC ? 2 : 3) : 1)
+// NP = no producer warp (resident chains only: the one bulk load of the chain is issued by the MMA warp): 160-thread CTAs, FOUR
+// per SM at 96 registers.  The narrow chains are bound by the latency of their gather -> MMA -> epilogue hand-offs, i.e. by
+// how many tiles an SM keeps in flight; a fourth CTA is a fourth tile.
+template <int G, bool PROF, bool SC, bool NP>
+__global__ void __launch_bounds__(128 * G + 64 + (SC ? 32 : 0) - (NP ? 32 : 0), G == 1 ? (NP ? 4 : (SC ? 2 : 3)) : 1)
 sa_mma_kernel(const __grid_constant__ SaArgs a) {
-    constexpr int W_PROD = 4 * G, W_MMA = 4 * G + 1, W_SCOUT = 4 * G + 2;
+    constexpr int W_PROD = NP ? -1 : 4 * G, W_MMA = NP ? 4 * G : 4 * G + 1, W_SCOUT = 4 * G + 2;
     extern __shared__ __align__(128) uint8_t smem[];
     // carve: [header: barriers + tmem slot][XA][XB][weights]
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
@@ -184,6 +187,13 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
             // accumulator, wait for the activation chunks, issue, commit.  The general loop below spends ~2 k cycles of
             // address arithmetic and parameter loads per job, which is the critical path of these latency-bound chains.
             const bool leader = elect_one();
+            if (NP && leader) {   // no producer warp: the resident chain is loaded from here
+                mbar_expect_tx(W_FULL(0), (uint32_t)a.w_total);
+                for (int off = 0; off < a.w_total; off += MM_STAGE_BYTES) {
+                    const int bytes = min(MM_STAGE_BYTES, a.w_total - off);
+                    bulk_g2s(smem_u32(wst + off), a.wtiles + off, (uint32_t)bytes, W_FULL(0));
+                }
+            }
             uint32_t x_lo[MM_MAX_LAYERS], x_hi[MM_MAX_LAYERS], w_lo[MM_MAX_LAYERS], idesc[MM_MAX_LAYERS], tstride[MM_MAX_LAYERS];
             int nv[MM_MAX_LAYERS], nk2[MM_MAX_LAYERS], nxc[MM_MAX_LAYERS], vkl[MM_MAX_LAYERS];
 #pragma unroll
@@ -829,11 +839,14 @@ static int sa_plan(const spsk_sa_mma_desc *d, SaPlan *P) {
         *resident = 0; *nstages = st > cap ? cap : st; *smem = xtot + *nstages * MM_STAGE_BYTES;
         return true;
     };
-    int ctas = 0, cmax = pair ? 1 : 3;
-    if (const char *e = getenv("SPSK_SA_MAX_CTAS")) cmax = max(1, min(3, atoi(e)));   // tuning / A-B measurements
+    int ctas = 0, cmax = pair ? 1 : 4;
+    if (const char *e = getenv("SPSK_SA_MAX_CTAS")) cmax = max(1, min(4, atoi(e)));   // tuning / A-B measurements
+    bool one_job_per_layer = true;   // the register-resident "narrow" issue loop (the only one the 4-CTA shape runs)
+    for (int l = 0; l < nL; ++l) one_job_per_layer = one_job_per_layer && P->L[l].n_cc == 1;
     for (int c = cmax; c >= 1; --c) {
         int res, st, sm;
         if (!fits(c, &res, &st, &sm)) continue;
+        if (c == 4 && !(res && one_job_per_layer && !d->l0_fused)) continue;   // four CTAs per SM: resident narrow chains only (no producer warp)
         ctas = c; P->resident = res; P->nstages = st; P->smem = sm;
         break;
     }
@@ -852,7 +865,7 @@ static int sa_plan(const spsk_sa_mma_desc *d, SaPlan *P) {
         const int e = other / MM_STAGE_BYTES;
         if (e >= 3) P->lstages = e > MM_MAX_STAGES ? MM_MAX_STAGES : e;
     }
-    P->tmem_cols = ctas == 1 ? 512 : (ctas == 2 ? 256 : 128);
+    P->tmem_cols = ctas == 1 ? 512 : (ctas == 2 ? 256 : 128);   // 3 or 4 CTAs: 128 columns each
     P->nbuf = P->tmem_cols / 128;
     // streaming chains: tabulate the per-tile MMA schedule in shared memory when it fits (one 16-byte entry per weight tile)
     P->sched_n = 0;
@@ -984,10 +997,20 @@ extern "C" int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stre
 #define SPSK_SA_LAUNCH(GV, PV, SCV)                                                                                          \
     do {                                                                                                                    \
         static SmemAttrOnce attr;                                                                                           \
-        if (int rc = attr.ensure(reinterpret_cast<const void *>(sa_mma_kernel<GV, PV, SCV>), 227 * 1024, "sa_mma_kernel")) return rc; \
-        sa_mma_kernel<GV, PV, SCV><<<grid, 128 * GV + 64 + (SCV ? 32 : 0), P.smem, as_stream(stream)>>>(a);                   \
+        if (int rc = attr.ensure(reinterpret_cast<const void *>(sa_mma_kernel<GV, PV, SCV, false>), 227 * 1024, "sa_mma_kernel")) return rc; \
+        sa_mma_kernel<GV, PV, SCV, false><<<grid, 128 * GV + 64 + (SCV ? 32 : 0), P.smem, as_stream(stream)>>>(a);            \
     } while (0)
-    if (two_groups) {
+    if (P.ctas == 4) {   // resident narrow chain, no producer warp
+        SPSK_REQUIRE(a.narrow && a.resident, SPSK_ERR_UNSUPPORTED, "sa_mma: the 4-CTA shape needs the resident narrow issue loop (unset SPSK_SA_NO_NARROW)");
+        static SmemAttrOnce attr4, attr4p;
+        if (a.prof) {
+            if (int rc = attr4p.ensure(reinterpret_cast<const void *>(sa_mma_kernel<1, true, false, true>), 227 * 1024, "sa_mma_kernel<np,prof>")) return rc;
+            sa_mma_kernel<1, true, false, true><<<grid, 160, P.smem, as_stream(stream)>>>(a);
+        } else {
+            if (int rc = attr4.ensure(reinterpret_cast<const void *>(sa_mma_kernel<1, false, false, true>), 227 * 1024, "sa_mma_kernel<np>")) return rc;
+            sa_mma_kernel<1, false, false, true><<<grid, 160, P.smem, as_stream(stream)>>>(a);
+        }
+    } else if (two_groups) {
         if (a.prof) { if (sc) SPSK_SA_LAUNCH(2, true, true); else SPSK_SA_LAUNCH(2, true, false); }
         else { if (sc) SPSK_SA_LAUNCH(2, false, true); else SPSK_SA_LAUNCH(2, false, false); }
     } else {
