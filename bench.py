@@ -304,6 +304,7 @@ def profile_kernels(net, dev_points, steps: int):
         else:
             os.environ["SPSK_FPS_PREFETCH"] = prev_prefetch
     table = {}
+    order = []
     for name, a, e0, e1 in records:
         key = name
         if name in ("spsk_farthest_point_sampling",):
@@ -320,6 +321,11 @@ def profile_kernels(net, dev_points, steps: int):
         t = table.setdefault(key, {"ms": 0.0, "launches": 0, "args": a})
         t["ms"] += ms
         t["launches"] += 1
+        order.append(key)
+    dump = os.environ.get("SPSK_DUMP_CALLS")
+    if dump:   # the library calls of ONE step, in launch order (scripts/ncu_traffic.py aligns an ncu launch list with it)
+        per = len(order) // steps
+        Path(dump).write_text(json.dumps(order[-per:]))
     return table, steps
 
 

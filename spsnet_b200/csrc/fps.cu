@@ -454,7 +454,8 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
                 if (CL) bp = __reduce_max_sync(0xFFFFFFFFu, (ir != 0u && cand == rr) ? (uint32_t)pos : 0u);
                 if (lane == pb) { bmax_bits = mx; brank = rr; bpos = bp; }
             }
-            if (TM && mask) tmem_wait_st();   // the next load of these columns (a later iteration) must see the stores
+            // (the tcgen05.wait::st that orders these stores before the next load of the same columns -- a later iteration -- is
+            // taken after the block barrier below, off the critical warp's path to it)
         } else if (LADDER == 2) {
             // two-level ladder: groups of 8 sub-buckets, then the bits of a non-empty group
 #pragma unroll
@@ -505,6 +506,7 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
             }
             if (PROF && pf) { const long long t1 = clock64(); pc[2] += t1 - t0; t0 = t1; }
             __syncthreads();
+            if (TM && mask0) tmem_wait_st();
             if (PROF && pf) { const long long t1 = clock64(); pc[3] += t1 - t0; t0 = t1; }
             // block best over the W warp slots
             const uint2 v = sl[lane];
@@ -527,6 +529,7 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
             uint4 *cs_ = cslot[j & 1];
             if (lane == 0) cs_[warp] = make_uint4(wm, wr, wpos, 0u);
             __syncthreads();
+            if (TM && mask0) tmem_wait_st();
             const uint4 sv = cs_[lane];
             const uint32_t cm = __reduce_max_sync(0xFFFFFFFFu, sv.x);
             const uint32_t cr = __reduce_max_sync(0xFFFFFFFFu, (sv.x == cm) ? sv.y : 0u);

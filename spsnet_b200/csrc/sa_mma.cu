@@ -55,8 +55,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + MM_HDR - 16);
     uint32_t *ready_cnt = reinterpret_cast<uint32_t *>(smem + MM_HDR - 32);   // scout -> issuer: schedule entries whose waits are over
-    uint4 *sched = reinterpret_cast<uint4 *>(smem + MM_HDR);               // a.sched_n entries (streaming chains)
-    uint8_t *xa = smem + MM_HDR + ((a.sched_n * 16 + 127) & ~127);
+    uint8_t *xa = smem + MM_HDR;
     uint8_t *xb = xa + a.xa_bytes;
     uint8_t *wst = xb + a.xb_bytes;
     const uint32_t bar0 = smem_u32(bars);
@@ -86,39 +85,6 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
         mbar_init(HID_DONE, 1);
         mbar_init_fence();
         *ready_cnt = 0u;
-    }
-    if (warp == W_MMA && a.sched_n > 0 && (tid & 31) == 0) {
-        // Streaming chains: the per-tile schedule (one entry per weight tile) is identical for every tile, so it is tabulated
-        // once in shared memory (read by the issuing warp and by the scout warp):
-        //   .x = activation descriptor lo of the tile's first K block   .y = instruction descriptor
-        //   .z = activation desc hi | weight desc hi << 16
-        //   .w = nk16[0:3) first_kc[3] last_kc[4] cc0[5] need_chunk[6:11) lring[11] hid_done[12] last_layer[13] xbuf[14] layer_start[15]
-        int e = 0;
-        for (int l = 0; l < nL; ++l) {
-            const SaLayer &Ly = a.L[l];
-            const bool last = (l == nL - 1);
-            const uint32_t x_lo0 = umma_desc_lo(smem_u32((l & 1) ? xb : xa), 128u);
-            const uint32_t x_hi = umma_desc_hi((uint32_t)Ly.xw * 16u);
-            for (int cci = 0; cci < Ly.n_cc; ++cci) {
-                const int cc = chunk_of(l, cci, Ly.n_cc);
-                const int ncols = min(128, Ly.cpad - cc * 128);
-                for (int kc = 0; kc < Ly.n_kc; ++kc, ++e) {
-                    const int kw = min(64, Ly.vk - kc * 64);
-                    const int nk16 = kw >> 4;
-                    uint32_t f = (uint32_t)nk16;
-                    if (kc == 0) f |= 1u << 3;
-                    if (kc == Ly.n_kc - 1) f |= 1u << 4;
-                    if (cci == 0) f |= (1u << 5) | ((uint32_t)((kc * 4 + nk16 - 1) >> 2) << 6);
-                    if (a.lstages > 0 && last) f |= 1u << 11;
-                    if (a.lstages > 0 && l == nL - 2 && cci == Ly.n_cc - 1 && kc == Ly.n_kc - 1) f |= 1u << 12;
-                    if (last) f |= 1u << 13;
-                    f |= (uint32_t)(l & 1) << 14;
-                    if (cci == 0 && kc == 0) f |= 1u << 15;
-                    const uint32_t idesc = last ? umma_idesc(128, MM_ROWS) : umma_idesc(128, ncols);
-                    sched[e] = make_uint4(x_lo0 + (uint32_t)kc * 64u, idesc, x_hi | (umma_desc_hi((uint32_t)kw * 16u) << 16), f);
-                }
-            }
-        }
     }
     if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
     tc_fence_before();
@@ -247,8 +213,14 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                 }
             }
         } else if (a.sched_n > 0) {
-            // Streaming chains: the issue loop reads the tabulated schedule (built above): per entry one 16-byte read, <= 4 MMAs,
-            // the commits -- no address arithmetic, no parameter loads.
+            // Streaming chains: the per-tile schedule (one entry per weight tile) is identical for every tile and every CTA, so the
+            // HOST tabulates it into the kernel parameters (SaArgs::sched, see build_schedule).  Parameters are read with uniform
+            // loads straight into the uniform registers tcgen05.mma takes its operands from: the round-1 table lived in shared
+            // memory, so every descriptor went LDS -> vector register -> R2UR (~100 instructions per weight tile around four
+            // 66-cycle MMAs whose issue blocks).  Entry layout:
+            //   .x = activation descriptor lo of the tile's first K block, RELATIVE to the CTA's dynamic shared memory base
+            //   .y = instruction descriptor   .z = activation desc hi | weight desc hi << 16
+            //   .w = nk16[0:3) first_kc[3] last_kc[4] cc0[5] need_chunk[6:11) lring[11] hid_done[12] last_layer[13] xbuf[14] layer_start[15]
             //
             // It also does NO mbarrier wait when the scout warp is on (default).  Measured on this GPU (round 2,
             // scripts/dev/issue_loop_probe.cu): one mbarrier.try_wait on an ALREADY COMPLETED barrier costs the issuing thread
@@ -270,12 +242,14 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
             const int nent = a.sched_n;
             const bool scout = SC && a.scout != 0;
             const uint32_t ready_addr = smem_u32(ready_cnt);
+            const uint32_t smem_base16 = smem_u32(smem) >> 4;   // descriptor units
             uint32_t done = 0u, avail = 0u;   // entries issued so far / entries known to be clear
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 int xwait = 0, buf = 0;
                 uint32_t d_tmem = tmem_base;
                 for (int e = 0; e < nent; ++e) {
-                    const uint4 E = sched[e];
+                    uint4 E = a.sched[e];
+                    E.x += smem_base16;
                     const uint32_t f = E.w;
                     if (f & (1u << 15)) xwait = 0;
                     if (f & (1u << 3)) {
@@ -461,7 +435,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
                 int xwait = 0;
                 for (int e = 0; e < nent; ++e) {
-                    const uint32_t f = sched[e].w;
+                    const uint32_t f = a.sched[e].w;
                     if (f & (1u << 15)) xwait = 0;
                     if (f & (1u << 3)) {
                         const int buf = (int)(job & nbmask);
@@ -867,19 +841,51 @@ static int sa_plan(const spsk_sa_mma_desc *d, SaPlan *P) {
     }
     P->tmem_cols = ctas == 1 ? 512 : (ctas == 2 ? 256 : 128);   // 3 or 4 CTAs: 128 columns each
     P->nbuf = P->tmem_cols / 128;
-    // streaming chains: tabulate the per-tile MMA schedule in shared memory when it fits (one 16-byte entry per weight tile)
+    // streaming chains: tabulate the per-tile MMA schedule (one 16-byte entry per weight tile) into the kernel parameters
     P->sched_n = 0;
     if (!pair && !P->resident && !split && !getenv("SPSK_SA_NO_SCHED")) {
         int ntab = 0;
         for (int l = 0; l < nL; ++l) ntab += P->L[l].n_cc * P->L[l].n_kc;
-        const int tab_bytes = (ntab * 16 + 127) & ~127;
-        const int per = (sm_bytes / ctas - 1024) & ~127;
-        if (ntab <= MM_SCHED_MAX && P->smem + tab_bytes <= per) { P->sched_n = ntab; P->smem += tab_bytes; }
+        if (ntab <= MM_SCHED_MAX) P->sched_n = ntab;
     }
     // shared-memory floor so that no more than `ctas` CTAs land on an SM (their TMEM allocations would not fit)
     const int floor_bytes = (sm_bytes / (ctas + 1) - 1024 + 256) & ~127;
     if (P->smem < floor_bytes) P->smem = floor_bytes;
     return SPSK_OK;
+}
+
+// The per-tile MMA schedule of a streaming chain (see the tabulated issue loop of sa_mma_kernel).  Shared-memory addresses are
+// relative to the CTA's dynamic shared memory: [header MM_HDR][XA][XB][weight ring].
+static void build_schedule(SaArgs &a) {
+    const int nL = a.nlayers;
+    int e = 0;
+    for (int l = 0; l < nL; ++l) {
+        const SaLayer &Ly = a.L[l];
+        const bool last = (l == nL - 1);
+        const uint32_t x_off = (uint32_t)MM_HDR + ((l & 1) ? (uint32_t)a.xa_bytes : 0u);
+        const uint32_t x_lo0 = (x_off >> 4) | ((128u >> 4) << 16);                  // umma_desc_lo(base + x_off, LBO 128) - (base >> 4)
+        const uint32_t x_hi = (((uint32_t)Ly.xw * 16u) >> 4) | (1u << 14);           // umma_desc_hi(SBO)
+        for (int cci = 0; cci < Ly.n_cc; ++cci) {
+            const int ncols = (Ly.cpad - cci * 128) < 128 ? (Ly.cpad - cci * 128) : 128;   // (a rotated chunk order only permutes equal 128-wide chunks)
+            for (int kc = 0; kc < Ly.n_kc; ++kc, ++e) {
+                const int kw = (Ly.vk - kc * 64) < 64 ? (Ly.vk - kc * 64) : 64;
+                const int nk16 = kw >> 4;
+                uint32_t f = (uint32_t)nk16;
+                if (kc == 0) f |= 1u << 3;
+                if (kc == Ly.n_kc - 1) f |= 1u << 4;
+                if (cci == 0) f |= (1u << 5) | ((uint32_t)((kc * 4 + nk16 - 1) >> 2) << 6);
+                if (a.lstages > 0 && last) f |= 1u << 11;
+                if (a.lstages > 0 && l == nL - 2 && cci == Ly.n_cc - 1 && kc == Ly.n_kc - 1) f |= 1u << 12;
+                if (last) f |= 1u << 13;
+                f |= (uint32_t)(l & 1) << 14;
+                if (cci == 0 && kc == 0) f |= 1u << 15;
+                const int n_idesc = last ? MM_ROWS : ncols;
+                const uint32_t idesc = (1u << 4) | ((uint32_t)(n_idesc >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // umma_idesc(128, n)
+                const uint32_t w_hi = (((uint32_t)kw * 16u) >> 4) | (1u << 14);
+                a.sched[e] = make_uint4(x_lo0 + (uint32_t)kc * 64u, idesc, x_hi | (w_hi << 16), f);
+            }
+        }
+    }
 }
 
 }  // namespace spsk
@@ -991,6 +997,7 @@ extern "C" int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stre
     if (const char *e = getenv("SPSK_SA_GRID_MULT")) mult = max(1, min(8, atoi(e)));
     const int slots = SPSK_NUM_SMS * P.ctas * mult;
     const int grid = a.ntiles < slots ? a.ntiles : slots;
+    if (a.sched_n > 0) build_schedule(a);
     const bool two_groups = P.ctas == 1 && !getenv("SPSK_SA_ONE_GROUP");
     const bool sc = a.scout && a.sched_n > 0 && !a.narrow && (two_groups || P.ctas <= 2);
     a.scout = sc ? 1 : 0;

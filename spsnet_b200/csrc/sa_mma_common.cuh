@@ -55,6 +55,7 @@ struct SaArgs {
     unsigned long long *prof;   // optional per-role wait/work cycle counters (spsk_sa_mma_set_profile), null = off
     unsigned int *ovf;          // fp16 range guard word of this device (may be null) and this call's tag bit
     unsigned int ovf_bit;
+    uint4 sched[MM_SCHED_MAX];  // streaming chains: the per-tile MMA schedule (sched_n entries), see sa_mma.cu::build_schedule
 };
 
 // byte offset of weight tile (cc, kc) inside a layer: chunks of 128 couts are contiguous (cc-major), inside a chunk
