@@ -120,7 +120,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                         const int cc = chunk_of(l, cci, Ly.n_cc);
                         const int ncols = min(128, Ly.cpad - cc * 128);
                         for (int kc = 0; kc < Ly.n_kc; ++kc) {
-                            const int kw = min(64, Ly.vk - kc * 64);
+                            const int kw = min(64, Ly.wk - kc * 64);
                             const uint32_t bytes = (uint32_t)(ncols * kw * 2);
                             const uint8_t *src = a.wtiles + wtile_off(Ly, cc, kc, ncols);
                             uint32_t full, empty, dst, ph;
@@ -161,7 +161,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                 }
             }
             uint32_t x_lo[MM_MAX_LAYERS], x_hi[MM_MAX_LAYERS], w_lo[MM_MAX_LAYERS], idesc[MM_MAX_LAYERS], tstride[MM_MAX_LAYERS];
-            int nv[MM_MAX_LAYERS], nk2[MM_MAX_LAYERS], nxc[MM_MAX_LAYERS], vkl[MM_MAX_LAYERS];
+            int nv[MM_MAX_LAYERS], nk1[MM_MAX_LAYERS], nk2[MM_MAX_LAYERS], nxc[MM_MAX_LAYERS], wkl[MM_MAX_LAYERS];
 #pragma unroll
             for (int l = 0; l < MM_MAX_LAYERS; ++l) {
                 const SaLayer &Ly = a.L[l < nL ? l : 0];
@@ -172,9 +172,10 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                 tstride[l] = (uint32_t)(Ly.cpad * 64 * 2) >> 4;            // one full 64-k tile of this layer, in descriptor units
                 idesc[l] = last ? umma_idesc(128, MM_ROWS) : umma_idesc(128, Ly.cpad);
                 nv[l] = Ly.vk >> 4;
+                nk1[l] = a.split ? (Ly.kpad >> 4) : 0x7FFFFFFF;       // split: K blocks [0, nk1) = Xh.Wh, [nk1, nk2) = Xl.Wh, [nk2, nv) = Xh.Wl
                 nk2[l] = a.split ? 2 * (Ly.kpad >> 4) : 0x7FFFFFFF;
                 nxc[l] = Ly.n_xc;
-                vkl[l] = Ly.vk;
+                wkl[l] = Ly.wk;
             }
             mbar_wait(W_FULL(0), 0u);   // the resident weights have landed
             uint32_t job = 0;
@@ -196,9 +197,10 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                         if (leader) {
                             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
                             for (int v = 0; v < nv[l]; ++v) {
-                                const int xblk = v >= nk2[l] ? v - nk2[l] : v;
-                                const int kc = v >> 2, jj = v & 3;
-                                const uint32_t kw = (uint32_t)min(64, vkl[l] - kc * 64);
+                                const int xblk = v >= nk2[l] ? v - nk2[l] : v;       // [hi | lo | hi]
+                                const int wblk = v >= nk1[l] ? v - nk1[l] : v;       // [Wh | Wh | Wl] out of the packed [Wh ; Wl]
+                                const int kc = wblk >> 2, jj = wblk & 3;
+                                const uint32_t kw = (uint32_t)min(64, wkl[l] - kc * 64);
                                 const uint32_t wl = w_lo[l] + (uint32_t)kc * tstride[l] + 16u * (uint32_t)jj;
                                 const uint32_t wh = umma_desc_hi(kw * 16u);
                                 const uint32_t xl = x_lo[l] + 16u * (uint32_t)xblk;
@@ -336,7 +338,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                     const int xbuf = l & 1;
                     const uint32_t x_lo0 = umma_desc_lo(smem_u32(xbuf ? xb : xa), 128u);
                     const uint32_t x_hi = umma_desc_hi((uint32_t)Ly.xw * 16u);
-                    const int nk2 = 2 * (Ly.kpad >> 4);   // split: x blocks [0, nk2) are [hi | lo]; v >= nk2 re-reads hi
+                    const int nk1 = Ly.kpad >> 4;         // split: weight blocks [0, nk1) = Wh (times Xh and Xl), [nk1, 2 nk1) = Wl (times Xh)
                     int xwait = 0;                        // readiness chunks of this layer's input already waited for
                     for (int cci = 0; cci < Ly.n_cc; ++cci, ++job) {
                         const int cc = chunk_of(l, cci, Ly.n_cc);
@@ -347,7 +349,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                         const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 128);
                         const uint32_t idesc = last ? umma_idesc(128, MM_ROWS) : umma_idesc(128, ncols);
                         for (int kc = 0; kc < Ly.n_kc; ++kc) {
-                            const int kw = min(64, Ly.vk - kc * 64);
+                            const int kw = min(64, Ly.wk - kc * 64);
                             uint32_t wbase, wempty = 0u;
                             if (a.resident) {
                                 if (first) { mbar_wait(W_FULL(0), 0u); first = false; }
@@ -394,11 +396,16 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                                     }
                                 } else {
                                     for (int j = 0; j < nk16; ++j) {
-                                        const int v = kc * 4 + j;
-                                        const int xblk = (a.split && v >= nk2) ? v - nk2 : v;
-                                        const uint32_t xl = x_lo0 + 16u * (uint32_t)xblk, wl = w_lo + 16u * (uint32_t)j;
-                                        if (!last) umma_f16_lohi(d_tmem, xl, x_hi, wl, w_hi, idesc, v ? 1u : 0u);
-                                        else umma_f16_lohi(d_tmem, wl, w_hi, xl, x_hi, idesc, v ? 1u : 0u);
+                                        const int wb = kc * 4 + j;   // K block of the packed weights
+                                        const uint32_t wl = w_lo + 16u * (uint32_t)j;
+                                        auto issue = [&](int xblk, uint32_t acc) {
+                                            const uint32_t xl = x_lo0 + 16u * (uint32_t)xblk;
+                                            if (!last) umma_f16_lohi(d_tmem, xl, x_hi, wl, w_hi, idesc, acc);
+                                            else umma_f16_lohi(d_tmem, wl, w_hi, xl, x_hi, idesc, acc);
+                                        };
+                                        if (!a.split) issue(wb, wb ? 1u : 0u);
+                                        else if (wb < nk1) { issue(wb, wb ? 1u : 0u); issue(nk1 + wb, 1u); }   // Xh.Wh + Xl.Wh: one Wh block, two products
+                                        else issue(wb - nk1, 1u);                                              // Xh.Wl
                                     }
                                 }
                                 pf.add(PF_MMA_ISSUE, t_i);
@@ -783,10 +790,11 @@ static int sa_plan(const spsk_sa_mma_desc *d, SaPlan *P) {
         Ly.n_cc = pair ? (cpad + 255) / 256 : (cpad + 127) / 128;
         Ly.xw = split ? 2 * kpad : kpad;
         Ly.vk = split ? 3 * kpad : kpad;
-        Ly.n_kc = (Ly.vk + 63) / 64;
+        Ly.wk = split ? 2 * kpad : kpad;
+        Ly.n_kc = (Ly.wk + 63) / 64;
         Ly.n_xc = (Ly.xw + 63) / 64;
         Ly.w_off = w_off; Ly.bias_off = b_off;
-        w_off += Ly.vk * cpad * 2;
+        w_off += Ly.wk * cpad * 2;
         b_off += cpad;
         const int xbytes = Ly.xw * MM_ROWS * 2;
         if (l & 1) P->xb_bytes = max(P->xb_bytes, xbytes); else P->xa_bytes = max(P->xa_bytes, xbytes);
@@ -868,7 +876,7 @@ static void build_schedule(SaArgs &a) {
         for (int cci = 0; cci < Ly.n_cc; ++cci) {
             const int ncols = (Ly.cpad - cci * 128) < 128 ? (Ly.cpad - cci * 128) : 128;   // (a rotated chunk order only permutes equal 128-wide chunks)
             for (int kc = 0; kc < Ly.n_kc; ++kc, ++e) {
-                const int kw = (Ly.vk - kc * 64) < 64 ? (Ly.vk - kc * 64) : 64;
+                const int kw = (Ly.wk - kc * 64) < 64 ? (Ly.wk - kc * 64) : 64;
                 const int nk16 = kw >> 4;
                 uint32_t f = (uint32_t)nk16;
                 if (kc == 0) f |= 1u << 3;

@@ -19,8 +19,9 @@ struct SaLayer {
     int cpad;      // output width: multiple of 16 (hidden) / 128 (last)
     int n_cc;      // ceil(cpad / 128)
     int xw;        // activation buffer width in halfs: kpad (plain) or 2*kpad (split: [hi | lo])
-    int vk;        // K the MMAs run over: kpad (plain) or 3*kpad (split)
-    int n_kc;      // ceil(vk / 64)  weight tiles per cout chunk
+    int vk;        // K the MMAs run over: kpad (plain) or 3*kpad (split: Xh.Wh + Xl.Wh + Xh.Wl)
+    int wk;        // K of the packed weights: kpad (plain) or 2*kpad (split: [Wh ; Wl], Wh is read by two of the three products)
+    int n_kc;      // ceil(wk / 64)  weight tiles per cout chunk
     int n_xc;      // ceil(xw / 64)  readiness chunks of the activation buffer
     int w_off;     // byte offset of this layer's tiles in the packed weights
     int bias_off;  // float offset into the bias array
@@ -61,7 +62,7 @@ struct SaArgs {
 // byte offset of weight tile (cc, kc) inside a layer: chunks of 128 couts are contiguous (cc-major), inside a chunk
 // the tiles follow each other along K; a tile is ncols x kw fp16 in canonical layout with SBO = kw*16
 __device__ __forceinline__ int wtile_off(const SaLayer &Ly, int cc, int kc, int ncols) {
-    return Ly.w_off + (128 * cc * Ly.vk + ncols * 64 * kc) * 2;
+    return Ly.w_off + (128 * cc * Ly.wk + ncols * 64 * kc) * 2;
 }
 
 // 16 accumulator columns -> + bias -> ReLU -> fp16 -> two 16-byte stores into the next operand (K-major).

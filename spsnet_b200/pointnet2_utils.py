@@ -490,7 +490,7 @@ class MmaChain:
     plain mode : fp16 operands; layer-0 input order [features (ceil8(c_feat)), x, y, z, 0...] (the reference's order
                  is [x, y, z, features], pointnet2_utils.py:315 -- a pure row permutation of W0)
     split mode : chosen automatically for narrow chains (every width <= 64, c_feat <= 8: IA-SSD layer 0); weights
-                 become [Wh; Wh; Wl] so that [Xh | Xl | Xh] . W' = Xh.Wh + Xl.Wh + Xh.Wl  (fp32-grade)
+                 become [Wh; Wl] and the kernel evaluates Xh.Wh + Xl.Wh + Xh.Wl  (fp32-grade)
     """
 
     def __init__(self, chain, c_feat: int, use_xyz: bool, split: bool | None = None, pair: bool | None = None):
@@ -531,7 +531,7 @@ class MmaChain:
             if self.split:
                 Wh = W.half()
                 Wl = (W - Wh.float()).half()
-                Wv = torch.cat([Wh, Wh, Wl], dim=0)
+                Wv = torch.cat([Wh, Wl], dim=0)   # Wh serves two of the three products (Xh.Wh, Xl.Wh), stored once
             else:
                 Wv = W.half()
             vk = Wv.shape[0]
