@@ -309,7 +309,7 @@ def profile_kernels(net, dev_points, steps: int):
         key = name
         if name in ("spsk_farthest_point_sampling",):
             key = f"{name}[n={a[1]},m={a[2]}]"
-        elif name == "spsk_ball_query_msg":
+        elif name in ("spsk_ball_query_msg", "spsk_ball_query_msg_grid"):
             key = f"{name}[n={a[1]},m={a[2]}]"
         elif name == "spsk_grouped_linear":
             key = f"{name}[cin={a[3]},cout={a[6]}]"

@@ -19,7 +19,9 @@ PATTERNS = {  # library call -> kernel name regexes, in launch order (each match
     "spsk_ball_query": [r"ball_query_kernel"],
     "spsk_score_topk": [r"score_topk_kernel"],
     "spsk_gather_rows": [r"gather_rows_kernel"],
-    "spsk_gather_points": [r"gather_"],
+    "spsk_gather_points": [r"gather_cols_kernel|gather_points"],
+    "spsk_ball_query_grid_workspace_bytes": [], "spsk_nms_workspace_bytes": [], "spsk_detect_workspace_bytes": [],
+    "spsk_scatter_grad_workspace_bytes": [], "spsk_sa_mma_config": [], "spsk_fp16_overflow_poll": [],
     "spsk_make_twin": [r"make_twin_kernel"],
     "spsk_grouped_linear": [r"linear_ffma|grouped"],
     "spsk_pointwise_linear": [r"linear_ffma|pointwise"],

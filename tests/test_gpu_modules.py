@@ -13,6 +13,9 @@ from helpers import assert_close, make_backbone, rel_err, small_sa_cfg  # noqa: 
 from spsnet_b200 import scenes  # noqa: E402
 
 
+REL_TOL_LOGITS = 1e-3   # north_star: MLP outputs within 1e-3 relative
+
+
 def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
@@ -113,15 +116,14 @@ def test_sa_module_vs_reference_modules(ref_ops, kind, n):
     np.testing.assert_array_equal(got[0].cpu().numpy(), want[0].cpu().numpy())  # new_xyz
     assert_close(got[1].cpu().numpy(), want[1].cpu().numpy(), what=f"{kind} new_features vs reference")
     if want[2] is not None:
-        # The class logits sit three more GEMMs downstream and, with random heads, span a range ~10x smaller than the
-        # features they are computed from, so their range-relative error is amplified for ANY 11-bit-significand path:
-        # the bar is 1e-3, or -- when the reference's own stock configuration (cuDNN TF32) misses that against its fp32
-        # self on the same inputs -- no worse than 1.25x the reference's own deviation (measured in this test).
+        # The class logits decide the next layer's top-k picks: same 1e-3 bar as the features, no escape clause.  (The reference's
+        # own stock configuration -- cuDNN TF32 -- is printed next to it: it misses the bar on some heads, the fused path, whose
+        # aggregation / confidence GEMMs are fp32-grade hi + lo arithmetic, does not: scripts/diag_precision.py, six seeds,
+        # profiles/r02_diag_precision.txt.)
         e = rel_err(got[2].cpu().numpy(), want[2].cpu().numpy())
         e_ref = rel_err(stock[2].cpu().numpy(), want[2].cpu().numpy())
         print(f"[cls] {kind}: ours vs reference-fp32 {e:.2e}; reference stock (TF32) vs reference-fp32 {e_ref:.2e}")
-        tol = max(1e-3, 1.25 * e_ref)
-        assert e <= tol, f"{kind} cls vs reference: relative error {e:.3e} > {tol:.1e}"
+        assert e <= REL_TOL_LOGITS, f"{kind} cls vs reference: relative error {e:.3e} > {REL_TOL_LOGITS:.1e}"
 
 
 @pytest.mark.parametrize("stype,n,npoint", [("F-FPS", 1024, 256), ("FS", 1024, 128), ("ds_FPS", 2048, 512), ("ry_FPS", 2048, 512),
