@@ -214,7 +214,7 @@ __device__ __forceinline__ void st_cluster_v4(const void *local_ptr, uint32_t ct
 template <int P, bool CL, int LADDER, bool PROF, int ST>
 __global__ void __launch_bounds__(512, 1)
 fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__restrict__ temp, int *__restrict__ idx,
-                  unsigned long long *__restrict__ prof) {
+                  unsigned long long *__restrict__ prof, int bitonic) {
     constexpr int T = 512, W = 16, NP = T * P;
     constexpr bool TM = ST == 1, SM = ST == 2, GEN = ST != 0;
     constexpr uint32_t s_mask = 1023u, s_log2 = 10u;   // reference block size is 1024 for n >= 1024
@@ -268,42 +268,93 @@ fps_pruned_kernel(int n_scene, int m, const float *__restrict__ src, float *__re
         const float cells = (c == 2) ? 16.f : 128.f;
         scl[c] = cells / fmaxf(h - l, 1e-20f);
     }
-    // ---- keys: (7+7-bit xy Morton code, 4-bit z cell) << 14 | index ; padding sorts last
-    for (int i = tid; i < NP; i += T) {
-        uint32_t key = 0xFFFFFFFFu;
-        if (i < n) {
-            const float x = __ldg(base + (size_t)i * 3), y = __ldg(base + (size_t)i * 3 + 1), z = __ldg(base + (size_t)i * 3 + 2);
-            uint32_t cx = min(127, max(0, (int)((x - org[0]) * scl[0])));
-            uint32_t cy = min(127, max(0, (int)((y - org[1]) * scl[1])));
-            const uint32_t cz = min(15, max(0, (int)((z - org[2]) * scl[2])));
-            cx = (cx | (cx << 4)) & 0x0F0Fu; cx = (cx | (cx << 2)) & 0x3333u; cx = (cx | (cx << 1)) & 0x5555u;
-            cy = (cy | (cy << 4)) & 0x0F0Fu; cy = (cy | (cy << 2)) & 0x3333u; cy = (cy | (cy << 1)) & 0x5555u;
-            // the top cell's last z slice is merged into its neighbour so that no real key equals the padding key
-            // 0xFFFFFFFF (code 0x3FFFF with local index 16383 would); cells only decide how much is pruned, never the result
-            const uint32_t code = min((((cx | (cy << 1)) & 0x3FFFu) << 4) | cz, 0x3FFFEu);
-            key = (code << 14) | (uint32_t)i;
+    // ---- spatial order of the owned points.  It only decides HOW MUCH is pruned, never the result, so it need not be a total
+    // order: a counting sort by the top log2(NP) bits of the (7+7-bit xy Morton, 4-bit z) cell code -- as many cells as point
+    // slots -- replaces the full bitonic sort of (code, index) keys, which cost ~8 % of the 16384 -> 4096 kernel (105 passes over
+    // 16384 keys, a block barrier each).  Shared-memory atomics, one scan, one scatter; the order inside a cell is whatever the
+    // atomics give (run to run the sub-buckets may differ, the samples cannot).  `bitonic` keeps the round-1 sort for A/B.
+    auto cell_code = [&](int i) -> uint32_t {
+        const float x = __ldg(base + (size_t)i * 3), y = __ldg(base + (size_t)i * 3 + 1), z = __ldg(base + (size_t)i * 3 + 2);
+        uint32_t cx = min(127, max(0, (int)((x - org[0]) * scl[0])));
+        uint32_t cy = min(127, max(0, (int)((y - org[1]) * scl[1])));
+        const uint32_t cz = min(15, max(0, (int)((z - org[2]) * scl[2])));
+        cx = (cx | (cx << 4)) & 0x0F0Fu; cx = (cx | (cx << 2)) & 0x3333u; cx = (cx | (cx << 1)) & 0x5555u;
+        cy = (cy | (cy << 4)) & 0x0F0Fu; cy = (cy | (cy << 2)) & 0x3333u; cy = (cy | (cy << 1)) & 0x5555u;
+        return (((cx | (cy << 1)) & 0x3FFFu) << 4) | cz;   // 18 bits
+    };
+    unsigned short *sorted16 = reinterpret_cast<unsigned short *>(smem) + 3 * NP;   // counting sort: point index by sorted position
+    if (bitonic) {
+        // keys: cell code << 14 | index ; padding sorts last
+        for (int i = tid; i < NP; i += T) {
+            uint32_t key = 0xFFFFFFFFu;
+            // the top cell's last z slice is merged into its neighbour so that no real key equals the padding key 0xFFFFFFFF
+            // (code 0x3FFFF with local index 16383 would)
+            if (i < n) key = (min(cell_code(i), 0x3FFFEu) << 14) | (uint32_t)i;
+            keys[i] = key;
         }
-        keys[i] = key;
-    }
-    __syncthreads();
-    for (int k = 2; k <= NP; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < NP; i += T) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const uint32_t a = keys[i], b = keys[ixj];
-                    const bool up = (i & k) == 0;
-                    if (up ? (a > b) : (a < b)) { keys[i] = b; keys[ixj] = a; }
+        __syncthreads();
+        for (int k = 2; k <= NP; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < NP; i += T) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const uint32_t a = keys[i], b = keys[ixj];
+                        const bool up = (i & k) == 0;
+                        if (up ? (a > b) : (a < b)) { keys[i] = b; keys[ixj] = a; }
+                    }
                 }
+                __syncthreads();
             }
-            __syncthreads();
         }
+    } else {
+        // [hist u32 x NP][codes u16 x NP][sorted u16 x NP] = 8 NP bytes of the 12 NP-byte xyz region
+        uint32_t *hist = reinterpret_cast<uint32_t *>(smem);
+        unsigned short *codes = reinterpret_cast<unsigned short *>(smem) + 2 * NP;
+        constexpr int CB = (P == 2 ? 10 : P == 4 ? 11 : P == 8 ? 12 : P == 16 ? 13 : 14);   // log2(NP) cells
+        for (int i = tid; i < NP; i += T) { hist[i] = 0u; sorted16[i] = 0xFFFFu; }
+        __syncthreads();
+        for (int i = tid; i < n; i += T) {
+            const uint32_t c = cell_code(i) >> (18 - CB);
+            codes[i] = (unsigned short)c;
+            atomicAdd(&hist[c], 1u);
+        }
+        __syncthreads();
+        // exclusive scan over the NP counters: thread t owns counters [t P, (t + 1) P)
+        uint32_t loc[P], run = 0u;
+#pragma unroll
+        for (int p = 0; p < P; ++p) { loc[p] = run; run += hist[tid * P + p]; }
+        uint32_t inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= o) inc += up;
+        }
+        uint32_t *wsum = reinterpret_cast<uint32_t *>(&red[0][0]);   // 16 warp totals (red is free again: the box is reduced)
+        __syncthreads();
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        uint32_t wbase = 0u;
+        for (int w = 0; w < warp; ++w) wbase += wsum[w];
+        const uint32_t excl = wbase + inc - run;
+#pragma unroll
+        for (int p = 0; p < P; ++p) hist[tid * P + p] = excl + loc[p];
+        __syncthreads();
+        for (int i = tid; i < n; i += T) sorted16[atomicAdd(&hist[codes[i]], 1u)] = (unsigned short)i;
+        __syncthreads();
     }
     // ---- take ownership: slot p of this lane = sorted position ((p*W + warp)*32 + lane)
     uint32_t oidx[P];
     float tmp[GEN ? 1 : P];
 #pragma unroll
-    for (int p = 0; p < P; ++p) oidx[p] = keys[(p * W + warp) * 32 + lane];
+    for (int p = 0; p < P; ++p) {
+        const int spos = (p * W + warp) * 32 + lane;
+        if (bitonic) {
+            oidx[p] = keys[spos];
+        } else {
+            const uint32_t v = sorted16[spos];
+            oidx[p] = v == 0xFFFFu ? 0xFFFFFFFFu : v;
+        }
+    }
     if (TM) tc_fence_before();
     __syncthreads();   // keys consumed; the region becomes sx/sy/sz
     uint32_t tbase = 0u;   // TM: this warp's first column in its lane quarter
@@ -601,12 +652,13 @@ static int launch_fps_pruned_v(int b, int n, int m, int csize, const float *src,
     const size_t smem = sizeof(float) * 3 * 512 * P + (CL ? 0 : sizeof(unsigned short) * 512 * P)   // xyz (+ index -> position map)
                         + (ST == 2 ? 8 * 512 * P : 0);                                               // (+ minima and ~rank)
     auto kern = fps_pruned_kernel<P, CL, LADDER, PROF, ST>;
+    static const int bitonic = getenv("SPSK_FPS_SORT") != nullptr && getenv("SPSK_FPS_SORT")[0] == 'b' ? 1 : 0;   // A/B: the round-1 full sort
     if (smem + 8192 > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fps_pruned_kernel)");
     }
     if (!CL) {
-        kern<<<b, 512, smem, st>>>(n, m, src, temp, idx, g_fps_prof);
+        kern<<<b, 512, smem, st>>>(n, m, src, temp, idx, g_fps_prof, bitonic);
     } else {
         if (csize > 8) {
             // 16-CTA clusters are a non-portable size: opt in, and make sure this device can co-schedule one
@@ -630,7 +682,7 @@ static int launch_fps_pruned_v(int b, int n, int m, int csize, const float *src,
             cudaError_t q = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
             if (q != cudaSuccess || nclusters < 1) { (void)cudaGetLastError(); return SPSK_FPS_NO_CLUSTER; }
         }
-        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, n, m, src, temp, idx, g_fps_prof);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, n, m, src, temp, idx, g_fps_prof, bitonic);
         if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(fps_pruned_kernel, cluster)");
     }
     SPSK_LAUNCH_CHECK("fps_pruned_kernel");
