@@ -338,9 +338,8 @@ extern "C" int spsk_ball_query_msg_grid(int b, int n, int m, int nscales, const 
     SPSK_LAUNCH_CHECK("bq_grid_build_kernel");
     // prefix-scan policy (see the kernel): start at BG_PREFIX_MIN candidates, scan `cand` points.  SPSK_BQ_PREFIX_MIN /
     // SPSK_BQ_PREFIX_MUL4 (length = cand * MUL4 / 4) are tuning knobs for A/B measurements.
-    int prefix_min = BG_PREFIX_MIN, prefix_mul4 = 4;
-    if (const char *e = getenv("SPSK_BQ_PREFIX_MIN")) prefix_min = max(32, atoi(e));
-    if (const char *e = getenv("SPSK_BQ_PREFIX_MUL4")) prefix_mul4 = max(1, atoi(e));
+    static const int prefix_min = [] { const char *e = getenv("SPSK_BQ_PREFIX_MIN"); return e ? max(32, atoi(e)) : BG_PREFIX_MIN; }();
+    static const int prefix_mul4 = [] { const char *e = getenv("SPSK_BQ_PREFIX_MUL4"); return e ? max(1, atoi(e)) : 4; }();
     const int words = (n + 31) / 32;
     const size_t smem = sizeof(uint32_t) * (size_t)BG_WARPS * nscales * words;
     SPSK_REQUIRE(smem <= 200 * 1024, SPSK_ERR_UNSUPPORTED, "ball_query_msg_grid: bitmap of %zu B does not fit shared memory", smem);

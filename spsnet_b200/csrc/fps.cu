@@ -654,8 +654,8 @@ static int launch_fps_pruned_v(int b, int n, int m, int csize, const float *src,
     auto kern = fps_pruned_kernel<P, CL, LADDER, PROF, ST>;
     static const int bitonic = getenv("SPSK_FPS_SORT") != nullptr && getenv("SPSK_FPS_SORT")[0] == 'b' ? 1 : 0;   // A/B: the round-1 full sort
     if (smem + 8192 > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(fps_pruned_kernel)");
+        static SmemAttrOnce attr;   // one static per template instantiation: set once per (kernel, device), not per launch
+        if (int rc = attr.ensure(reinterpret_cast<const void *>(kern), (int)smem, "cudaFuncSetAttribute(fps_pruned_kernel)")) return rc;
     }
     if (!CL) {
         kern<<<b, 512, smem, st>>>(n, m, src, temp, idx, g_fps_prof, bitonic);
@@ -702,8 +702,8 @@ static int launch_fps_pruned(int b, int n, int m, int csize, const float *src, f
         if (g_fps_prof != nullptr) return launch_fps_pruned_v<P, CL, 2, true, ST>(b, n, m, csize, src, temp, idx, st);
         return launch_fps_pruned_v<P, CL, 2, false, ST>(b, n, m, csize, src, temp, idx, st);
     }
-    int mode = 2;   // 1 = ladder, 2 = two-level ladder (fastest at every P on B200), 0 = switch over set bits
-    if (const char *e = getenv("SPSK_FPS_DISPATCH")) mode = e[0] == 'l' ? 1 : (e[0] == 'g' ? 2 : 0);
+    // 1 = ladder, 2 = two-level ladder (fastest at every P on B200), 0 = switch over set bits (A/B knob of the register kernel)
+    static const int mode = [] { const char *e = getenv("SPSK_FPS_DISPATCH"); return !e ? 2 : (e[0] == 'l' ? 1 : (e[0] == 'g' ? 2 : 0)); }();
     if (mode == 1) return launch_fps_pruned_v<P, CL, 1>(b, n, m, csize, src, temp, idx, st);
     if (mode == 2 && g_fps_prof != nullptr) return launch_fps_pruned_v<P, CL, 2, true>(b, n, m, csize, src, temp, idx, st);
     if (mode == 2) return launch_fps_pruned_v<P, CL, 2>(b, n, m, csize, src, temp, idx, st);
@@ -891,7 +891,8 @@ static int fps_dispatch(int b, int n, int m, const float *src, float *temp, int 
     // cannot co-schedule it)
     if (!DISTMAT && threads == 1024 && n > 16384 && n <= 16 * 16384 && !fps_dense_forced()) {
         int cl = n <= 2 * 16384 ? 2 : (n <= 4 * 16384 ? 4 : (n <= 8 * 16384 ? 8 : 16));
-        if (const char *e = getenv("SPSK_FPS_CLUSTER")) { const int v = atoi(e); if ((v == 2 || v == 4 || v == 8 || v == 16) && v >= cl) cl = v; }
+        static const int want_cl = [] { const char *e = getenv("SPSK_FPS_CLUSTER"); return e ? atoi(e) : 0; }();
+        if ((want_cl == 2 || want_cl == 4 || want_cl == 8 || want_cl == 16) && want_cl >= cl) cl = want_cl;
         const int per_cta = (n + cl - 1) / cl;
         int rc;
         if (per_cta <= 2048) rc = launch_fps_pruned<4, true>(b, n, m, cl, src, temp, idx, st);

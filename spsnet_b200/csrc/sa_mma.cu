@@ -761,6 +761,28 @@ make_twin_kernel(int c, int n, int cpad8, const float *__restrict__ in, __half *
 
 static unsigned long long *g_sa_prof = nullptr;
 
+// ---- tuning / A-B knobs: environment variables, read ONCE per process (not on every launch) -------------------------------
+struct SaTuning {
+    int max_stages, max_ctas, grid_mult;
+    bool no_lring, no_sched, rot, no_narrow, one_group, scout;
+    SaTuning() {
+        auto geti = [](const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; };
+        max_stages = max(2, min(MM_MAX_STAGES, geti("SPSK_SA_MAX_STAGES", MM_MAX_STAGES)));   // sensitivity measurements
+        max_ctas = max(1, min(4, geti("SPSK_SA_MAX_CTAS", 4)));
+        grid_mult = max(1, min(8, geti("SPSK_SA_GRID_MULT", 1)));   // persistent CTAs, exactly one resident set (2 measured 1 % slower with 8 batches in flight)
+        no_lring = getenv("SPSK_SA_NO_LRING") != nullptr;
+        no_sched = getenv("SPSK_SA_NO_SCHED") != nullptr;
+        rot = getenv("SPSK_SA_ROT") != nullptr;              // opt-in: measured neutral on B200 (the weight stream is not L2 hot-line bound)
+        no_narrow = getenv("SPSK_SA_NO_NARROW") != nullptr;
+        one_group = getenv("SPSK_SA_ONE_GROUP") != nullptr;
+        scout = getenv("SPSK_SA_SCOUT") != nullptr;          // opt-in: measured neutral on B200 (292 vs 280-290 us on layer 5 scale 2): the waits it removes are real stalls
+    }
+};
+static const SaTuning &sa_tuning() {
+    static const SaTuning t;
+    return t;
+}
+
 // ---- host-side planning ---------------------------------------------------------------------------------
 struct SaPlan {
     SaLayer L[MM_MAX_LAYERS];
@@ -816,13 +838,12 @@ static int sa_plan(const spsk_sa_mma_desc *d, SaPlan *P) {
         if (xtot + P->w_total <= per) { *resident = 1; *nstages = 1; *smem = xtot + P->w_total; return true; }
         const int st = (per - xtot) / MM_STAGE_BYTES;
         if (st < 2) return false;
-        int cap = MM_MAX_STAGES;
-        if (const char *e = getenv("SPSK_SA_MAX_STAGES")) cap = max(2, min(MM_MAX_STAGES, atoi(e)));   // tuning / sensitivity measurements
+        const int cap = sa_tuning().max_stages;
         *resident = 0; *nstages = st > cap ? cap : st; *smem = xtot + *nstages * MM_STAGE_BYTES;
         return true;
     };
-    int ctas = 0, cmax = pair ? 1 : 4;
-    if (const char *e = getenv("SPSK_SA_MAX_CTAS")) cmax = max(1, min(4, atoi(e)));   // tuning / A-B measurements
+    int ctas = 0;
+    const int cmax = pair ? 1 : sa_tuning().max_ctas;
     bool one_job_per_layer = true;   // the register-resident "narrow" issue loop (the only one the 4-CTA shape runs)
     for (int l = 0; l < nL; ++l) one_job_per_layer = one_job_per_layer && P->L[l].n_cc == 1;
     for (int c = cmax; c >= 1; --c) {
@@ -842,7 +863,7 @@ static int sa_plan(const spsk_sa_mma_desc *d, SaPlan *P) {
         P->nstages = min(MM_MAX_STAGES, max(2, (P->smem - xtot) / MM_STAGE_BYTES));
         P->smem = xtot + P->nstages * MM_STAGE_BYTES;
     }
-    if (!P->resident && P->nstages < 4 && nL >= 2 && !getenv("SPSK_SA_NO_LRING")) {
+    if (!P->resident && P->nstages < 4 && nL >= 2 && !sa_tuning().no_lring) {
         const int other = ((nL - 2) & 1) ? P->xb_bytes : P->xa_bytes;
         const int e = other / MM_STAGE_BYTES;
         if (e >= 3) P->lstages = e > MM_MAX_STAGES ? MM_MAX_STAGES : e;
@@ -851,7 +872,7 @@ static int sa_plan(const spsk_sa_mma_desc *d, SaPlan *P) {
     P->nbuf = P->tmem_cols / 128;
     // streaming chains: tabulate the per-tile MMA schedule (one 16-byte entry per weight tile) into the kernel parameters
     P->sched_n = 0;
-    if (!pair && !P->resident && !split && !getenv("SPSK_SA_NO_SCHED")) {
+    if (!pair && !P->resident && !split && !sa_tuning().no_sched) {
         int ntab = 0;
         for (int l = 0; l < nL; ++l) ntab += P->L[l].n_cc * P->L[l].n_kc;
         if (ntab <= MM_SCHED_MAX) P->sched_n = ntab;
@@ -969,13 +990,12 @@ extern "C" int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stre
     a.ntiles = (int)ntiles;
     a.lstages = P.lstages;
     a.sched_n = P.sched_n;
-    static const bool want_scout = getenv("SPSK_SA_SCOUT") != nullptr;   // opt-in (A/B knob): measured neutral on B200 (292 vs 280-290 us on layer 5 scale 2) -- the waits it removes are real stalls, not overhead
-    a.scout = want_scout ? 1 : 0;
-    a.rot_last = (P.L[d->nlayers - 1].n_cc > 1 && getenv("SPSK_SA_ROT")) ? 1 : 0;   // opt-in: measured neutral on B200 (the weight stream is not L2 hot-line bound)
+    a.scout = sa_tuning().scout ? 1 : 0;
+    a.rot_last = (P.L[d->nlayers - 1].n_cc > 1 && sa_tuning().rot) ? 1 : 0;
     a.l0_fused = d->l0_fused ? 1 : 0;
     a.l0_off = P.l0_off;
     SPSK_REQUIRE(!a.l0_fused || P.resident, SPSK_ERR_UNSUPPORTED, "sa_mma: layer-0 fusion needs the chain resident in shared memory");
-    a.narrow = P.resident && !getenv("SPSK_SA_NO_NARROW");
+    a.narrow = P.resident && !sa_tuning().no_narrow;
     for (int l = 0; l < d->nlayers; ++l)
         if (P.L[l].n_cc != 1) a.narrow = 0;
     a.nstages = P.nstages; a.resident = P.resident; a.w_total = P.w_total; a.tmem_cols = P.tmem_cols; a.nbuf = P.nbuf;
@@ -1001,12 +1021,11 @@ extern "C" int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stre
         a.ntiles = (int)((a.rows + 255) / 256);   // 256-row tiles, one per CTA pair
         return spsk_sa_mma_pair_launch(a, P.smem, as_stream(stream));
     }
-    int mult = 1;   // persistent CTAs, exactly one resident set (2 measured 1 % slower with 8 batches in flight)
-    if (const char *e = getenv("SPSK_SA_GRID_MULT")) mult = max(1, min(8, atoi(e)));
+    const int mult = sa_tuning().grid_mult;
     const int slots = SPSK_NUM_SMS * P.ctas * mult;
     const int grid = a.ntiles < slots ? a.ntiles : slots;
     if (a.sched_n > 0) build_schedule(a);
-    const bool two_groups = P.ctas == 1 && !getenv("SPSK_SA_ONE_GROUP");
+    const bool two_groups = P.ctas == 1 && !sa_tuning().one_group;
     const bool sc = a.scout && a.sched_n > 0 && !a.narrow && (two_groups || P.ctas <= 2);
     a.scout = sc ? 1 : 0;
 #define SPSK_SA_LAUNCH(GV, PV, SCV)                                                                                          \
