@@ -222,8 +222,9 @@ SPSK_API int spsk_make_twin(int b, int c, int n, int cpad8, const float *feature
  *               of 128), cpad[l] == kpad[l+1].  Plain mode: kpad[0] >= ceil8(c_feat) + 8*use_xyz with k order
  *               [features (ceil8(c_feat)), x, y, z, 0...].  Split mode: kpad[0] == 16, k order [f0..f7, x, y, z, 0...]
  *               (c_feat <= 8; xyz first when c_feat == 0), every width <= 64.
- *   wtiles    : per layer (layers concatenated) the matrix W'[vk, cpad] (vk = kpad, or 3*kpad = [Wh; Wh; Wl] rows in
- *               split mode) cut into tiles of (<=128 couts) x (<=64 k), ordered cout-chunk major then k, each tile
+ *   wtiles    : per layer (layers concatenated) the matrix W'[wk, cpad] (wk = kpad, or 2*kpad = [Wh; Wl] rows in
+ *               split mode -- the kernel runs 3*kpad of K per tile, Xh.Wh + Xl.Wh + Xh.Wl, reading the Wh rows twice)
+ *               cut into tiles of (<=128 couts) x (<=64 k), ordered cout-chunk major then k, each tile
  *               `ncols x kw` fp16 in the canonical K-major no-swizzle UMMA layout
  *               byte(r, k) = (r/8)*(kw*16) + (k/8)*128 + (r%8)*16 + (k%8)*2;  zero padded
  *   bias      : folded BN shift, layers concatenated, cpad[l] floats each (zero padded)
