@@ -43,7 +43,7 @@ typedef enum spsk_status {
 
 /* Human-readable description of the last error raised on the calling thread. */
 SPSK_API const char *spsk_last_error(void);
-/* ABI version of this header (bumped on any signature change or added entry point; currently 2). */
+/* ABI version of this header (bumped on any signature change or added entry point; currently 4). */
 SPSK_API int spsk_abi_version(void);
 /* Number of CUDA kernels this library has launched in this process (all threads). */
 SPSK_API unsigned long long spsk_launch_count(void);
@@ -259,6 +259,14 @@ typedef struct spsk_sa_mma_desc {
                                couts each), each as tiles of <= 64 k in the canonical layout */
     int ovf_tag;            /* fp16 range guard: bit (ovf_tag & 31) of the per-device overflow word is set when a hidden activation or
                                an fp16 output of this call exceeds 65504 (see spsk_fp16_overflow_poll); appended in ABI 3 */
+    double *stats;          /* non-NULL: BATCH-STATISTICS pass of training-mode BatchNorm (reference pointnet2_modules.py:203-211 with
+                               the module in train()): the chain is evaluated as usual, but the last layer's epilogue, instead of bias
+                               + ReLU + max-pool, adds the raw accumulators z[row, c] of every real row into per-CTA partial sums
+                               stats[(part * cpad_last + c) * 2 + {0, 1}] += {sum z, sum z*z}   (fp32 inside a 128-row tile, fp64
+                               across tiles; each (part, c) cell is owned by ONE thread: no atomics, bit-reproducible).  The caller
+                               zeroes the buffer, sums it over `part` and divides by b*m*nsample; out_cm / out16 are not written
+                               and may be NULL.  Plain launch shapes only (pair == 0).  Appended in ABI 4 */
+    int stats_parts;        /* capacity of `stats` in parts; must be >= spsk_sa_mma_stats_parts() of this descriptor */
 } spsk_sa_mma_desc;
 
 /* Launch shape the library picks for a chain (only nlayers / kpad / cpad / split are read): dynamic shared memory,
@@ -266,6 +274,8 @@ typedef struct spsk_sa_mma_desc {
  * SPSK_ERR_UNSUPPORTED when the chain does not fit. */
 SPSK_API int spsk_sa_mma_config(const spsk_sa_mma_desc *d, int *smem_bytes, int *ctas_per_sm, int *nstages, int *resident);
 SPSK_API int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stream);
+/* Number of partial-sum slices a statistics pass of this descriptor (sizes and chain filled in) writes: CTAs x epilogue groups. */
+SPSK_API int spsk_sa_mma_stats_parts(const spsk_sa_mma_desc *d, int *nparts);
 /* Tuning aid: when `counters` (device memory, SPSK_SA_PROF_COUNTERS x u64, zeroed by the caller) is non-NULL every
  * following spsk_sa_mma_forward adds the SM cycles its warp roles spent per wait / work category (order: mma total,
  * mma wait acc-empty, mma wait weights, mma wait activations, producer wait stage, producer wait hidden-done, epilogue

@@ -47,6 +47,7 @@ SIGNATURES = {
     "spsk_make_twin": [_i, _i, _i, _i, _p, _p, _p],
     "spsk_sa_mma_config": [_p, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)],
     "spsk_sa_mma_forward": [_p, _p],
+    "spsk_sa_mma_stats_parts": [_p, C.POINTER(_i)],
     "spsk_sa_mma_set_profile": [_p],
     "spsk_pw_mma_forward": [_p, _p],
     "spsk_fp16_overflow_poll": [C.POINTER(C.c_uint), _i],
@@ -88,6 +89,7 @@ class SaMmaDesc(C.Structure):
         ("wtiles", _p), ("bias", _p), ("cout_last", _i),
         ("out_cm", _p), ("c_total", _i), ("co_off", _i),
         ("out16", _p), ("ld16", _i), ("co16", _i), ("n16", _i), ("o16lo", _i), ("l0_fused", _i), ("pair", _i), ("ovf_tag", _i),
+        ("stats", _p), ("stats_parts", _i),
     ]
 
 

@@ -687,6 +687,24 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                     pf.add(PF_EPI_WORK_HID, t_w);
                 }
             }
+            // ---- batch-statistics pass (training-mode BN): last layer D[cout, row], thread = cout; no bias / ReLU / pool, the raw
+            //      accumulators of the tile's real rows are summed per cout into this (CTA, group)'s slice of a.stats
+            if (a.stats) {
+                const SaLayer &Ly = a.L[nL - 1];
+                const long long left = a.rows - (long long)tile * MM_ROWS;
+                const int nv = left < MM_ROWS ? (int)left : MM_ROWS;
+                double *slice = a.stats + (size_t)(blockIdx.x * G + (G == 2 ? grp : 0u)) * (size_t)Ly.cpad * 2;
+                for (int cci = 0; cci < Ly.n_cc; ++cci, ++job) {
+                    if (G == 2 && (job & 1u) != grp) continue;
+                    const int cc = chunk_of(nL - 1, cci, Ly.n_cc);
+                    const int buf = (int)(job & ((uint32_t)a.nbuf - 1u));
+                    mbar_wait(ACC_FULL(buf), (job >> a.nbuf_log2) & 1u);
+                    tc_fence_after();
+                    stats_chunk(tmem_base + lane_field + (uint32_t)(buf * 128), nv, slice + (size_t)(cc * 128 + r) * 2);
+                    tc_fence_before();
+                    mbar_arrive(ACC_EMPTY(buf));
+                }
+            } else
             // ---- last layer: D[cout, row]; thread = cout; max over each centre's nsample columns
             {
                 const SaLayer &Ly = a.L[nL - 1];
@@ -950,10 +968,26 @@ extern "C" int spsk_sa_mma_config(const spsk_sa_mma_desc *d, int *smem_bytes, in
     return SPSK_OK;
 }
 
+extern "C" int spsk_sa_mma_stats_parts(const spsk_sa_mma_desc *d, int *nparts) {
+    using namespace spsk;
+    SPSK_REQUIRE(d && nparts, SPSK_ERR_INVALID_ARG, "sa_mma: null descriptor");
+    SPSK_REQUIRE(!d->pair, SPSK_ERR_UNSUPPORTED, "sa_mma: the batch-statistics pass runs on the single-CTA kernel (pair == 0)");
+    SaPlan P;
+    if (int rc = sa_plan(d, &P)) return rc;
+    const long long rows = (long long)d->b * d->m * d->nsample;
+    const long long ntiles = (rows + MM_ROWS - 1) / MM_ROWS;
+    const long long slots = (long long)SPSK_NUM_SMS * P.ctas * sa_tuning().grid_mult;
+    const long long grid = ntiles < slots ? ntiles : slots;
+    const bool two_groups = P.ctas == 1 && !sa_tuning().one_group;
+    *nparts = (int)(grid * (two_groups ? 2 : 1));
+    return SPSK_OK;
+}
+
 extern "C" int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stream) {
     using namespace spsk;
     SPSK_REQUIRE(d, SPSK_ERR_INVALID_ARG, "sa_mma: null descriptor");
-    SPSK_REQUIRE(d->wtiles && d->bias && (d->out_cm || d->out16), SPSK_ERR_INVALID_ARG, "sa_mma: null weights / no output");
+    SPSK_REQUIRE(d->wtiles && d->bias && (d->out_cm || d->out16 || d->stats), SPSK_ERR_INVALID_ARG, "sa_mma: null weights / no output");
+    SPSK_REQUIRE(!d->stats || !d->pair, SPSK_ERR_UNSUPPORTED, "sa_mma: the batch-statistics pass runs on the single-CTA kernel (pair == 0)");
     SPSK_REQUIRE(d->nsample >= 1 && d->nsample <= MM_ROWS && (d->nsample & (d->nsample - 1)) == 0, SPSK_ERR_UNSUPPORTED,
                  "sa_mma: nsample=%d must be a power of two <= %d", d->nsample, MM_ROWS);
     SPSK_REQUIRE(d->b >= 0 && d->n >= 1 && d->m >= 0 && d->c_feat >= 0, SPSK_ERR_INVALID_ARG, "sa_mma: bad sizes");
@@ -1017,6 +1051,7 @@ extern "C" int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stre
     a.prof = g_sa_prof;
     a.ovf = fp16_overflow_word();
     a.ovf_bit = 1u << (d->ovf_tag & 31);
+    a.stats = d->stats;
     if (d->pair) {
         a.ntiles = (int)((a.rows + 255) / 256);   // 256-row tiles, one per CTA pair
         return spsk_sa_mma_pair_launch(a, P.smem, as_stream(stream));
@@ -1026,6 +1061,12 @@ extern "C" int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stre
     const int grid = a.ntiles < slots ? a.ntiles : slots;
     if (a.sched_n > 0) build_schedule(a);
     const bool two_groups = P.ctas == 1 && !sa_tuning().one_group;
+    if (a.stats) {
+        SPSK_REQUIRE((reinterpret_cast<uintptr_t>(d->stats) & 15) == 0, SPSK_ERR_INVALID_ARG, "sa_mma: stats must be 16-byte aligned");
+        SPSK_REQUIRE(d->stats_parts >= grid * (two_groups ? 2 : 1), SPSK_ERR_INVALID_ARG, "sa_mma: stats holds %d parts, this launch writes %d",
+                     d->stats_parts, grid * (two_groups ? 2 : 1));
+        a.out = nullptr; a.out16 = nullptr;
+    }
     const bool sc = a.scout && a.sched_n > 0 && !a.narrow && (two_groups || P.ctas <= 2);
     a.scout = sc ? 1 : 0;
 #define SPSK_SA_LAUNCH(GV, PV, SCV)                                                                                          \

@@ -56,6 +56,7 @@ struct SaArgs {
     unsigned long long *prof;   // optional per-role wait/work cycle counters (spsk_sa_mma_set_profile), null = off
     unsigned int *ovf;          // fp16 range guard word of this device (may be null) and this call's tag bit
     unsigned int ovf_bit;
+    double *stats;              // batch-statistics pass (training-mode BN): per-(CTA, epilogue group) partial sums, see include/spsk.h
     uint4 sched[MM_SCHED_MAX];  // streaming chains: the per-tile MMA schedule (sched_n entries), see sa_mma.cu::build_schedule
 };
 
@@ -173,6 +174,28 @@ static __device__ __noinline__ void pool_chunk_any(uint32_t taddr, PoolOut &o, i
             if (((c0 + i + 1) & (ns - 1)) == 0) { o.emit(run); run = -3.0e38f; }
         }
     }
+}
+
+// Batch-statistics pass: thread = cout, columns = the tile's rows.  Sum and sum of squares of the raw accumulators over the
+// `nv` real rows of the tile (fp32 over <= 128 values), added in fp64 to the cell this thread owns (no other thread of the grid
+// touches it: plain read-modify-write, reproducible bit for bit).
+static __device__ __forceinline__ void stats_chunk(uint32_t taddr, int nv, double *cell) {
+    float s = 0.f, q = 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < nv; c0 += 32) {
+        float v[32];
+        tmem_ld32(taddr + (uint32_t)c0, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const float x = (c0 + i < nv) ? v[i] : 0.f;
+            s += x;
+            q = fmaf(x, x, q);
+        }
+    }
+    double2 acc = *reinterpret_cast<double2 *>(cell);
+    acc.x += (double)s;
+    acc.y += (double)q;
+    *reinterpret_cast<double2 *>(cell) = acc;
 }
 
 // ---- optional role profiling: cycles spent per wait / work category, summed over CTAs ------------------------

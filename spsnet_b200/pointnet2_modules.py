@@ -11,8 +11,12 @@ Two execution paths per module:
     scales, and GEMM kernels whose A-loader does the grouping and whose epilogue does BN(folded)+ReLU
     [+max-pool]; the (B,3+C,npoint,nsample) grouped tensor and the conv/BN/ReLU intermediates of the
     reference are never materialised in the reference's form;
-  * training / autograd: the reference's op-by-op composition (grouping -> torch Conv/BN/ReLU -> pool) on
-    top of the same CUDA ops, so gradients and batch-statistics BN behave exactly like the reference.
+  * training (`self.training`): the grouped shared MLPs run on the same fused kernel with BATCH-statistics BatchNorm
+    (train_fused.py: one statistics pass per layer + one pooled pass; running statistics updated like torch does;
+    SyncBatchNorm = one small all-reduce per layer); the backward recomputes the reference composition from the saved
+    inputs.  Conv1d stacks (aggregation / confidence / vote) stay on torch modules in training.
+  * autograd in eval mode, or anything the fused kernels do not cover (avg-pool, GroupAll, SPSK_TRAIN_FUSED=0): the
+    reference's op-by-op composition (grouping -> torch Conv/BN/ReLU -> pool) on top of the same CUDA ops.
 """
 from __future__ import annotations
 
@@ -24,6 +28,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import pointnet2_utils as pu
+from . import train_fused
 
 __all__ = [
     "PointnetSAModuleMSG", "PointnetSAModuleMSG_WithSampling", "Vote_layer", "PointnetSAModule",
@@ -353,6 +358,11 @@ class _PointnetSAModuleBase(nn.Module):
         if _fused_ok(self, xyz, features, new_xyz) and self._fusable_groupers() and len(self.mlps) > 0 \
                 and all(len(m) > 0 for m in self.mlps):
             return self._msg_fused(xyz, new_xyz, features, want16)
+        if self.training and train_fused.enabled():
+            # training-mode BatchNorm on the fused kernel: L statistics passes + one pooled pass (train_fused.py)
+            out = train_fused.msg_train(self, xyz, new_xyz, features)
+            if out is not None:
+                return out, None
         return self._msg_composed(xyz, new_xyz, features), None
 
     def _pw_layers(self, name: str, seq: nn.Sequential, split: bool):

@@ -484,6 +484,34 @@ def _canonical_tile(block: torch.Tensor) -> torch.Tensor:
     return block.reshape(rows // 8, 8, kw // 8, 8).permute(0, 2, 1, 3).contiguous().reshape(-1)
 
 
+def _pack_chunks(Wt: torch.Tensor, ncols: int) -> torch.Tensor:
+    """All cout chunks of one width at once: Wt (nchunk*ncols, vk) fp16 -> the chunks' tiles, chunk-major then k, every tile
+    `ncols x kw` (kw = 64, the last one vk % 64) in the canonical layout of `_canonical_tile`.  Two strided copies per call instead
+    of one per tile: training re-packs the weights every step."""
+    nch, vk = Wt.shape[0] // ncols, Wt.shape[1]
+    nfk = vk // 64
+    kr = vk - nfk * 64
+    parts = []
+    if nfk:
+        parts.append(Wt[:, :nfk * 64].reshape(nch, ncols // 8, 8, nfk, 8, 8).permute(0, 3, 1, 4, 2, 5).reshape(nch, -1))
+    if kr:
+        parts.append(Wt[:, nfk * 64:].reshape(nch, ncols // 8, 8, 1, kr // 8, 8).permute(0, 3, 1, 4, 2, 5).reshape(nch, -1))
+    return (parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)).reshape(-1)
+
+
+def _pack_layer(Wv: torch.Tensor) -> list:
+    """Wv (vk, cp) fp16 -> flat tiles of (<= 128 couts) x (<= 64 k), cout-chunk major then k (include/spsk.h: wtiles)."""
+    Wt = Wv.t()
+    cp = Wt.shape[0]
+    nfc = cp // 128
+    out = []
+    if nfc:
+        out.append(_pack_chunks(Wt[:nfc * 128], 128))
+    if cp - nfc * 128:
+        out.append(_pack_chunks(Wt[nfc * 128:], cp - nfc * 128))
+    return out
+
+
 class MmaChain:
     """A folded Conv/BN/ReLU chain packed for spsk_sa_mma_forward (layout: include/spsk.h).
 
@@ -546,11 +574,7 @@ class MmaChain:
                             kw = min(64, vk - k0_)
                             tiles.append(_canonical_tile(Wv[k0_:k0_ + kw, r0:r0 + cw // 2].t()))
             else:
-                for c0 in range(0, cp, 128):
-                    ncols = min(128, cp - c0)
-                    for k0_ in range(0, vk, 64):
-                        kw = min(64, vk - k0_)
-                        tiles.append(_canonical_tile(Wv[k0_:k0_ + kw, c0:c0 + ncols].t()))
+                tiles += _pack_layer(Wv)
             bv = torch.zeros(cp, dtype=torch.float32, device=dev)
             bv[:cout] = bias
             biases.append(bv)
@@ -615,8 +639,18 @@ def make_twin(features: torch.Tensor, cpad8: int) -> torch.Tensor:
     return twin
 
 
+def sa_mma_stats_parts(idx: torch.Tensor, n: int, chain: MmaChain) -> int:
+    """Partial-sum slices a batch-statistics pass of `chain` over these centres writes (include/spsk.h)."""
+    B, M, ns = idx.shape
+    d = chain._desc()
+    d.b, d.n, d.m, d.nsample = B, n, M, ns
+    v = C.c_int(0)
+    check(lib.spsk_sa_mma_stats_parts(C.byref(d), C.byref(v)), "sa_mma_stats_parts")
+    return int(v.value)
+
+
 def sa_mma_forward(*, xyz, new_xyz, idx, chain: MmaChain, twin=None, features=None, out_pooled=None, co_off=0,
-                   out16=None, co16=0, n16=None, o16lo=0):
+                   out16=None, co16=0, n16=None, o16lo=0, stats=None):
     """One fused MSG scale (include/spsk.h: spsk_sa_mma_forward).  `twin` (B, N, ld) fp16 in plain mode, `features`
     (B, C, N) fp32 in split mode; results go to out_pooled[:, co_off:co_off+cout, :] (fp32, (B, C_total, M)) and/or
     out16[:, co16:co16+n16] (fp16, (B*M, ld16)); with o16lo > 0 the fp16 residuals go to out16[:, o16lo+co16 : ...]."""
@@ -638,8 +672,15 @@ def sa_mma_forward(*, xyz, new_xyz, idx, chain: MmaChain, twin=None, features=No
         d.out16, d.ld16, d.co16 = out16.data_ptr(), out16.shape[-1], co16
         d.n16 = chain.cout_last if n16 is None else n16
         d.o16lo = int(o16lo)
+    if stats is not None:
+        # batch-statistics pass (training-mode BN): stats (parts, cpad_last, 2) float64, zeroed by the caller; nothing else is written
+        if stats.dtype != torch.float64 or not stats.is_contiguous() or stats.dim() != 3 or stats.shape[1] != chain.cpad[-1] or stats.shape[2] != 2:
+            raise RuntimeError("sa_mma_forward: stats must be a contiguous (parts, cpad_last, 2) float64 tensor")
+        d.stats, d.stats_parts = stats.data_ptr(), stats.shape[0]
     with torch.cuda.device(idx.device):
         check(lib.spsk_sa_mma_forward(C.byref(d), _stream()), "sa_mma_forward")
+    if stats is not None:
+        return stats
     return out_pooled if out_pooled is not None else out16
 
 

@@ -1,0 +1,260 @@
+"""Training-mode forward of the grouped shared MLP on the fused tensor-core kernel: Conv2d(1x1) -> BatchNorm2d with BATCH
+statistics -> ReLU, repeated, -> max-pool over the neighbours (reference pointnet2_modules.py:203-211 built, :429-445 run,
+with the module in `train()`; SyncBatchNorm after `tools/train.py:122-123`), SURVEY.md section 8(f) rank 4.
+
+The reference materialises the grouped tensor (B, C, npoint, nsample) and every Conv / BN / ReLU result and lets cuDNN reduce
+the batch statistics.  Here nothing of that size exists in the forward:
+
+  pass l = 0 .. L-1   `spsk_sa_mma_forward` in its statistics mode on the chain truncated after conv l -- layers < l carry the
+                      batch statistics already found (folded into W and bias exactly like running statistics are at inference),
+                      conv l runs raw -- and the epilogue of conv l reduces sum z and sum z^2 per channel over all
+                      B*npoint*nsample rows (per-thread cells, fp64 across tiles, no atomics: reproducible).  A (2, C) fp64 sum
+                      over the per-CTA slices [+ ONE all-reduce of 2C+1 doubles per layer for SyncBatchNorm] gives mean and biased
+                      variance; the running statistics get the reference's momentum update (unbiased variance).
+  pass L              the inference kernel with all L layers folded on the batch statistics -> pooled features.
+
+L + 1 launches that recompute the (cheap, on-chip) chain instead of L round trips of the (B, C, npoint, nsample) tensors through
+HBM.  The backward recomputes the reference composition from the saved inputs (xyz, new_xyz, features, idx -- a few MB) with
+torch autograd, so gradients are those of the fp32 reference function, BatchNorm's dependence on the batch statistics included;
+the activations (hundreds of MB per layer at KITTI sizes) are never kept between forward and backward.  Hand-written backward
+GEMMs are the step after this one.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import pointnet2_utils as pu
+
+_BN_TYPES = (nn.BatchNorm2d, nn.SyncBatchNorm)
+
+
+def enabled() -> bool:
+    """SPSK_TRAIN_FUSED=0 keeps `module.train()` on the reference's op-by-op composition."""
+    return os.environ.get("SPSK_TRAIN_FUSED", "1") != "0"
+
+
+# ---------------------------------------------------------------------------------------------------
+# pure-torch pieces (run on CPU too: tests/test_train_fused_cpu.py)
+# ---------------------------------------------------------------------------------------------------
+
+def split_layers(seq: nn.Sequential) -> Optional[List[Tuple[nn.Conv2d, nn.Module]]]:
+    """[(conv, bn), ...] when `seq` is (Conv2d 1x1 without bias, BatchNorm2d | SyncBatchNorm (affine, in training mode), ReLU)
+    repeated -- the only form the reference builds with bn=True (pointnet2_modules.py:204-211) -- else None."""
+    mods = list(seq)
+    if not mods or len(mods) % 3:
+        return None
+    out = []
+    for i in range(0, len(mods), 3):
+        conv, bn, act = mods[i:i + 3]
+        if not isinstance(conv, nn.Conv2d) or conv.kernel_size != (1, 1) or conv.bias is not None or conv.groups != 1:
+            return None
+        if not isinstance(bn, _BN_TYPES) or not bn.affine or not bn.training:
+            return None
+        if not isinstance(act, nn.ReLU):
+            return None
+        out.append((conv, bn))
+    return out
+
+
+def sync_group(bn: nn.Module):
+    """The process group a SyncBatchNorm layer reduces over, or None when the statistics stay local (plain BatchNorm2d, no
+    initialised process group, or a world of one)."""
+    if not isinstance(bn, nn.SyncBatchNorm):
+        return None
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return None
+    group = bn.process_group if bn.process_group is not None else dist.group.WORLD
+    return group if dist.get_world_size(group) > 1 else None
+
+
+def bn_moments(sums: torch.Tensor, count: int, group=None) -> Tuple[torch.Tensor, torch.Tensor, float]:
+    """(C, 2) fp64 [sum z, sum z^2] over `count` local rows -> (mean, biased variance, total count), fp64; with `group` the three
+    quantities are summed over the ranks first: ONE all-reduce of 2C + 1 doubles (what SyncBatchNorm's all_gather of
+    (mean, invstd, count) amounts to, torch/nn/modules/_functions.py)."""
+    c = sums.shape[0]
+    if group is not None:
+        import torch.distributed as dist
+
+        buf = torch.cat([sums.reshape(-1), sums.new_tensor([float(count)])])
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        sums, total = buf[:2 * c].reshape(c, 2), float(buf[-1].item())
+    else:
+        total = float(count)
+    mean = sums[:, 0] / total
+    var = (sums[:, 1] / total - mean * mean).clamp_min_(0.0)
+    return mean, var, total
+
+
+def bn_fold(weight: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, mean: torch.Tensor, var: torch.Tensor, eps: float):
+    """conv (cout, cin) + BN on (mean, var) -> (wt (cin, cout), bias (cout)) fp32 with y = x @ wt + bias; folded in fp64."""
+    g = gamma.double() * torch.rsqrt(var.double() + eps)
+    wt = (weight.double() * g[:, None]).t().contiguous().float()
+    bias = (beta.double() - mean.double() * g).float()
+    return wt, bias
+
+
+def bn_update_running(bn: nn.Module, mean: torch.Tensor, var: torch.Tensor, total: float) -> None:
+    """The reference's running-statistics update (torch _BatchNorm.forward + batch_norm kernels): exponential average with
+    `momentum` (cumulative average when it is None), unbiased variance."""
+    if not bn.track_running_stats or bn.running_mean is None:
+        return
+    bn.num_batches_tracked.add_(1)
+    mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked.item())
+    unbiased = var * (total / max(total - 1.0, 1.0))
+    bn.running_mean.mul_(1.0 - mom).add_(mean.to(bn.running_mean.dtype), alpha=mom)
+    bn.running_var.mul_(1.0 - mom).add_(unbiased.to(bn.running_var.dtype), alpha=mom)
+
+
+def _bn_train(z: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, group):
+    """Batch-statistics BN as a differentiable torch expression (no running-statistics side effect).  Local: F.batch_norm.
+    Synchronised: two differentiable all-reduces (sum -> mean, centred sum of squares -> variance)."""
+    if group is None:
+        return F.batch_norm(z, None, None, gamma, beta, True, 0.0, eps)
+    import torch.distributed.nn.functional as dfn
+
+    c = z.shape[1]
+    dims = (0, 2, 3)
+    first = dfn.all_reduce(torch.cat([z.sum(dims), z.new_tensor([z.numel() / c])]), group=group)
+    total = first[-1]
+    mean = (first[:c] / total).view(1, c, 1, 1)
+    zc = z - mean
+    var = (dfn.all_reduce((zc * zc).sum(dims), group=group) / total).view(1, c, 1, 1)
+    return zc * (gamma.view(1, c, 1, 1) * torch.rsqrt(var + eps)) + beta.view(1, c, 1, 1)
+
+
+def mlp_recompute(grouped: torch.Tensor, params: Sequence[torch.Tensor], eps: Sequence[float], groups: Sequence) -> torch.Tensor:
+    """The reference composition on a grouped tensor (B, C, npoint, nsample): [conv1x1 -> BN(batch stats) -> ReLU] x L -> max
+    over nsample, as a torch graph (reference pointnet2_modules.py:431-436)."""
+    x = grouped
+    for l in range(len(params) // 3):
+        w, gamma, beta = params[3 * l:3 * l + 3]
+        x = F.conv2d(x, w)
+        x = F.relu(_bn_train(x, gamma, beta, eps[l], groups[l]))
+    return F.max_pool2d(x, kernel_size=[1, x.size(3)]).squeeze(-1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the fused forward
+# ---------------------------------------------------------------------------------------------------
+
+def _probe_ok(layers, c_feat: int, use_xyz: bool) -> Tuple[bool, bool]:
+    """(every truncated chain and the full chain fit the kernel, split arithmetic of the full chain)."""
+    chain = [(conv.weight.detach().reshape(conv.out_channels, conv.in_channels).float().t().contiguous(),
+              torch.zeros(conv.out_channels, device=conv.weight.device), True) for conv, _ in layers]
+    full = pu.MmaChain(chain, c_feat, use_xyz, pair=False)
+    if not full.ok:
+        return False, False
+    for l in range(1, len(chain)):
+        if not pu.MmaChain(chain[:l], c_feat, use_xyz, split=full.split, pair=False).ok:
+            return False, False
+    return True, full.split
+
+
+class FusedTrainMLP(torch.autograd.Function):
+    """One MSG scale.  apply(meta, xyz, new_xyz, features | None, idx, W0, gamma0, beta0, W1, ...) -> (B, C_last, npoint).
+    `meta`: dict(use_xyz, split, bns=[BatchNorm modules], eps=[...], groups=[process group | None, ...])."""
+
+    @staticmethod
+    def forward(ctx, meta, xyz, new_xyz, features, idx, *params):
+        use_xyz, split = meta["use_xyz"], meta["split"]
+        bns, eps, groups = meta["bns"], meta["eps"], meta["groups"]
+        B, M, ns = idx.shape
+        N = xyz.shape[1]
+        count = B * M * ns
+        c_feat = features.shape[1] if features is not None else 0
+        with torch.no_grad():
+            twin = None
+            if c_feat and not split:
+                twin = pu.make_twin(features.contiguous(), (c_feat + 7) // 8 * 8)
+            common = dict(xyz=xyz, new_xyz=new_xyz, idx=idx, twin=twin, features=features if split else None)
+            folded = []
+            for l, bn in enumerate(bns):
+                w = params[3 * l].detach().reshape(params[3 * l].shape[0], -1).float()
+                gamma, beta = params[3 * l + 1].detach().float(), params[3 * l + 2].detach().float()
+                raw = (w.t().contiguous(), torch.zeros(w.shape[0], dtype=torch.float32, device=w.device), True)
+                pk = pu.MmaChain(folded + [raw], c_feat, use_xyz, split=split, pair=False)
+                if not pk.ok:
+                    raise RuntimeError("train_fused: chain does not fit the fused kernel (probe and launch disagree)")
+                parts = torch.zeros((pu.sa_mma_stats_parts(idx, N, pk), pk.cpad[-1], 2), dtype=torch.float64, device=idx.device)
+                pu.sa_mma_forward(chain=pk, stats=parts, **common)
+                mean, var, total = bn_moments(parts.sum(dim=0)[:w.shape[0]], count, groups[l])
+                bn_update_running(bn, mean, var, total)
+                wt, bias = bn_fold(w, gamma, beta, mean, var, eps[l])
+                folded.append((wt, bias, True))
+            pk = pu.MmaChain(folded, c_feat, use_xyz, split=split, pair=False)
+            out = torch.empty((B, pk.cout_last, M), dtype=torch.float32, device=idx.device)
+            pu.sa_mma_forward(chain=pk, out_pooled=out, co_off=0, **common)
+        ctx.meta = meta
+        ctx.has_feat = features is not None
+        ctx.save_for_backward(xyz, new_xyz, features if features is not None else xyz.new_empty(0), idx, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        meta = ctx.meta
+        xyz, new_xyz, features, idx, *params = ctx.saved_tensors
+        need = ctx.needs_input_grad   # (meta, xyz, new_xyz, features, idx, *params)
+        with torch.enable_grad():
+            xyz_ = xyz.detach().requires_grad_(need[1])
+            new_xyz_ = new_xyz.detach().requires_grad_(need[2])
+            feat_ = features.detach().requires_grad_(need[3]) if ctx.has_feat else None
+            params_ = [p.detach().requires_grad_(need[5 + i]) for i, p in enumerate(params)]
+            grouped = pu._group(xyz_, new_xyz_, feat_, idx, meta["use_xyz"])
+            out = mlp_recompute(grouped, params_, meta["eps"], meta["groups"])
+            cand = [xyz_, new_xyz_, feat_] + params_
+            wanted = [t for t in cand if t is not None and t.requires_grad]
+            grads = iter(torch.autograd.grad(out, wanted, grad_out.contiguous(), allow_unused=True)) if wanted else iter(())
+        res = [next(grads) if (t is not None and t.requires_grad) else None for t in cand]
+        return (None, res[0], res[1], res[2], None, *res[3:])
+
+
+def msg_train(module, xyz: torch.Tensor, new_xyz: torch.Tensor, features: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """All MSG scales of a set-abstraction module in training mode on the fused path; None when some scale is outside what the
+    kernel covers (the caller then runs the reference composition)."""
+    if not xyz.is_cuda or module.pool_method != "max_pool" or len(module.mlps) == 0:
+        return None
+    if not all(isinstance(g, (pu.QueryAndGroup, pu.QueryDilatedAndGroup)) for g in module.groupers):
+        return None
+    c_feat = features.shape[1] if features is not None else 0
+    scales = []
+    cache = module.__dict__.setdefault("_train_probe", {})
+    for si, (g, mlp) in enumerate(zip(module.groupers, module.mlps)):
+        ns = g.nsample
+        if ns > 128 or (ns & (ns - 1)):
+            return None
+        layers = split_layers(mlp)
+        if layers is None or len(layers) > 4 or (features is None and not g.use_xyz):
+            return None
+        key = (si, c_feat, g.use_xyz, tuple(conv.weight.shape for conv, _ in layers), layers[0][0].weight.device)
+        if cache.get(si, (None,))[0] != key:
+            cache[si] = (key,) + _probe_ok(layers, c_feat, g.use_xyz)
+        _, ok, split = cache[si]
+        if not ok:
+            return None
+        scales.append((g, layers, split))
+    xyz = xyz.contiguous()
+    new_xyz = new_xyz.contiguous()
+    if features is not None:
+        features = features.contiguous()
+    with torch.no_grad():
+        if all(isinstance(g, pu.QueryAndGroup) for g in module.groupers):
+            idxs = pu.ball_query_msg([g.radius for g in module.groupers], [g.nsample for g in module.groupers], xyz, new_xyz)
+        else:
+            idxs = [pu.ball_query_dilated(g.radius_in, g.radius_out, g.nsample, xyz, new_xyz) if isinstance(g, pu.QueryDilatedAndGroup)
+                    else pu.ball_query(g.radius, g.nsample, xyz, new_xyz) for g in module.groupers]
+    outs = []
+    for (g, layers, split), idx in zip(scales, idxs):
+        meta = dict(use_xyz=g.use_xyz, split=split, bns=[bn for _, bn in layers], eps=[float(bn.eps) for _, bn in layers],
+                    groups=[sync_group(bn) for _, bn in layers])
+        params = []
+        for conv, bn in layers:
+            params += [conv.weight, bn.weight, bn.bias]
+        outs.append(FusedTrainMLP.apply(meta, xyz, new_xyz, features, idx, *params))
+    return outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)

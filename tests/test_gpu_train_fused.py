@@ -1,0 +1,266 @@
+"""-m gpu: training-mode BatchNorm on the fused kernel (spsnet_b200/train_fused.py).
+
+  * the statistics pass of spsk_sa_mma_forward against a float64 evaluation of the same chain (every launch shape: resident
+    narrow / split, ring, two epilogue groups, many tiles per CTA, ragged last tile), bit-reproducible;
+  * a set-abstraction module in train(): fused vs the reference composition of the same module (SPSK_TRAIN_FUSED=0) -- pooled
+    features within 1e-3, running statistics, and -- with the same upstream gradient -- every gradient;
+  * the drop-in module in train() against the UNMODIFIED reference module + its CUDA ops (oracle/_ref) in train():
+    forward, running statistics of every BatchNorm layer, parameter gradients
+    (reference pointnet2_modules.py:203-211, 429-445; pointnet2_utils.py:184-222 for the grouping backward)."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+
+from helpers import assert_close, rel_err  # noqa: E402
+from spsnet_b200 import scenes  # noqa: E402
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(autouse=True)
+def _fp32_truth():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+# (name, c_feat, widths, nsample, B, N, M)
+STAT_CASES = [
+    ("narrow_split", 1, [16, 16, 32], 16, 2, 2048, 512),         # resident, split arithmetic, 4 CTAs per SM
+    ("narrow_ragged", 1, [32, 32, 64], 16, 1, 1000, 100),        # 1600 rows: 12 full tiles + half a tile
+    ("plain_mid", 64, [64, 64, 128], 32, 2, 1024, 256),          # plain fp16 operands, resident
+    ("plain_1layer", 64, [96], 16, 2, 1024, 256),                # statistics of the FIRST conv (a one-layer chain)
+    ("ring_two_groups", 256, [256, 512, 1024], 32, 4, 2048, 1024),   # streaming ring, G = 2, 8 cout chunks, ~7 tiles per CTA
+    ("xyz_only", 0, [16, 32], 8, 2, 512, 128),
+]
+
+
+@pytest.mark.parametrize("name,c_feat,widths,ns,B,N,M", STAT_CASES, ids=[c[0] for c in STAT_CASES])
+def test_statistics_pass_vs_float64(name, c_feat, widths, ns, B, N, M):
+    from spsnet_b200 import pointnet2_utils as pu
+
+    torch.manual_seed(3)
+    xyz = dev(scenes.make_batch(21, B, N)[:, :, :3])
+    sel = pu.furthest_point_sample(xyz, M)
+    new_xyz = pu.gather_rows(xyz, sel)
+    feats = (torch.randn(B, c_feat, N, device="cuda") * 0.7 + 0.2) if c_feat else None
+    idx = pu.ball_query(1.2, ns, xyz, new_xyz)
+    cin = c_feat + 3
+    chain = []
+    for l, cout in enumerate(widths):
+        wt = torch.randn(cin, cout, device="cuda") / cin ** 0.5
+        last = l == len(widths) - 1
+        bias = torch.zeros(cout, device="cuda") if last else torch.randn(cout, device="cuda") * 0.2
+        chain.append((wt, bias, True))
+        cin = cout
+    pk = pu.MmaChain(chain, c_feat, True, pair=False)
+    assert pk.ok
+    nparts = pu.sa_mma_stats_parts(idx, N, pk)
+    twin = pu.make_twin(feats, (c_feat + 7) // 8 * 8) if (c_feat and not pk.split) else None
+
+    def run():
+        parts = torch.zeros((nparts, pk.cpad[-1], 2), dtype=torch.float64, device="cuda")
+        pu.sa_mma_forward(xyz=xyz, new_xyz=new_xyz, idx=idx, chain=pk, twin=twin, features=feats if pk.split else None, stats=parts)
+        return parts
+
+    parts = run()
+    assert torch.equal(parts, run())                                   # per-thread cells, no atomics: reproducible bit for bit
+    sums = parts.sum(0)
+    assert float(sums[widths[-1]:].abs().max() if pk.cpad[-1] > widths[-1] else 0.0) == 0.0   # padded couts: exactly zero
+    # float64 truth from the reference composition of the grouped tensor
+    g = pu._group(xyz, new_xyz, feats, idx, True).double()            # (B, 3 + C, M, ns)
+    rows = g.permute(0, 2, 3, 1).reshape(-1, g.shape[1])
+    for l, (wt, bias, _) in enumerate(chain):
+        z = rows @ wt.double()
+        rows = torch.relu(z + bias.double())
+    count = B * M * ns
+    mean_w, var_w = z.mean(0), z.var(0, unbiased=False)
+    mean = sums[:widths[-1], 0] / count
+    var = sums[:widths[-1], 1] / count - mean * mean
+    std = var_w.sqrt()
+    e_mean = float(((mean - mean_w).abs() / (std + mean_w.abs() + 1e-12)).max())
+    e_var = float(((var - var_w).abs() / (var_w + 1e-12)).max())
+    print(f"[stats] {name}: parts={nparts} split={pk.split} ctas/SM={pk.ctas_per_sm} resident={pk.resident} mean err {e_mean:.2e} var err {e_var:.2e}")
+    assert e_mean <= 1e-3 and e_var <= 2e-3
+
+
+MSG_CASES = {
+    # KITTI layer 0 (split chains), layer 1 (plain, resident), layer 2 scale 2 widths (ring) -- small point counts
+    "l0": dict(cin=1, radii=[0.2, 0.8], nsamples=[16, 32], mlps=[[1, 16, 16, 32], [1, 32, 32, 64]], n=2048, m=512),
+    "l1": dict(cin=64, radii=[0.8, 1.6], nsamples=[16, 32], mlps=[[64, 64, 64, 128], [64, 64, 96, 128]], n=1024, m=256),
+    "l2": dict(cin=128, radii=[1.6, 4.8], nsamples=[16, 32], mlps=[[128, 128, 128, 256], [128, 128, 256, 256]], n=512, m=128),
+    "dil": dict(cin=5, radii=[0.8, 1.6], nsamples=[16, 32], mlps=[[5, 17, 33], [5, 24, 40]], n=700, m=100, dilated=True),
+}
+
+
+def _msg_module(kind, seed=0):
+    from spsnet_b200 import pointnet2_modules as pm
+
+    c = MSG_CASES[kind]
+    torch.manual_seed(seed)
+    if c.get("dilated"):
+        m = pm.PointnetSAModuleMSG_WithSampling(npoint_list=[c["m"]], sample_range_list=[-1], sample_type_list=["D-FPS"], radii=c["radii"],
+                                                nsamples=c["nsamples"], mlps=copy.deepcopy(c["mlps"]), dilated_group=True,
+                                                aggregation_mlp=None, confidence_mlp=None, num_class=3)
+    else:
+        m = pm.PointnetSAModuleMSG(npoint=c["m"], radii=c["radii"], nsamples=c["nsamples"], mlps=copy.deepcopy(c["mlps"]), use_xyz=True)
+    for mod in m.modules():
+        if isinstance(mod, nn.BatchNorm2d):
+            mod.weight.data.uniform_(0.5, 1.5)
+            mod.bias.data.uniform_(-0.2, 0.2)
+    return m.cuda().train()
+
+
+@pytest.mark.parametrize("kind", list(MSG_CASES))
+def test_msg_train_fused_vs_composition(kind, monkeypatch):
+    """Same module, same inputs, same upstream gradient: fused statistics + pooled pass + recompute backward against the
+    reference composition with torch BatchNorm2d in train()."""
+    from spsnet_b200 import pointnet2_utils as pu
+
+    c = MSG_CASES[kind]
+    B = 2
+    fused = _msg_module(kind, seed=4)
+    comp = copy.deepcopy(fused)
+    xyz = dev(scenes.make_batch(33, B, c["n"])[:, :, :3])
+    new_xyz0 = pu.gather_rows(xyz, pu.furthest_point_sample(xyz, c["m"]))
+    feats0 = torch.randn(B, c["cin"], c["n"], device="cuda")
+    outs, grads, stats = [], [], []
+    for mod, flag in ((fused, "1"), (comp, "0")):
+        monkeypatch.setenv("SPSK_TRAIN_FUSED", flag)
+        feats = feats0.clone().requires_grad_(True)
+        new_xyz = new_xyz0.clone().requires_grad_(True)
+        for step in range(2):                                      # two steps: running statistics chain through the momentum update
+            out, _ = mod._msg(xyz, new_xyz, feats)
+        torch.manual_seed(9)
+        gout = torch.randn_like(out)
+        params = [p for p in mod.parameters()]
+        g = torch.autograd.grad(out, [feats, new_xyz] + params, gout)
+        outs.append(out.detach())
+        grads.append(g)
+        stats.append([(b.running_mean.clone(), b.running_var.clone(), int(b.num_batches_tracked)) for b in mod.modules() if isinstance(b, nn.BatchNorm2d)])
+    assert outs[0].shape == outs[1].shape
+    assert_close(outs[0].cpu().numpy(), outs[1].cpu().numpy(), what=f"{kind} pooled features, train()")
+    for (m0, v0, n0), (m1, v1, n1) in zip(*stats):
+        assert n0 == n1 == 2
+        assert rel_err(m0.cpu().numpy(), m1.cpu().numpy()) <= 1e-3
+        assert rel_err(v0.cpu().numpy(), v1.cpu().numpy()) <= 2e-3
+    names = ["features", "new_xyz"] + [n for n, _ in fused.named_parameters()]
+    for n, a, b in zip(names, *grads):
+        e = rel_err(a.cpu().numpy(), b.cpu().numpy())
+        assert e <= 2e-4, f"{kind}: grad {n} relative error {e:.2e}"
+
+
+def test_fused_training_is_the_path_taken(monkeypatch):
+    """train() really runs the statistics kernel (and the composition is used when it is switched off)."""
+    from spsnet_b200 import pointnet2_utils as pu
+    from spsnet_b200._lib import lib
+
+    m = _msg_module("l1", seed=1)
+    xyz = dev(scenes.make_batch(34, 2, 1024)[:, :, :3])
+    new_xyz = pu.gather_rows(xyz, pu.furthest_point_sample(xyz, 256))
+    feats = torch.randn(2, 64, 1024, device="cuda", requires_grad=True)
+    calls = []
+    real = pu.sa_mma_forward
+    monkeypatch.setattr(pu, "sa_mma_forward", lambda **kw: (calls.append("stats" if kw.get("stats") is not None else "pool"), real(**kw))[1])
+    out, _ = m._msg(xyz, new_xyz, feats)
+    assert calls == ["stats", "stats", "stats", "pool"] * 2 and out.requires_grad
+    calls.clear()
+    monkeypatch.setenv("SPSK_TRAIN_FUSED", "0")
+    m._msg(xyz, new_xyz, feats)
+    assert calls == []
+    assert lib.spsk_abi_version() >= 4
+
+
+REF_KINDS = {
+    "l0": dict(npoint_list=[512], sample_type_list=["D-FPS"], radii=[0.2, 0.8], nsamples=[16, 32],
+               mlps=[[1, 16, 16, 32], [1, 32, 32, 64]], aggregation_mlp=[64], confidence_mlp=None, cin=1, n=2048),
+    "l1": dict(npoint_list=[256], sample_type_list=["D-FPS"], radii=[0.8, 1.6], nsamples=[16, 32],
+               mlps=[[64, 64, 64, 128], [64, 64, 96, 128]], aggregation_mlp=[128], confidence_mlp=[128], cin=64, n=1024),
+}
+
+
+@pytest.mark.parametrize("kind", list(REF_KINDS))
+def test_sa_module_train_vs_reference_module_train(ref_ops, kind):
+    """The drop-in module in train() against the unmodified reference module + CUDA ops in train(): same state_dict, same
+    batch -- sampled indices bit-exact, features / logits within 1e-3, every BatchNorm's running statistics, and the
+    parameter gradients of a fixed linear loss."""
+    if ref_ops is None:
+        pytest.skip("oracle/_ref (rebuilt reference) not present")
+    from spsnet_b200 import pointnet2_modules as pm
+
+    kw = copy.deepcopy(REF_KINDS[kind])
+    cin, n = kw.pop("cin"), kw.pop("n")
+    torch.manual_seed(2)
+    ours = pm.PointnetSAModuleMSG_WithSampling(sample_range_list=[-1], num_class=3, **copy.deepcopy(kw)).cuda().train()
+    for mod in ours.modules():
+        if isinstance(mod, (nn.BatchNorm1d, nn.BatchNorm2d)):
+            mod.weight.data.uniform_(0.5, 1.5)
+            mod.bias.data.uniform_(-0.2, 0.2)
+    ref = ref_ops.modules.PointnetSAModuleMSG_WithSampling(sample_range_list=[-1], num_class=3, **copy.deepcopy(kw)).cuda().train()
+    ref.load_state_dict(ours.state_dict())
+    B = 2
+    xyz = dev(scenes.make_batch(61, B, n)[:, :, :3])
+    feats = torch.randn(B, cin, n, device="cuda")
+    res = []
+    for mod in (ours, ref):
+        out = mod(xyz, feats.clone(), None)
+        torch.manual_seed(13)
+        loss = (out[1] * torch.randn_like(out[1])).sum()
+        if out[2] is not None:
+            loss = loss + (out[2] * torch.randn_like(out[2])).sum()
+        mod.zero_grad()
+        loss.backward()
+        res.append(out)
+    np.testing.assert_array_equal(res[0][3].cpu().numpy(), res[1][3].cpu().numpy())
+    np.testing.assert_array_equal(res[0][0].detach().cpu().numpy(), res[1][0].detach().cpu().numpy())
+    assert_close(res[0][1].detach().cpu().numpy(), res[1][1].detach().cpu().numpy(), what=f"{kind} new_features, train()")
+    if res[1][2] is not None:
+        assert_close(res[0][2].detach().cpu().numpy(), res[1][2].detach().cpu().numpy(), what=f"{kind} cls logits, train()")
+    sd_o, sd_r = ours.state_dict(), ref.state_dict()
+    for k in sd_o:
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            e = rel_err(sd_o[k].cpu().numpy(), sd_r[k].cpu().numpy())
+            assert e <= 2e-3, f"{kind}: {k} relative error {e:.2e}"
+        if k.endswith("num_batches_tracked"):
+            assert int(sd_o[k]) == int(sd_r[k]) == 1
+    worst = 0.0
+    for (name, p), (_, q) in zip(ours.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None and q.grad is not None, name
+        worst = max(worst, rel_err(p.grad.cpu().numpy(), q.grad.cpu().numpy()))
+    print(f"[train vs reference] {kind}: worst parameter-gradient relative error {worst:.2e}")
+    assert worst <= 1e-2
+
+
+def test_backbone_training_step_runs_on_the_fused_path(monkeypatch):
+    """A whole IA-SSD SA stack in train(): forward + backward + SGD step, finite, every grouped-MLP BatchNorm updated once."""
+    from helpers import small_sa_cfg
+    from spsnet_b200 import backbone as bb
+    from spsnet_b200 import pointnet2_utils as pu
+
+    torch.manual_seed(0)
+    net = bb.IASSD_Backbone(small_sa_cfg((512, 128, 64, 32)), num_class=3, input_channels=4).cuda().train()
+    calls = []
+    real = pu.sa_mma_forward
+    monkeypatch.setattr(pu, "sa_mma_forward", lambda **kw: (calls.append(kw.get("stats") is not None), real(**kw))[1])
+    B, N = 2, 2048
+    pts = dev(scenes.to_points(scenes.make_batch(81, B, N)))
+    opt = torch.optim.SGD(net.parameters(), lr=1e-3)
+    out = net({"batch_size": B, "points": pts})
+    loss = out["centers_features"].square().mean() + out["ctr_offsets"][:, 1:].square().mean()
+    loss.backward()
+    opt.step()
+    assert torch.isfinite(loss)
+    assert sum(calls) == 4 * 2 * 3 and len(calls) - sum(calls) == 4 * 2      # 4 MSG layers x 2 scales x (3 statistics passes + 1 pooled pass)
+    n2d = [m for m in net.modules() if isinstance(m, nn.BatchNorm2d)]
+    assert n2d and all(int(m.num_batches_tracked) == 1 for m in n2d)
+    grads = [p.grad for p in net.parameters() if p.grad is not None]
+    assert grads and all(torch.isfinite(g).all() for g in grads)
