@@ -284,6 +284,28 @@ SPSK_API int spsk_sa_mma_stats_parts(const spsk_sa_mma_desc *d, int *nparts);
 #define SPSK_SA_PROF_COUNTERS 14
 SPSK_API int spsk_sa_mma_set_profile(unsigned long long *counters);
 
+/* ---- training-mode BatchNorm around the statistics passes (spsk_sa_mma_desc.stats), reference pointnet2_modules.py:203-211 with
+ * the module in train().  One training forward of an L-layer chain is, per layer l:
+ *   spsk_sa_pack_layer(raw conv l as the LAST layer of the truncated chain) -> spsk_sa_mma_forward(stats) -> spsk_bn_stats_reduce
+ *   [-> all-reduce of the 2c+1 doubles across ranks: SyncBatchNorm] -> spsk_bn_stats_finalize -> spsk_sa_pack_layer(conv l x scale)
+ * and then one ordinary spsk_sa_mma_forward on the chain folded with the batch statistics. */
+
+/* Pack one layer's weights for spsk_sa_mma_forward: w (cout, cin) fp32 row-major, the layout of Conv2d(1x1).weight; `scale`
+ * (cout floats or NULL) multiplies row c (the BN fold); output = the layer's tiles of W'[wk, cpad] exactly as `wtiles` describes
+ * them above (wk = kpad, or 2*kpad = [Wh; Wl] with split), zero padded, written at `wtiles` (the caller adds the layer's offset
+ * wk * cpad * 2 bytes per preceding layer).  first != 0: layer 0, whose reference input order [x y z | features]
+ * (pointnet2_utils.py:315) is permuted to the kernel's [features | x y z | 0] order; cin must equal c_feat + 3*use_xyz. */
+SPSK_API int spsk_sa_pack_layer(const float *w, int cout, int cin, const float *scale, int first, int c_feat, int use_xyz, int kpad, int cpad,
+                                int split, void *wtiles, spsk_stream_t stream);
+/* parts (nparts, cpad, 2) fp64 of a statistics pass -> sums[2*ch + {0,1}] = {sum z, sum z*z} for ch < c, sums[2*c] = count
+ * (2c + 1 doubles; summed in a fixed order: reproducible). */
+SPSK_API int spsk_bn_stats_reduce(const double *parts, int nparts, int cpad, int c, double count, double *sums, spsk_stream_t stream);
+/* sums (2c + 1 doubles, see above) -> mean, biased variance -> scale[ch] = gamma / sqrt(var + eps), bias[ch] = beta - mean * scale
+ * (the BN fold for the following passes); running_mean / running_var (both or neither) get torch's update with `momentum`
+ * (unbiased variance) unless momentum < 0; `moments` (c, 2) fp64 receives (mean, var) when non-NULL. */
+SPSK_API int spsk_bn_stats_finalize(const double *sums, int c, const float *gamma, const float *beta, float eps, float momentum,
+                                    float *running_mean, float *running_var, float *scale, float *bias, double *moments, spsk_stream_t stream);
+
 /* Point-wise layer on the tensor cores:  y[row, c] = relu?( bias[c] + sum_k x[row, k] * W[c, k] )  over point-major
  * fp16 rows (replaces the aggregation / confidence / vote Conv1d + BN + ReLU stacks, pointnet2_modules.py:216-243,
  * 447-458, 485-500).
