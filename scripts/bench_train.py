@@ -103,6 +103,38 @@ def main():
             row[arm] = {"fwd_ms": round(t_f, 3), "fwd_bwd_ms": round(t_fb, 3), "peak_mb": round((torch.cuda.max_memory_allocated() - base_mem) / 2 ** 20, 1)}
         rows.append(row)
         print(json.dumps(row), flush=True)
+    # the whole IA-SSD SA stack in train(): one forward + backward per step, peak memory of a step
+    from spsnet_b200 import backbone as bb
+    from spsnet_b200.configs import kitti_iassd_cfg
+
+    torch.manual_seed(0)
+    net = bb.IASSD_Backbone(kitti_iassd_cfg(), num_class=3, input_channels=4).cuda().train()
+    pts = torch.from_numpy(np.ascontiguousarray(scenes.to_points(scenes.make_batch(7, B, 16384)))).cuda()
+    row = {"layer": "backbone (KITTI IA-SSD SA stack)", "batch": B, "n": 16384}
+    for arm, flag in (("fused", "1"), ("composed", "0")):
+        os.environ["SPSK_TRAIN_FUSED"] = flag
+        mod = copy.deepcopy(net)
+
+        def step(mod=mod):
+            out = mod({"batch_size": B, "points": pts})
+            loss = out["centers_features"].square().mean() + out["ctr_offsets"][:, 1:].square().mean()
+            mod.zero_grad(set_to_none=True)
+            loss.backward()
+
+        def fwd_only(mod=mod):
+            return mod({"batch_size": B, "points": pts})["centers_features"]
+
+        t_f = timed(fwd_only, reps=5)
+        t_fb = timed(step, reps=5)
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        base_mem = torch.cuda.memory_allocated()
+        step()
+        torch.cuda.synchronize()
+        row[arm] = {"fwd_ms": round(t_f, 3), "fwd_bwd_ms": round(t_fb, 3), "peak_mb": round((torch.cuda.max_memory_allocated() - base_mem) / 2 ** 20, 1)}
+        del mod
+    rows.append(row)
+    print(json.dumps(row), flush=True)
     if a.out:
         Path(a.out).write_text(json.dumps({"device": torch.cuda.get_device_name(0), "rows": rows}, indent=1))
 

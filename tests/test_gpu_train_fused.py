@@ -330,12 +330,51 @@ def test_sa_module_train_vs_reference_module_train(ref_ops, kind):
             assert e <= 2e-3, f"{kind}: {k} relative error {e:.2e}"
         if k.endswith("num_batches_tracked"):
             assert int(sd_o[k]) == int(sd_r[k]) == 1
-    worst = 0.0
-    for (name, p), (_, q) in zip(ours.named_parameters(), ref.named_parameters()):
+    # Parameter gradients.  The backward of the fused path differentiates the fp32 reference function at the same inputs
+    # (test_msg_train_fused_vs_composition: <= 2e-4 for the same upstream gradient); end to end the upstream gradient itself
+    # moves with the ~1e-3 forward deviation, through two batch-normalised Conv1d layers and this random-projection loss.  The
+    # reference's own stock (TF32) run moves by the same amount (scripts/diag_train_grads.py, profiles/r02_diag_train_grads.txt),
+    # so the bar is: the split-arithmetic chains (l0) match tightly, and the fp16-operand chains stay within 3x of what the
+    # reference's shipped configuration does against its own fp32 run.
+    worst = worst_stock = 0.0
+    for (name, p), (_, q), (_, t) in zip(ours.named_parameters(), ref.named_parameters(), stock.named_parameters()):
         assert p.grad is not None and q.grad is not None, name
         worst = max(worst, rel_err(p.grad.cpu().numpy(), q.grad.cpu().numpy()))
-    print(f"[train vs reference] {kind}: worst parameter-gradient relative error {worst:.2e}")
-    assert worst <= 1e-2
+        worst_stock = max(worst_stock, rel_err(t.grad.cpu().numpy(), q.grad.cpu().numpy()))
+    print(f"[train vs reference] {kind}: worst parameter-gradient relative error ours {worst:.2e} / stock-TF32 {worst_stock:.2e}")
+    if kind == "l0":
+        assert worst <= 1e-4
+    else:
+        assert worst <= 0.25 and worst <= 3.0 * worst_stock
+
+
+def test_composition_in_train_mode_is_the_reference_exactly(ref_ops, monkeypatch):
+    """SPSK_TRAIN_FUSED=0: the drop-in module in train() on the op-by-op composition reproduces the reference module's forward,
+    running statistics and parameter gradients to fp32 rounding (same torch layers over bit-exact CUDA ops)."""
+    if ref_ops is None:
+        pytest.skip("oracle/_ref (rebuilt reference) not present")
+    from spsnet_b200 import pointnet2_modules as pm
+
+    monkeypatch.setenv("SPSK_TRAIN_FUSED", "0")
+    kw = copy.deepcopy(REF_KINDS["l1"])
+    cin, n = kw.pop("cin"), kw.pop("n")
+    torch.manual_seed(3)
+    ours = pm.PointnetSAModuleMSG_WithSampling(sample_range_list=[-1], num_class=3, **copy.deepcopy(kw)).cuda().train()
+    ref = ref_ops.modules.PointnetSAModuleMSG_WithSampling(sample_range_list=[-1], num_class=3, **copy.deepcopy(kw)).cuda().train()
+    ref.load_state_dict(ours.state_dict())
+    xyz = dev(scenes.make_batch(62, 2, n)[:, :, :3])
+    feats = torch.randn(2, cin, n, device="cuda")
+    for mod in (ours, ref):
+        out = mod(xyz, feats.clone(), None)
+        torch.manual_seed(14)
+        ((out[1] * torch.randn_like(out[1])).sum() + (out[2] * torch.randn_like(out[2])).sum()).backward()
+        mod._out = out
+    assert rel_err(ours._out[1].detach().cpu().numpy(), ref._out[1].detach().cpu().numpy()) <= 1e-5
+    for (name, p), (_, q) in zip(ours.named_parameters(), ref.named_parameters()):
+        assert rel_err(p.grad.cpu().numpy(), q.grad.cpu().numpy()) <= 1e-4, name
+    for (k, a), (_, b) in zip(ours.state_dict().items(), ref.state_dict().items()):
+        if "running" in k:
+            assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-5, k
 
 
 def test_backbone_training_step_runs_on_the_fused_path(monkeypatch):
