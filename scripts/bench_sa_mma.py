@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Micro-benchmark of the fused scale kernel (sa_mma.cu) on the IA-SSD KITTI shapes, B = 16, with the optional
 per-role cycle counters.   python scripts/bench_sa_mma.py [names...] [--prof]"""
-import sys, time
+import os, sys, time
 from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
@@ -54,9 +54,15 @@ def main():
             buf = torch.zeros(14, dtype=torch.int64, device="cuda")
             lib.spsk_sa_mma_set_profile(buf.data_ptr())
             run(); torch.cuda.synchronize()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            for _ in range(5): run()
+            p1.record(); torch.cuda.synchronize()
+            print(f"   profiling-kernel time {p0.elapsed_time(p1) * 200:8.1f} us  (SPSK_SA_ABL={os.environ.get('SPSK_SA_ABL', '0')})")
+            buf.zero_(); run(); torch.cuda.synchronize()
             lib.spsk_sa_mma_set_profile(None)
             v = buf.cpu().numpy().astype(np.float64)
-            ncta = min(rows // 256, 148) if pk.pair else min(rows // 128, 148 * pk.ctas_per_sm * 2)
+            ncta = min(rows // 256, 148) if pk.pair else min(rows // 128, 148 * pk.ctas_per_sm)   # persistent CTAs: one resident set (grid_mult = 1)
             print("   per-CTA kcycles: " + "  ".join(f"{n}={x/ncta/1e3:.1f}" for n, x in zip(NAMES, v)))
 
 if __name__ == "__main__":

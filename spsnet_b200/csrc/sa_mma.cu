@@ -41,20 +41,17 @@ namespace spsk {
 // G = epilogue warpgroups.  G = 1 (192 threads, up to 3 CTAs per SM) for chains whose concurrency comes from co-resident
 // CTAs; G = 2 (320 threads, one CTA per SM) for the wide chains: the two warpgroups take alternate jobs, so two
 // accumulators drain concurrently and every scheduler holds two epilogue warps to hide TMEM / shared-memory latency.
-// SC = the CTA carries a scout warp (streaming chains; see the tabulated issue loop).  Not for the 3-CTAs-per-SM shapes: a
-// seventh warp would round the register allocation up to eight and cap the epilogue warps at 80 registers.
 // NP = no producer warp (resident chains only: the one bulk load of the chain is issued by the MMA warp): 160-thread CTAs, FOUR
 // per SM at 96 registers.  The narrow chains are bound by the latency of their gather -> MMA -> epilogue hand-offs, i.e. by
 // how many tiles an SM keeps in flight; a fourth CTA is a fourth tile.
-template <int G, bool PROF, bool SC, bool NP>
-__global__ void __launch_bounds__(128 * G + 64 + (SC ? 32 : 0) - (NP ? 32 : 0), G == 1 ? (NP ? 4 : (SC ? 2 : 3)) : 1)
+template <int G, bool PROF, bool NP>
+__global__ void __launch_bounds__(128 * G + 64 - (NP ? 32 : 0), G == 1 ? (NP ? 4 : 3) : 1)
 sa_mma_kernel(const __grid_constant__ SaArgs a) {
-    constexpr int W_PROD = NP ? -1 : 4 * G, W_MMA = NP ? 4 * G : 4 * G + 1, W_SCOUT = 4 * G + 2;
+    constexpr int W_PROD = NP ? -1 : 4 * G, W_MMA = NP ? 4 * G : 4 * G + 1;
     extern __shared__ __align__(128) uint8_t smem[];
     // carve: [header: barriers + tmem slot][XA][XB][weights]
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + MM_HDR - 16);
-    uint32_t *ready_cnt = reinterpret_cast<uint32_t *>(smem + MM_HDR - 32);   // scout -> issuer: schedule entries whose waits are over
     uint8_t *xa = smem + MM_HDR;
     uint8_t *xb = xa + a.xa_bytes;
     uint8_t *wst = xb + a.xb_bytes;
@@ -84,7 +81,6 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
         for (int s = 0; s < MM_MAX_STAGES; ++s) { mbar_init(WL_FULL(s), 1); mbar_init(WL_EMPTY(s), 1); }
         mbar_init(HID_DONE, 1);
         mbar_init_fence();
-        *ready_cnt = 0u;
     }
     if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
     tc_fence_before();
@@ -104,6 +100,30 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                     bulk_g2s(smem_u32(wst + off), a.wtiles + off, (uint32_t)bytes, W_FULL(0));
                 }
             }
+        } else if (a.sched_n > 0) {
+            // table-driven (see the tabulated issue loop): stage, barriers and phase of every weight tile are static per entry
+            ProfT<PROF> pf;
+            pf.init(a.prof != nullptr && leader);
+            const int nent = a.sched_n;
+            uint32_t tpar = 0u, tcount = 0u;
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, tpar ^= 1u, ++tcount) {
+                for (int e = 0; e < nent; ++e) {
+                    const uint4 R = a.ring[e];
+                    if (a.sched[e].w & SCH_LRING_FIRST) { const long long t0 = pf.now(); mbar_wait(HID_DONE, tpar); pf.add(PF_PROD_HID, t0); }
+                    { const long long t0 = pf.now(); mbar_wait(bar0 + ((R.z >> 10) & 1023u), ((R.z >> 20) ^ ((R.z >> 21) & tpar) ^ 1u) & 1u); pf.add(PF_PROD_W_EMPTY, t0); }
+                    if (leader) {
+                        const uint32_t full = bar0 + (R.z & 1023u), bytes = R.y & 0xFFFFu;
+                        if (bytes == 0u || (PROF && (a.abl & 1) && tcount > 0u)) {
+                            mbar_arrive(full);   // padding entry (keeps the ring position static), or ablation: stage "lands" without a copy
+                        } else {
+                            mbar_expect_tx(full, bytes);
+                            bulk_g2s(bar0 + ((R.y >> 16) << 4), a.wtiles + R.x, bytes, full);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            pf.flush(a.prof);
         } else {
             ProfT<PROF> pf;
             pf.init(a.prof != nullptr && leader);
@@ -215,105 +235,73 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                 }
             }
         } else if (a.sched_n > 0) {
-            // Streaming chains: the per-tile schedule (one entry per weight tile) is identical for every tile and every CTA, so the
-            // HOST tabulates it into the kernel parameters (SaArgs::sched, see build_schedule).  Parameters are read with uniform
-            // loads straight into the uniform registers tcgen05.mma takes its operands from: the round-1 table lived in shared
-            // memory, so every descriptor went LDS -> vector register -> R2UR (~100 instructions per weight tile around four
-            // 66-cycle MMAs whose issue blocks).  Entry layout:
-            //   .x = activation descriptor lo of the tile's first K block, RELATIVE to the CTA's dynamic shared memory base
-            //   .y = instruction descriptor   .z = activation desc hi | weight desc hi << 16
-            //   .w = nk16[0:3) first_kc[3] last_kc[4] cc0[5] need_chunk[6:11) lring[11] hid_done[12] last_layer[13] xbuf[14] layer_start[15]
-            //
-            // It also does NO mbarrier wait when the scout warp is on (default).  Measured on this GPU (round 2,
-            // scripts/dev/issue_loop_probe.cu): one mbarrier.try_wait on an ALREADY COMPLETED barrier costs the issuing thread
-            // ~220 cycles -- almost the 264 cycles of the four 128x128x16 MMAs it guards -- and the loop needs one per weight tile
-            // plus one per accumulator and per activation chunk.  The scout warp walks the same schedule, takes every wait in
-            // program order (accumulator free, activation chunks landed, weight stage landed) and publishes the number of
-            // entries that are clear with a release store; the issuer compares a cached copy and re-reads the counter with an
-            // acquire load (one shared-memory load, which usually clears several tiles at once) only when it catches up.
+            // Streaming chains: the per-tile schedule is identical for every tile and every CTA, so the HOST tabulates it into
+            // the kernel parameters (SaArgs::sched / ::ring, see build_schedule) and this loop only interprets it.  What the
+            // ablations of round 2 showed (profiles/r02_sa_mma_ablations.txt): with the weight copies removed, or the hidden
+            // epilogues, the kernel time did not move, and with THREE OF FOUR MMAs removed it dropped by 15 % -- the chain was
+            // bound by this single warp's instruction latency per weight tile (ring bookkeeping, barrier addresses, phase bits
+            // kept in local memory, flag decoding: ~450 cycles around four 66-cycle MMAs), not by the tensor pipe.  So everything
+            // that can be static IS static: the ring slot of every weight tile is fixed by padding each ring's entries per tile
+            // to a multiple of its depth (padding entries: the producer arrives without copying, this loop only releases the
+            // slot), which makes the slot address, both barrier addresses and the phase parity table constants -- parity =
+            // static bit ^ (tile parity & "odd number of uses per tile" bit).  Parameters are read with uniform loads straight
+            // into the uniform registers tcgen05.mma takes its operands from.
+            //   sched[e]: .x activation descriptor lo of the tile's first K block, relative to the CTA's shared memory (16 B units)
+            //             .y instruction descriptor   .z activation desc hi | weight desc hi << 16   .w SCH_* flags | nk16
+            //   ring[e] : .x byte offset of the weight tile in the packed weights   .y bytes (0 = padding) | slot offset / 16 << 16
+            //             .z full barrier | empty barrier << 10 | parity << 20 | parity tile-dependent << 21 | activation wait
+            //                valid << 22 | its parity << 23 | tile-dependent << 24   .w activation-chunk barrier  (offsets from bar0)
             const bool leader = elect_one();
             ProfT<PROF> pf;
             pf.init(a.prof != nullptr && leader);
             const long long t_start = pf.now();
-            uint32_t job = 0;
-            int ws = 0, ls = 0;
-            uint32_t wph = 0u, lph = 0u;
-            uint32_t xph[2] = {0u, 0u};
-            uint8_t *lst = ((nL - 2) & 1) ? xb : xa;
+            uint32_t job = 0, tpar = 0u;
             const uint32_t nbmask = (uint32_t)a.nbuf - 1u;
             const int nent = a.sched_n;
-            const bool scout = SC && a.scout != 0;
-            const uint32_t ready_addr = smem_u32(ready_cnt);
-            const uint32_t smem_base16 = smem_u32(smem) >> 4;   // descriptor units
-            uint32_t done = 0u, avail = 0u;   // entries issued so far / entries known to be clear
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-                int xwait = 0, buf = 0;
+            const uint32_t smem_base16 = bar0 >> 4;   // descriptor units
+            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, tpar ^= 1u) {
+                int buf = 0;
                 uint32_t d_tmem = tmem_base;
                 for (int e = 0; e < nent; ++e) {
-                    uint4 E = a.sched[e];
-                    E.x += smem_base16;
+                    const uint4 E = a.sched[e];
+                    const uint4 R = a.ring[e];
                     const uint32_t f = E.w;
-                    if (f & (1u << 15)) xwait = 0;
-                    if (f & (1u << 3)) {
+                    if (f & SCH_FIRST_KC) {
                         buf = (int)(job & nbmask);
                         const uint32_t use = job >> a.nbuf_log2;
-                        if (!scout && use > 0) { const long long t0 = pf.now(); mbar_wait(ACC_EMPTY(buf), (use - 1) & 1u); pf.add(PF_MMA_ACC_EMPTY, t0); }
+                        if (use > 0) { const long long t0 = pf.now(); mbar_wait(ACC_EMPTY(buf), (use - 1) & 1u); pf.add(PF_MMA_ACC_EMPTY, t0); }
                         d_tmem = tmem_base + (uint32_t)(buf * 128);
                     }
-                    uint32_t wbase, wempty;
-                    if (f & (1u << 11)) {
-                        if (!scout) { const long long t0 = pf.now(); mbar_wait(WL_FULL(ls), lph); pf.add(PF_MMA_ISSUE, t0); }   // (profile slot "mma_issue" = last-layer ring waits in this path)
-                        wbase = smem_u32(lst + (size_t)ls * MM_STAGE_BYTES);
-                        wempty = WL_EMPTY(ls);
-                        if (++ls == a.lstages) { ls = 0; lph ^= 1u; }
-                    } else {
-                        if (!scout) { const long long t0 = pf.now(); mbar_wait(W_FULL(ws), wph); pf.add(PF_MMA_W_FULL, t0); }
-                        wbase = smem_u32(wst + (size_t)ws * MM_STAGE_BYTES);
-                        wempty = W_EMPTY(ws);
-                        if (++ws == a.nstages) { ws = 0; wph ^= 1u; }
-                    }
-                    if (!scout && (f & (1u << 5))) {
-                        const int need = (int)((f >> 6) & 31u);
-                        const int xbuf = (int)((f >> 14) & 1u);
-                        while (xwait <= need) {
-                            const long long t0 = pf.now();
-                            mbar_wait(XR(xbuf, xwait), (xph[xbuf] >> xwait) & 1u);
-                            pf.add(PF_MMA_XR, t0);
-                            xph[xbuf] ^= (1u << xwait);
-                            ++xwait;
-                        }
-                    }
-                    ++done;
-                    if (scout && avail < done) {
-                        const long long t0 = pf.now();
-                        uint32_t spin = 0u;
-                        do {
-                            asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(avail) : "r"(ready_addr) : "memory");
-                            if (++spin > (1u << 26)) __trap();   // a protocol bug traps instead of hanging the GPU
-                        } while (avail < done);
-                        pf.add(PF_MMA_W_FULL, t0);
-                    }
+                    { const long long t0 = pf.now(); mbar_wait(bar0 + (R.z & 1023u), ((R.z >> 20) ^ ((R.z >> 21) & tpar)) & 1u); pf.add(PF_MMA_W_FULL, t0); }
+                    if (R.z & (1u << 22)) { const long long t0 = pf.now(); mbar_wait(bar0 + R.w, ((R.z >> 23) ^ ((R.z >> 24) & tpar)) & 1u); pf.add(PF_MMA_XR, t0); }
                     tc_fence_after();
                     if (leader) {
-                        const uint32_t w_lo = umma_desc_lo(wbase, 128u);
-                        const uint32_t x_hi = E.z & 0xFFFFu, w_hi = E.z >> 16;
-                        const int nk16 = (int)(f & 7u);
-                        const uint32_t acc0 = (f & (1u << 3)) ? 0u : 1u;
-                        if (!(f & (1u << 13))) {
-                            umma_f16_lohi(d_tmem, E.x, x_hi, w_lo, w_hi, E.y, acc0);
-                            for (int j = 1; j < nk16; ++j) umma_f16_lohi(d_tmem, E.x + 16u * j, x_hi, w_lo + 16u * j, w_hi, E.y, 1u);
-                        } else {
-                            umma_f16_lohi(d_tmem, w_lo, w_hi, E.x, x_hi, E.y, acc0);
-                            for (int j = 1; j < nk16; ++j) umma_f16_lohi(d_tmem, w_lo + 16u * j, w_hi, E.x + 16u * j, x_hi, E.y, 1u);
+                        const long long t_i = pf.now();
+                        const int nk16 = (PROF && (a.abl & 8) && (f & 7u)) ? 1 : (int)(f & 7u);   // 0 for padding entries
+                        if (nk16) {
+                            const uint32_t x_lo = E.x + smem_base16;
+                            const uint32_t w_lo = (((smem_base16 + (R.y >> 16)) & 0x3FFFu) | ((128u >> 4) << 16));   // umma_desc_lo(slot, LBO 128)
+                            const uint32_t x_hi = E.z & 0xFFFFu, w_hi = E.z >> 16;
+                            const uint32_t acc0 = (f & SCH_FIRST_KC) ? 0u : 1u;
+                            if (!(f & SCH_LAST_LAYER)) {
+                                umma_f16_lohi(d_tmem, x_lo, x_hi, w_lo, w_hi, E.y, acc0);
+                                for (int j = 1; j < nk16; ++j) umma_f16_lohi(d_tmem, x_lo + 16u * j, x_hi, w_lo + 16u * j, w_hi, E.y, 1u);
+                            } else {
+                                umma_f16_lohi(d_tmem, w_lo, w_hi, x_lo, x_hi, E.y, acc0);
+                                for (int j = 1; j < nk16; ++j) umma_f16_lohi(d_tmem, w_lo + 16u * j, w_hi, x_lo + 16u * j, x_hi, E.y, 1u);
+                            }
                         }
-                        umma_commit(wempty);   // stage reusable once these MMAs retire
-                        if (f & (1u << 4)) {
+                        pf.add(PF_MMA_ISSUE, t_i);
+                        const long long t_c = pf.now();
+                        umma_commit(bar0 + ((R.z >> 10) & 1023u));   // slot reusable once these MMAs retire
+                        if (f & SCH_LAST_KC) {
                             umma_commit(ACC_FULL(buf));
-                            if (f & (1u << 12)) umma_commit(HID_DONE);
+                            if (f & SCH_HID_DONE) umma_commit(HID_DONE);
                         }
+                        pf.add(PF_MMA_COMMIT, t_c);
                     }
                     __syncwarp();
-                    if (f & (1u << 4)) ++job;
+                    if (f & SCH_LAST_KC) ++job;
                 }
             }
             pf.add(PF_MMA_TOTAL, t_start);
@@ -424,52 +412,6 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
             }
             pf.add(PF_MMA_TOTAL, t_start);
             pf.flush(a.prof);
-        }
-    } else if (SC && warp == W_SCOUT) {
-        // ================= scout: every wait of the tabulated issue loop, taken ahead of the issuer =================
-        // Same schedule, same order, same phase bookkeeping as the issuer; after the waits of entry e are over it publishes
-        // e + 1 (release store: the bulk copies and epilogue stores it observed through the barriers are visible to whoever
-        // acquires the counter).  It can never run more than one barrier phase ahead: a stage / accumulator / activation chunk
-        // is only refilled after the ISSUER has consumed it, and the issuer consumes nothing the scout has not cleared.
-        if (a.sched_n > 0 && a.scout && !a.narrow) {
-            uint32_t job = 0, count = 0u;
-            int ws = 0, ls = 0;
-            uint32_t wph = 0u, lph = 0u;
-            uint32_t xph[2] = {0u, 0u};
-            const uint32_t nbmask = (uint32_t)a.nbuf - 1u;
-            const int nent = a.sched_n;
-            const uint32_t ready_addr = smem_u32(ready_cnt);
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-                int xwait = 0;
-                for (int e = 0; e < nent; ++e) {
-                    const uint32_t f = a.sched[e].w;
-                    if (f & (1u << 15)) xwait = 0;
-                    if (f & (1u << 3)) {
-                        const int buf = (int)(job & nbmask);
-                        const uint32_t use = job >> a.nbuf_log2;
-                        if (use > 0) mbar_wait(ACC_EMPTY(buf), (use - 1) & 1u);
-                    }
-                    if (f & (1u << 5)) {
-                        const int need = (int)((f >> 6) & 31u);
-                        const int xbuf = (int)((f >> 14) & 1u);
-                        while (xwait <= need) {
-                            mbar_wait(XR(xbuf, xwait), (xph[xbuf] >> xwait) & 1u);
-                            xph[xbuf] ^= (1u << xwait);
-                            ++xwait;
-                        }
-                    }
-                    if (f & (1u << 11)) {
-                        mbar_wait(WL_FULL(ls), lph);
-                        if (++ls == a.lstages) { ls = 0; lph ^= 1u; }
-                    } else {
-                        mbar_wait(W_FULL(ws), wph);
-                        if (++ws == a.nstages) { ws = 0; wph ^= 1u; }
-                    }
-                    ++count;
-                    if ((tid & 31) == 0) asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(ready_addr), "r"(count) : "memory");
-                    if (f & (1u << 4)) ++job;
-                }
-            }
         }
     } else {
         // ================= gather + epilogue (threads 0..127; thread = row / TMEM lane) =================
@@ -647,7 +589,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                     if (!a.split) {
                         for (int h0 = 0; h0 < ncols; h0 += 64) {   // one 64-wide K chunk of the next operand at a time
                             const int hend = min(ncols, h0 + 64);
-                            int c0 = h0;
+                            int c0 = (PROF && (a.abl & 2)) ? hend : h0;   // ablation: no TMEM loads / stores, only the hand-off
                             for (; c0 + 32 <= hend; c0 += 32) {
                                 float v[32];
                                 tmem_ld32(taddr + (uint32_t)c0, v);
@@ -782,18 +724,19 @@ static unsigned long long *g_sa_prof = nullptr;
 // ---- tuning / A-B knobs: environment variables, read ONCE per process (not on every launch) -------------------------------
 struct SaTuning {
     int max_stages, max_ctas, grid_mult;
-    bool no_lring, no_sched, rot, no_narrow, one_group, scout;
+    int abl;
+    bool no_lring, no_sched, rot, no_narrow, one_group;
     SaTuning() {
         auto geti = [](const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; };
         max_stages = max(2, min(MM_MAX_STAGES, geti("SPSK_SA_MAX_STAGES", MM_MAX_STAGES)));   // sensitivity measurements
         max_ctas = max(1, min(4, geti("SPSK_SA_MAX_CTAS", 4)));
         grid_mult = max(1, min(8, geti("SPSK_SA_GRID_MULT", 1)));   // persistent CTAs, exactly one resident set (2 measured 1 % slower with 8 batches in flight)
+        abl = geti("SPSK_SA_ABL", 0);                                 // ablations of the profiling kernels (see SaArgs::abl)
         no_lring = getenv("SPSK_SA_NO_LRING") != nullptr;
         no_sched = getenv("SPSK_SA_NO_SCHED") != nullptr;
         rot = getenv("SPSK_SA_ROT") != nullptr;              // opt-in: measured neutral on B200 (the weight stream is not L2 hot-line bound)
         no_narrow = getenv("SPSK_SA_NO_NARROW") != nullptr;
         one_group = getenv("SPSK_SA_ONE_GROUP") != nullptr;
-        scout = getenv("SPSK_SA_SCOUT") != nullptr;          // opt-in: measured neutral on B200 (292 vs 280-290 us on layer 5 scale 2): the waits it removes are real stalls
     }
 };
 static const SaTuning &sa_tuning() {
@@ -901,38 +844,93 @@ static int sa_plan(const spsk_sa_mma_desc *d, SaPlan *P) {
     return SPSK_OK;
 }
 
-// The per-tile MMA schedule of a streaming chain (see the tabulated issue loop of sa_mma_kernel).  Shared-memory addresses are
-// relative to the CTA's dynamic shared memory: [header MM_HDR][XA][XB][weight ring].
-static void build_schedule(SaArgs &a) {
+// The per-tile schedule of a streaming chain (see the tabulated issue loop and the table-driven producer of sa_mma_kernel).
+// Shared-memory offsets are relative to the CTA's dynamic shared memory: [header MM_HDR: barriers][XA][XB][weight ring]; the
+// barrier offsets mirror the W_FULL / W_EMPTY / XR / WL_FULL / WL_EMPTY lambdas of the kernel.  Returns the number of entries
+// (weight tiles + ring padding), or 0 when it does not fit MM_SCHED_MAX.
+static int build_schedule(SaArgs &a) {
     const int nL = a.nlayers;
-    int e = 0;
+    const bool lring = a.lstages > 0;
+    auto w_full = [](int s) { return 8u * (uint32_t)s; };
+    auto w_empty = [](int s) { return 8u * (uint32_t)(MM_MAX_STAGES + s); };
+    auto xr = [](int buf, int c) { return 8u * (uint32_t)(2 * MM_MAX_STAGES + 8 + buf * MM_MAX_XC + c); };
+    auto wl_full = [](int s) { return 8u * (uint32_t)(2 * MM_MAX_STAGES + 8 + 2 * MM_MAX_XC + s); };
+    auto wl_empty = [](int s) { return 8u * (uint32_t)(3 * MM_MAX_STAGES + 8 + 2 * MM_MAX_XC + s); };
+    // entries per tile of each ring, padded to a multiple of its depth
+    int n_ring[2] = {0, 0};
+    for (int l = 0; l < nL; ++l) n_ring[(lring && l == nL - 1) ? 1 : 0] += a.L[l].n_cc * a.L[l].n_kc;
+    const int depth[2] = {a.nstages, lring ? a.lstages : 1};
+    int pad[2], uses[2];
+    for (int r = 0; r < 2; ++r) {
+        pad[r] = (depth[r] - n_ring[r] % depth[r]) % depth[r];
+        uses[r] = (n_ring[r] + pad[r]) / depth[r];
+    }
+    if (n_ring[0] + n_ring[1] + pad[0] + pad[1] > MM_SCHED_MAX) return 0;
+    // completions per tile of every activation-chunk barrier (a buffer serves layers l, l+2, ...)
+    int n_compl[2][MM_MAX_XC] = {};
+    for (int l = 0; l < nL; ++l)
+        for (int c = 0; c < a.L[l].n_xc; ++c) ++n_compl[l & 1][c];
+    const uint32_t ring_base[2] = {(uint32_t)(MM_HDR + a.xa_bytes + a.xb_bytes),
+                                   (uint32_t)MM_HDR + ((((nL - 2) & 1) && nL >= 2) ? (uint32_t)a.xa_bytes : 0u)};   // overlay: input buffer of layer nL-2
+    int e = 0, pos[2] = {0, 0};
+    int seen[2][MM_MAX_XC] = {};   // completions of each activation-chunk barrier before the layer being emitted
+    auto ring_words = [&](int r, uint32_t src, uint32_t bytes, uint4 &R) {
+        const int slot = pos[r] % depth[r], k = pos[r] / depth[r];
+        ++pos[r];
+        const uint32_t slot_off = ring_base[r] + (uint32_t)slot * MM_STAGE_BYTES;
+        const uint32_t full = r ? wl_full(slot) : w_full(slot), empty = r ? wl_empty(slot) : w_empty(slot);
+        R.x = src;
+        R.y = bytes | ((slot_off >> 4) << 16);
+        R.z = full | (empty << 10) | ((uint32_t)(k & 1) << 20) | ((uint32_t)(uses[r] & 1) << 21);
+        R.w = 0u;
+    };
+    auto pad_ring = [&](int r) {
+        for (int i = 0; i < pad[r]; ++i, ++e) {
+            uint4 R;
+            ring_words(r, 0u, 0u, R);
+            a.sched[e] = make_uint4(0u, 0u, 0u, 0u);   // no MMAs, no job flags: the issuer only releases the slot
+            a.ring[e] = R;
+        }
+    };
     for (int l = 0; l < nL; ++l) {
         const SaLayer &Ly = a.L[l];
         const bool last = (l == nL - 1);
+        const int r = (lring && last) ? 1 : 0;
+        if (r == 1) pad_ring(0);   // ring 0 is complete for this tile before the overlay ring starts
         const uint32_t x_off = (uint32_t)MM_HDR + ((l & 1) ? (uint32_t)a.xa_bytes : 0u);
         const uint32_t x_lo0 = (x_off >> 4) | ((128u >> 4) << 16);                  // umma_desc_lo(base + x_off, LBO 128) - (base >> 4)
         const uint32_t x_hi = (((uint32_t)Ly.xw * 16u) >> 4) | (1u << 14);           // umma_desc_hi(SBO)
         for (int cci = 0; cci < Ly.n_cc; ++cci) {
-            const int ncols = (Ly.cpad - cci * 128) < 128 ? (Ly.cpad - cci * 128) : 128;   // (a rotated chunk order only permutes equal 128-wide chunks)
+            const int ncols = (Ly.cpad - cci * 128) < 128 ? (Ly.cpad - cci * 128) : 128;
             for (int kc = 0; kc < Ly.n_kc; ++kc, ++e) {
                 const int kw = (Ly.wk - kc * 64) < 64 ? (Ly.wk - kc * 64) : 64;
                 const int nk16 = kw >> 4;
                 uint32_t f = (uint32_t)nk16;
-                if (kc == 0) f |= 1u << 3;
-                if (kc == Ly.n_kc - 1) f |= 1u << 4;
-                if (cci == 0) f |= (1u << 5) | ((uint32_t)((kc * 4 + nk16 - 1) >> 2) << 6);
-                if (a.lstages > 0 && last) f |= 1u << 11;
-                if (a.lstages > 0 && l == nL - 2 && cci == Ly.n_cc - 1 && kc == Ly.n_kc - 1) f |= 1u << 12;
-                if (last) f |= 1u << 13;
-                f |= (uint32_t)(l & 1) << 14;
-                if (cci == 0 && kc == 0) f |= 1u << 15;
+                if (kc == 0) f |= SCH_FIRST_KC;
+                if (kc == Ly.n_kc - 1) f |= SCH_LAST_KC;
+                if (r == 1 && cci == 0 && kc == 0) f |= SCH_LRING_FIRST;
+                if (lring && l == nL - 2 && cci == Ly.n_cc - 1 && kc == Ly.n_kc - 1) f |= SCH_HID_DONE;
+                if (last) f |= SCH_LAST_LAYER;
                 const int n_idesc = last ? MM_ROWS : ncols;
                 const uint32_t idesc = (1u << 4) | ((uint32_t)(n_idesc >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // umma_idesc(128, n)
                 const uint32_t w_hi = (((uint32_t)kw * 16u) >> 4) | (1u << 14);
                 a.sched[e] = make_uint4(x_lo0 + (uint32_t)kc * 64u, idesc, x_hi | (w_hi << 16), f);
+                uint4 R;
+                ring_words(r, (uint32_t)(Ly.w_off + (128 * cci * Ly.wk + ncols * 64 * kc) * 2), (uint32_t)(ncols * kw * 2), R);
+                if (cci == 0) {
+                    // the 64-wide activation chunk this weight tile reads first becomes ready during the first cout chunk of the layer
+                    // (chunk kc: written by the gather / the previous layer's epilogue); later cout chunks re-read what is already there
+                    const int c = kc;   // (kc * 4 + nk16 - 1) >> 2
+                    R.z |= (1u << 22) | ((uint32_t)(seen[l & 1][c] & 1) << 23) | ((uint32_t)(n_compl[l & 1][c] & 1) << 24);
+                    R.w = xr(l & 1, c);
+                }
+                a.ring[e] = R;
             }
         }
+        for (int c = 0; c < Ly.n_xc; ++c) ++seen[l & 1][c];
     }
+    pad_ring(lring ? 1 : 0);
+    return e;
 }
 
 }  // namespace spsk
@@ -1024,7 +1022,6 @@ extern "C" int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stre
     a.ntiles = (int)ntiles;
     a.lstages = P.lstages;
     a.sched_n = P.sched_n;
-    a.scout = sa_tuning().scout ? 1 : 0;
     a.rot_last = (P.L[d->nlayers - 1].n_cc > 1 && sa_tuning().rot) ? 1 : 0;
     a.l0_fused = d->l0_fused ? 1 : 0;
     a.l0_off = P.l0_off;
@@ -1052,6 +1049,7 @@ extern "C" int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stre
     a.ovf = fp16_overflow_word();
     a.ovf_bit = 1u << (d->ovf_tag & 31);
     a.stats = d->stats;
+    a.abl = sa_tuning().abl;
     if (d->pair) {
         a.ntiles = (int)((a.rows + 255) / 256);   // 256-row tiles, one per CTA pair
         return spsk_sa_mma_pair_launch(a, P.smem, as_stream(stream));
@@ -1059,7 +1057,10 @@ extern "C" int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stre
     const int mult = sa_tuning().grid_mult;
     const int slots = SPSK_NUM_SMS * P.ctas * mult;
     const int grid = a.ntiles < slots ? a.ntiles : slots;
-    if (a.sched_n > 0) build_schedule(a);
+    if (a.sched_n > 0) {
+        a.sched_n = build_schedule(a);   // 0: does not fit the table, the general issue loop takes over
+        if (a.sched_n > 0) a.rot_last = 0;   // the table fixes the chunk order
+    }
     const bool two_groups = P.ctas == 1 && !sa_tuning().one_group;
     if (a.stats) {
         SPSK_REQUIRE((reinterpret_cast<uintptr_t>(d->stats) & 15) == 0, SPSK_ERR_INVALID_ARG, "sa_mma: stats must be 16-byte aligned");
@@ -1067,30 +1068,26 @@ extern "C" int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stre
                      d->stats_parts, grid * (two_groups ? 2 : 1));
         a.out = nullptr; a.out16 = nullptr;
     }
-    const bool sc = a.scout && a.sched_n > 0 && !a.narrow && (two_groups || P.ctas <= 2);
-    a.scout = sc ? 1 : 0;
-#define SPSK_SA_LAUNCH(GV, PV, SCV)                                                                                          \
+#define SPSK_SA_LAUNCH(GV, PV)                                                                                               \
     do {                                                                                                                    \
         static SmemAttrOnce attr;                                                                                           \
-        if (int rc = attr.ensure(reinterpret_cast<const void *>(sa_mma_kernel<GV, PV, SCV, false>), 227 * 1024, "sa_mma_kernel")) return rc; \
-        sa_mma_kernel<GV, PV, SCV, false><<<grid, 128 * GV + 64 + (SCV ? 32 : 0), P.smem, as_stream(stream)>>>(a);            \
+        if (int rc = attr.ensure(reinterpret_cast<const void *>(sa_mma_kernel<GV, PV, false>), 227 * 1024, "sa_mma_kernel")) return rc; \
+        sa_mma_kernel<GV, PV, false><<<grid, 128 * GV + 64, P.smem, as_stream(stream)>>>(a);                                    \
     } while (0)
     if (P.ctas == 4) {   // resident narrow chain, no producer warp
         SPSK_REQUIRE(a.narrow && a.resident, SPSK_ERR_UNSUPPORTED, "sa_mma: the 4-CTA shape needs the resident narrow issue loop (unset SPSK_SA_NO_NARROW)");
         static SmemAttrOnce attr4, attr4p;
         if (a.prof) {
-            if (int rc = attr4p.ensure(reinterpret_cast<const void *>(sa_mma_kernel<1, true, false, true>), 227 * 1024, "sa_mma_kernel<np,prof>")) return rc;
-            sa_mma_kernel<1, true, false, true><<<grid, 160, P.smem, as_stream(stream)>>>(a);
+            if (int rc = attr4p.ensure(reinterpret_cast<const void *>(sa_mma_kernel<1, true, true>), 227 * 1024, "sa_mma_kernel<np,prof>")) return rc;
+            sa_mma_kernel<1, true, true><<<grid, 160, P.smem, as_stream(stream)>>>(a);
         } else {
-            if (int rc = attr4.ensure(reinterpret_cast<const void *>(sa_mma_kernel<1, false, false, true>), 227 * 1024, "sa_mma_kernel<np>")) return rc;
-            sa_mma_kernel<1, false, false, true><<<grid, 160, P.smem, as_stream(stream)>>>(a);
+            if (int rc = attr4.ensure(reinterpret_cast<const void *>(sa_mma_kernel<1, false, true>), 227 * 1024, "sa_mma_kernel<np>")) return rc;
+            sa_mma_kernel<1, false, true><<<grid, 160, P.smem, as_stream(stream)>>>(a);
         }
     } else if (two_groups) {
-        if (a.prof) { if (sc) SPSK_SA_LAUNCH(2, true, true); else SPSK_SA_LAUNCH(2, true, false); }
-        else { if (sc) SPSK_SA_LAUNCH(2, false, true); else SPSK_SA_LAUNCH(2, false, false); }
+        if (a.prof) SPSK_SA_LAUNCH(2, true); else SPSK_SA_LAUNCH(2, false);
     } else {
-        if (a.prof) { if (sc) SPSK_SA_LAUNCH(1, true, true); else SPSK_SA_LAUNCH(1, true, false); }
-        else { if (sc) SPSK_SA_LAUNCH(1, false, true); else SPSK_SA_LAUNCH(1, false, false); }
+        if (a.prof) SPSK_SA_LAUNCH(1, true); else SPSK_SA_LAUNCH(1, false);
     }
 #undef SPSK_SA_LAUNCH
     SPSK_LAUNCH_CHECK("sa_mma_kernel");

@@ -6,12 +6,18 @@
 namespace spsk {
 
 constexpr int MM_ROWS = 128;          // grouped rows per tile
-constexpr int MM_THREADS = 224;       // G = 1: 4 gather/epilogue warps + producer + mma + scout;  G = 2: 8 + 3 = 352 threads
+constexpr int MM_THREADS = 192;       // G = 1: 4 gather/epilogue warps + producer + mma;  G = 2: 8 + 2 warps = 320 threads
 constexpr int MM_STAGE_BYTES = 16384; // largest weight tile: [128 cout][64 k] fp16
 constexpr int MM_MAX_LAYERS = 4;
 constexpr int MM_MAX_STAGES = 8;
 constexpr int MM_HDR = 1024;          // barriers + TMEM slot
-constexpr int MM_SCHED_MAX = 104;     // tabulated weight tiles per row tile (16 bytes each, placed after the header)
+constexpr int MM_SCHED_MAX = 104;     // tabulated weight tiles (+ ring padding entries) per row tile, 2 x 16 bytes each in the kernel parameters
+// flags of SaArgs::sched[e].w (bits 0..2 = MMAs of the entry, kw / 16; 0 for a padding entry)
+constexpr uint32_t SCH_FIRST_KC = 1u << 3;      // first weight tile of a job: take an accumulator
+constexpr uint32_t SCH_LAST_KC = 1u << 4;       // last weight tile of a job: commit the accumulator
+constexpr uint32_t SCH_LRING_FIRST = 1u << 11;  // first entry of the tile on the last layer's overlay ring: the producer waits for HID_DONE
+constexpr uint32_t SCH_HID_DONE = 1u << 12;     // last MMAs reading the activation buffer the overlay ring lives in
+constexpr uint32_t SCH_LAST_LAYER = 1u << 13;   // orientation B (weights are the A operand)
 constexpr int MM_MAX_XC = 16;         // 64-wide K chunks per activation buffer (K <= 1024)
 
 struct SaLayer {
@@ -37,7 +43,6 @@ struct SaArgs {
     int nstages, resident, w_total, tmem_cols, nbuf, nbuf_log2;
     int l0_fused, l0_off;   // split chains: layer 0 (K <= 11 real inputs) is evaluated in fp32 by the gather threads from the
                             // [16][cpad0] fp32 weights + bias appended to the resident weights at byte l0_off; the MMA chain starts at layer 1
-    int scout;       // tabulated issue loop: the scout warp takes every mbarrier wait and publishes a ready counter
     int rot_last;    // rotate the last layer's cout-chunk order by blockIdx (de-synchronises the CTAs' weight streams)
     int sched_n;     // > 0: streaming chain whose per-tile MMA schedule (sched_n weight tiles) is tabulated in shared memory
     int narrow;      // resident chain with one job per layer: the MMA warp runs the register-resident fast loop
@@ -56,8 +61,12 @@ struct SaArgs {
     unsigned long long *prof;   // optional per-role wait/work cycle counters (spsk_sa_mma_set_profile), null = off
     unsigned int *ovf;          // fp16 range guard word of this device (may be null) and this call's tag bit
     unsigned int ovf_bit;
+    int abl;                    // measurement aid, honoured by the PROFILING kernel variants only (SPSK_SA_ABL bit mask; results are then
+                                // WRONG by design): 1 = the producer signals weight stages without copying after the first tile,
+                                // 2 = hidden epilogues skip their shared-memory stores, 8 = one MMA per weight tile instead of kw/16
     double *stats;              // batch-statistics pass (training-mode BN): per-(CTA, epilogue group) partial sums, see include/spsk.h
     uint4 sched[MM_SCHED_MAX];  // streaming chains: the per-tile MMA schedule (sched_n entries), see sa_mma.cu::build_schedule
+    uint4 ring[MM_SCHED_MAX];   // ... and, per entry, the static ring slot / barriers / phase parities / global source of its weight tile
 };
 
 // byte offset of weight tile (cc, kc) inside a layer: chunks of 128 couts are contiguous (cc-major), inside a chunk

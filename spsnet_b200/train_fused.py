@@ -332,6 +332,8 @@ def msg_train(module, xyz: torch.Tensor, new_xyz: torch.Tensor, features: Option
     kernel covers (the caller then runs the reference composition)."""
     if not xyz.is_cuda or module.pool_method != "max_pool" or len(module.mlps) == 0:
         return None
+    if torch.is_autocast_enabled() or xyz.dtype != torch.float32 or (features is not None and features.dtype != torch.float32):
+        return None   # mixed-precision training keeps torch's own casting rules: the composition handles it
     if not all(isinstance(g, (pu.QueryAndGroup, pu.QueryDilatedAndGroup)) for g in module.groupers):
         return None
     c_feat = features.shape[1] if features is not None else 0
