@@ -246,11 +246,13 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
             // slot), which makes the slot address, both barrier addresses and the phase parity table constants -- parity =
             // static bit ^ (tile parity & "odd number of uses per tile" bit).  Parameters are read with uniform loads straight
             // into the uniform registers tcgen05.mma takes its operands from.
-            //   sched[e]: .x activation descriptor lo of the tile's first K block, relative to the CTA's shared memory (16 B units)
-            //             .y instruction descriptor   .z activation desc hi | weight desc hi << 16   .w SCH_* flags | nk16
-            //   ring[e] : .x byte offset of the weight tile in the packed weights   .y bytes (0 = padding) | slot offset / 16 << 16
-            //             .z full barrier | empty barrier << 10 | parity << 20 | parity tile-dependent << 21 | activation wait
-            //                valid << 22 | its parity << 23 | tile-dependent << 24   .w activation-chunk barrier  (offsets from bar0)
+            //   sched[e]: .x activation descriptor lo of the entry's first K block, relative to the CTA's shared memory (16 B units)
+            //             .y instruction descriptor   .z activation desc hi | weight desc hi << 16   .w SCH_* flags | MMAs | 2nd-tile offset
+            //   ring[e] : .x byte offset of the weight tile(s) in the packed weights   .y bytes (0 = padding) | slot offset / 16 << 16
+            //             .z full barrier | empty barrier << 10 | parity << 20 | parity tile-dependent << 21 | up to two activation
+            //                waits: valid / parity / tile-dependent at bits 22..24 and 25..27   .w their barriers (10 bits each; offsets from bar0)
+            // An entry covers ONE 64-wide k tile (16 KB slot) or, where the ring has room for >= 2 slots of 32 KB, TWO consecutive
+            // ones (one bulk copy, 8 MMAs): the waits, the commit and this loop's latency are paid per entry, the MMAs are not.
             const bool leader = elect_one();
             ProfT<PROF> pf;
             pf.init(a.prof != nullptr && leader);
@@ -259,12 +261,13 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
             const uint32_t nbmask = (uint32_t)a.nbuf - 1u;
             const int nent = a.sched_n;
             const uint32_t smem_base16 = bar0 >> 4;   // descriptor units
+            uint4 E = a.sched[0], R = a.ring[0];
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, tpar ^= 1u) {
                 int buf = 0;
                 uint32_t d_tmem = tmem_base;
                 for (int e = 0; e < nent; ++e) {
-                    const uint4 E = a.sched[e];
-                    const uint4 R = a.ring[e];
+                    const int en = e + 1 < nent ? e + 1 : 0;
+                    const uint4 En = a.sched[en], Rn = a.ring[en];   // next entry: its constant-bank latency hides under this entry's waits
                     const uint32_t f = E.w;
                     if (f & SCH_FIRST_KC) {
                         buf = (int)(job & nbmask);
@@ -273,22 +276,31 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                         d_tmem = tmem_base + (uint32_t)(buf * 128);
                     }
                     { const long long t0 = pf.now(); mbar_wait(bar0 + (R.z & 1023u), ((R.z >> 20) ^ ((R.z >> 21) & tpar)) & 1u); pf.add(PF_MMA_W_FULL, t0); }
-                    if (R.z & (1u << 22)) { const long long t0 = pf.now(); mbar_wait(bar0 + R.w, ((R.z >> 23) ^ ((R.z >> 24) & tpar)) & 1u); pf.add(PF_MMA_XR, t0); }
+                    if (R.z & (1u << 22)) {
+                        const long long t0 = pf.now();
+                        mbar_wait(bar0 + (R.w & 1023u), ((R.z >> 23) ^ ((R.z >> 24) & tpar)) & 1u);
+                        if (R.z & (1u << 25)) mbar_wait(bar0 + (R.w >> 10), ((R.z >> 26) ^ ((R.z >> 27) & tpar)) & 1u);
+                        pf.add(PF_MMA_XR, t0);
+                    }
                     tc_fence_after();
                     if (leader) {
                         const long long t_i = pf.now();
-                        const int nk16 = (PROF && (a.abl & 8) && (f & 7u)) ? 1 : (int)(f & 7u);   // 0 for padding entries
+                        const int nk16 = (PROF && (a.abl & 8) && (f & 15u)) ? 1 : (int)(f & 15u);   // 0 for padding entries
                         if (nk16) {
                             const uint32_t x_lo = E.x + smem_base16;
                             const uint32_t w_lo = (((smem_base16 + (R.y >> 16)) & 0x3FFFu) | ((128u >> 4) << 16));   // umma_desc_lo(slot, LBO 128)
+                            const uint32_t w_lo2 = w_lo + ((f >> 16) & 2047u) - 64u;                                  // second k tile, minus its j offset
                             const uint32_t x_hi = E.z & 0xFFFFu, w_hi = E.z >> 16;
                             const uint32_t acc0 = (f & SCH_FIRST_KC) ? 0u : 1u;
+                            const int n1 = nk16 < 4 ? nk16 : 4;
                             if (!(f & SCH_LAST_LAYER)) {
                                 umma_f16_lohi(d_tmem, x_lo, x_hi, w_lo, w_hi, E.y, acc0);
-                                for (int j = 1; j < nk16; ++j) umma_f16_lohi(d_tmem, x_lo + 16u * j, x_hi, w_lo + 16u * j, w_hi, E.y, 1u);
+                                for (int j = 1; j < n1; ++j) umma_f16_lohi(d_tmem, x_lo + 16u * j, x_hi, w_lo + 16u * j, w_hi, E.y, 1u);
+                                for (int j = 4; j < nk16; ++j) umma_f16_lohi(d_tmem, x_lo + 16u * j, x_hi, w_lo2 + 16u * j, w_hi, E.y, 1u);
                             } else {
                                 umma_f16_lohi(d_tmem, w_lo, w_hi, x_lo, x_hi, E.y, acc0);
-                                for (int j = 1; j < nk16; ++j) umma_f16_lohi(d_tmem, w_lo + 16u * j, w_hi, x_lo + 16u * j, x_hi, E.y, 1u);
+                                for (int j = 1; j < n1; ++j) umma_f16_lohi(d_tmem, w_lo + 16u * j, w_hi, x_lo + 16u * j, x_hi, E.y, 1u);
+                                for (int j = 4; j < nk16; ++j) umma_f16_lohi(d_tmem, w_lo2 + 16u * j, w_hi, x_lo + 16u * j, x_hi, E.y, 1u);
                             }
                         }
                         pf.add(PF_MMA_ISSUE, t_i);
@@ -302,6 +314,7 @@ sa_mma_kernel(const __grid_constant__ SaArgs a) {
                     }
                     __syncwarp();
                     if (f & SCH_LAST_KC) ++job;
+                    E = En; R = Rn;
                 }
             }
             pf.add(PF_MMA_TOTAL, t_start);
@@ -725,7 +738,7 @@ static unsigned long long *g_sa_prof = nullptr;
 struct SaTuning {
     int max_stages, max_ctas, grid_mult;
     int abl;
-    bool no_lring, no_sched, rot, no_narrow, one_group;
+    bool no_lring, no_sched, rot, no_narrow, one_group, no_double;
     SaTuning() {
         auto geti = [](const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; };
         max_stages = max(2, min(MM_MAX_STAGES, geti("SPSK_SA_MAX_STAGES", MM_MAX_STAGES)));   // sensitivity measurements
@@ -736,6 +749,7 @@ struct SaTuning {
         no_sched = getenv("SPSK_SA_NO_SCHED") != nullptr;
         rot = getenv("SPSK_SA_ROT") != nullptr;              // opt-in: measured neutral on B200 (the weight stream is not L2 hot-line bound)
         no_narrow = getenv("SPSK_SA_NO_NARROW") != nullptr;
+        no_double = getenv("SPSK_SA_NO_DOUBLE") != nullptr;   // A/B: one 64-wide k tile per schedule entry everywhere
         one_group = getenv("SPSK_SA_ONE_GROUP") != nullptr;
     }
 };
@@ -847,8 +861,8 @@ static int sa_plan(const spsk_sa_mma_desc *d, SaPlan *P) {
 // The per-tile schedule of a streaming chain (see the tabulated issue loop and the table-driven producer of sa_mma_kernel).
 // Shared-memory offsets are relative to the CTA's dynamic shared memory: [header MM_HDR: barriers][XA][XB][weight ring]; the
 // barrier offsets mirror the W_FULL / W_EMPTY / XR / WL_FULL / WL_EMPTY lambdas of the kernel.  Returns the number of entries
-// (weight tiles + ring padding), or 0 when it does not fit MM_SCHED_MAX.
-static int build_schedule(SaArgs &a) {
+// (weight-tile groups + ring padding), or 0 when it does not fit MM_SCHED_MAX.
+static int build_schedule(SaArgs &a, bool allow_double) {
     const int nL = a.nlayers;
     const bool lring = a.lstages > 0;
     auto w_full = [](int s) { return 8u * (uint32_t)s; };
@@ -856,10 +870,26 @@ static int build_schedule(SaArgs &a) {
     auto xr = [](int buf, int c) { return 8u * (uint32_t)(2 * MM_MAX_STAGES + 8 + buf * MM_MAX_XC + c); };
     auto wl_full = [](int s) { return 8u * (uint32_t)(2 * MM_MAX_STAGES + 8 + 2 * MM_MAX_XC + s); };
     auto wl_empty = [](int s) { return 8u * (uint32_t)(3 * MM_MAX_STAGES + 8 + 2 * MM_MAX_XC + s); };
-    // entries per tile of each ring, padded to a multiple of its depth
+    // a ring whose 16 KB stages can be regrouped into >= 2 slots of 32 KB takes two consecutive k tiles per entry
+    const int stages16[2] = {a.nstages, lring ? a.lstages : 0};
+    bool dbl[2];
+    int depth[2];
+    for (int r = 0; r < 2; ++r) {
+        dbl[r] = allow_double && stages16[r] >= 4;
+        depth[r] = stages16[r] ? (dbl[r] ? stages16[r] / 2 : stages16[r]) : 1;
+    }
+    auto ring_of = [&](int l) { return (lring && l == nL - 1) ? 1 : 0; };
+    // how many k tiles entry (layer l, first tile kc) covers: 2 when the ring is doubled and both tiles are full 64-wide ones
+    auto span = [&](int l, int kc) {
+        const SaLayer &Ly = a.L[l];
+        return (dbl[ring_of(l)] && kc + 1 < Ly.n_kc && Ly.wk - (kc + 1) * 64 >= 64) ? 2 : 1;
+    };
     int n_ring[2] = {0, 0};
-    for (int l = 0; l < nL; ++l) n_ring[(lring && l == nL - 1) ? 1 : 0] += a.L[l].n_cc * a.L[l].n_kc;
-    const int depth[2] = {a.nstages, lring ? a.lstages : 1};
+    for (int l = 0; l < nL; ++l) {
+        int per_chunk = 0;
+        for (int kc = 0; kc < a.L[l].n_kc; kc += span(l, kc)) ++per_chunk;
+        n_ring[ring_of(l)] += a.L[l].n_cc * per_chunk;
+    }
     int pad[2], uses[2];
     for (int r = 0; r < 2; ++r) {
         pad[r] = (depth[r] - n_ring[r] % depth[r]) % depth[r];
@@ -877,7 +907,7 @@ static int build_schedule(SaArgs &a) {
     auto ring_words = [&](int r, uint32_t src, uint32_t bytes, uint4 &R) {
         const int slot = pos[r] % depth[r], k = pos[r] / depth[r];
         ++pos[r];
-        const uint32_t slot_off = ring_base[r] + (uint32_t)slot * MM_STAGE_BYTES;
+        const uint32_t slot_off = ring_base[r] + (uint32_t)slot * (dbl[r] ? 2u : 1u) * MM_STAGE_BYTES;
         const uint32_t full = r ? wl_full(slot) : w_full(slot), empty = r ? wl_empty(slot) : w_empty(slot);
         R.x = src;
         R.y = bytes | ((slot_off >> 4) << 16);
@@ -895,36 +925,40 @@ static int build_schedule(SaArgs &a) {
     for (int l = 0; l < nL; ++l) {
         const SaLayer &Ly = a.L[l];
         const bool last = (l == nL - 1);
-        const int r = (lring && last) ? 1 : 0;
+        const int r = ring_of(l);
         if (r == 1) pad_ring(0);   // ring 0 is complete for this tile before the overlay ring starts
         const uint32_t x_off = (uint32_t)MM_HDR + ((l & 1) ? (uint32_t)a.xa_bytes : 0u);
         const uint32_t x_lo0 = (x_off >> 4) | ((128u >> 4) << 16);                  // umma_desc_lo(base + x_off, LBO 128) - (base >> 4)
         const uint32_t x_hi = (((uint32_t)Ly.xw * 16u) >> 4) | (1u << 14);           // umma_desc_hi(SBO)
         for (int cci = 0; cci < Ly.n_cc; ++cci) {
             const int ncols = (Ly.cpad - cci * 128) < 128 ? (Ly.cpad - cci * 128) : 128;
-            for (int kc = 0; kc < Ly.n_kc; ++kc, ++e) {
-                const int kw = (Ly.wk - kc * 64) < 64 ? (Ly.wk - kc * 64) : 64;
-                const int nk16 = kw >> 4;
-                uint32_t f = (uint32_t)nk16;
+            for (int kc = 0; kc < Ly.n_kc; ++e) {
+                const int nt = span(l, kc);
+                const int kw = (Ly.wk - kc * 64) < 64 ? (Ly.wk - kc * 64) : 64;   // width of the entry's first tile (the second, if any, is 64)
+                const int nk16 = (kw >> 4) + (nt == 2 ? 4 : 0);
+                uint32_t f = (uint32_t)nk16 | ((uint32_t)(ncols * 8) << 16);      // second tile: ncols x 64 halfs further = ncols * 8 units
                 if (kc == 0) f |= SCH_FIRST_KC;
-                if (kc == Ly.n_kc - 1) f |= SCH_LAST_KC;
+                if (kc + nt >= Ly.n_kc) f |= SCH_LAST_KC;
                 if (r == 1 && cci == 0 && kc == 0) f |= SCH_LRING_FIRST;
-                if (lring && l == nL - 2 && cci == Ly.n_cc - 1 && kc == Ly.n_kc - 1) f |= SCH_HID_DONE;
+                if (lring && l == nL - 2 && cci == Ly.n_cc - 1 && kc + nt >= Ly.n_kc) f |= SCH_HID_DONE;
                 if (last) f |= SCH_LAST_LAYER;
                 const int n_idesc = last ? MM_ROWS : ncols;
                 const uint32_t idesc = (1u << 4) | ((uint32_t)(n_idesc >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);   // umma_idesc(128, n)
                 const uint32_t w_hi = (((uint32_t)kw * 16u) >> 4) | (1u << 14);
                 a.sched[e] = make_uint4(x_lo0 + (uint32_t)kc * 64u, idesc, x_hi | (w_hi << 16), f);
                 uint4 R;
-                ring_words(r, (uint32_t)(Ly.w_off + (128 * cci * Ly.wk + ncols * 64 * kc) * 2), (uint32_t)(ncols * kw * 2), R);
+                ring_words(r, (uint32_t)(Ly.w_off + (128 * cci * Ly.wk + ncols * 64 * kc) * 2), (uint32_t)(ncols * (kw + (nt == 2 ? 64 : 0)) * 2), R);
                 if (cci == 0) {
-                    // the 64-wide activation chunk this weight tile reads first becomes ready during the first cout chunk of the layer
+                    // the 64-wide activation chunks these weight tiles read become ready during the first cout chunk of the layer
                     // (chunk kc: written by the gather / the previous layer's epilogue); later cout chunks re-read what is already there
-                    const int c = kc;   // (kc * 4 + nk16 - 1) >> 2
-                    R.z |= (1u << 22) | ((uint32_t)(seen[l & 1][c] & 1) << 23) | ((uint32_t)(n_compl[l & 1][c] & 1) << 24);
-                    R.w = xr(l & 1, c);
+                    for (int t = 0; t < nt; ++t) {
+                        const int c = kc + t;
+                        R.z |= ((1u | ((uint32_t)(seen[l & 1][c] & 1) << 1) | ((uint32_t)(n_compl[l & 1][c] & 1) << 2)) << (22 + 3 * t));
+                        R.w |= xr(l & 1, c) << (10 * t);
+                    }
                 }
                 a.ring[e] = R;
+                kc += nt;
             }
         }
         for (int c = 0; c < Ly.n_xc; ++c) ++seen[l & 1][c];
@@ -1058,7 +1092,7 @@ extern "C" int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stre
     const int slots = SPSK_NUM_SMS * P.ctas * mult;
     const int grid = a.ntiles < slots ? a.ntiles : slots;
     if (a.sched_n > 0) {
-        a.sched_n = build_schedule(a);   // 0: does not fit the table, the general issue loop takes over
+        a.sched_n = build_schedule(a, !sa_tuning().no_double);   // 0: does not fit the table, the general issue loop takes over
         if (a.sched_n > 0) a.rot_last = 0;   // the table fixes the chunk order
     }
     const bool two_groups = P.ctas == 1 && !sa_tuning().one_group;

@@ -12,9 +12,10 @@ constexpr int MM_MAX_LAYERS = 4;
 constexpr int MM_MAX_STAGES = 8;
 constexpr int MM_HDR = 1024;          // barriers + TMEM slot
 constexpr int MM_SCHED_MAX = 104;     // tabulated weight tiles (+ ring padding entries) per row tile, 2 x 16 bytes each in the kernel parameters
-// flags of SaArgs::sched[e].w (bits 0..2 = MMAs of the entry, kw / 16; 0 for a padding entry)
-constexpr uint32_t SCH_FIRST_KC = 1u << 3;      // first weight tile of a job: take an accumulator
-constexpr uint32_t SCH_LAST_KC = 1u << 4;       // last weight tile of a job: commit the accumulator
+// flags of SaArgs::sched[e].w (bits 0..3 = MMAs of the entry, K / 16 = 1..8; 0 for a padding entry;  bits 16..26 = descriptor
+// offset, in 16-byte units, of the entry's SECOND 64-wide k tile inside its ring slot)
+constexpr uint32_t SCH_FIRST_KC = 1u << 4;      // first weight tile of a job: take an accumulator
+constexpr uint32_t SCH_LAST_KC = 1u << 5;       // last weight tile of a job: commit the accumulator
 constexpr uint32_t SCH_LRING_FIRST = 1u << 11;  // first entry of the tile on the last layer's overlay ring: the producer waits for HID_DONE
 constexpr uint32_t SCH_HID_DONE = 1u << 12;     // last MMAs reading the activation buffer the overlay ring lives in
 constexpr uint32_t SCH_LAST_LAYER = 1u << 13;   // orientation B (weights are the A operand)
