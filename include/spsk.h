@@ -274,6 +274,12 @@ typedef struct spsk_sa_mma_desc {
  * SPSK_ERR_UNSUPPORTED when the chain does not fit. */
 SPSK_API int spsk_sa_mma_config(const spsk_sa_mma_desc *d, int *smem_bytes, int *ctas_per_sm, int *nstages, int *resident);
 SPSK_API int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stream);
+/* Host-only test / documentation aid: the static per-tile schedule (weight-tile groups, ring slots, barriers, phase parities) a
+ * streaming chain runs with; 8 uint32 per entry into `words` (capacity 8 * SPSK_SA_SCHED_MAX), layout in csrc/sa_mma.cu.
+ * info[6] = {hidden-ring stages, overlay-ring stages, resident, smem offset of the hidden ring, of the overlay ring, packed weight
+ * bytes}.  *n = 0 when the chain does not use the table (resident, split or pair chains). */
+#define SPSK_SA_SCHED_MAX 104
+SPSK_API int spsk_sa_mma_schedule(const spsk_sa_mma_desc *d, int *n, unsigned int *words, int *info);
 /* Number of partial-sum slices a statistics pass of this descriptor (sizes and chain filled in) writes: CTAs x epilogue groups. */
 SPSK_API int spsk_sa_mma_stats_parts(const spsk_sa_mma_desc *d, int *nparts);
 /* Tuning aid: when `counters` (device memory, SPSK_SA_PROF_COUNTERS x u64, zeroed by the caller) is non-NULL every

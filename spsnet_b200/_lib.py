@@ -48,6 +48,7 @@ SIGNATURES = {
     "spsk_sa_mma_config": [_p, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)],
     "spsk_sa_mma_forward": [_p, _p],
     "spsk_sa_mma_stats_parts": [_p, C.POINTER(_i)],
+    "spsk_sa_mma_schedule": [_p, C.POINTER(_i), _p, _p],
     "spsk_sa_pack_layer": [_p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p],
     "spsk_bn_stats_reduce": [_p, _i, _i, _i, C.c_double, _p, _p],
     "spsk_bn_stats_finalize": [_p, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p],

@@ -1000,6 +1000,37 @@ extern "C" int spsk_sa_mma_config(const spsk_sa_mma_desc *d, int *smem_bytes, in
     return SPSK_OK;
 }
 
+// Host-only: the static schedule a streaming chain would run with (test / documentation aid; no device work).
+//   words: capacity >= 8 * SPSK_SA_SCHED_MAX uint32; entry e = words[8e .. 8e+3] (sched: activation descriptor lo, instruction
+//   descriptor, descriptor hi words, flags) + words[8e+4 .. 8e+7] (ring: source offset, bytes | slot offset/16 << 16, barriers and
+//   parities, activation-chunk barriers) -- the layout documented at the tabulated issue loop of sa_mma_kernel.
+//   info[0] = hidden-ring 16 KB stages, [1] = overlay-ring 16 KB stages (0 = none), [2] = resident, [3] = shared-memory offset of
+//   the hidden ring, [4] = of the overlay ring, [5] = total packed weight bytes.  *n = 0 when the chain is not tabulated.
+extern "C" int spsk_sa_mma_schedule(const spsk_sa_mma_desc *d, int *n, unsigned int *words, int *info) {
+    using namespace spsk;
+    SPSK_REQUIRE(d && n && words && info, SPSK_ERR_INVALID_ARG, "sa_mma_schedule: null pointer");
+    SaPlan P;
+    if (int rc = sa_plan(d, &P)) return rc;
+    static SaArgs a;   // ~4 KB: keep it off the stack; host-only helper, not thread-safe by design (tests)
+    a = SaArgs{};
+    a.nlayers = d->nlayers;
+    for (int l = 0; l < d->nlayers; ++l) a.L[l] = P.L[l];
+    a.nstages = P.nstages; a.lstages = P.lstages; a.resident = P.resident;
+    a.xa_bytes = P.xa_bytes; a.xb_bytes = P.xb_bytes;
+    a.sched_n = (P.sched_n > 0 && !d->pair) ? build_schedule(a, !sa_tuning().no_double) : 0;
+    *n = a.sched_n;
+    for (int e = 0; e < a.sched_n; ++e) {
+        const uint4 E = a.sched[e], R = a.ring[e];
+        unsigned int *w = words + 8 * e;
+        w[0] = E.x; w[1] = E.y; w[2] = E.z; w[3] = E.w; w[4] = R.x; w[5] = R.y; w[6] = R.z; w[7] = R.w;
+    }
+    info[0] = P.nstages; info[1] = P.lstages; info[2] = P.resident;
+    info[3] = MM_HDR + P.xa_bytes + P.xb_bytes;
+    info[4] = MM_HDR + ((((d->nlayers - 2) & 1) && d->nlayers >= 2) ? P.xa_bytes : 0);
+    info[5] = P.w_total;
+    return SPSK_OK;
+}
+
 extern "C" int spsk_sa_mma_stats_parts(const spsk_sa_mma_desc *d, int *nparts) {
     using namespace spsk;
     SPSK_REQUIRE(d && nparts, SPSK_ERR_INVALID_ARG, "sa_mma: null descriptor");

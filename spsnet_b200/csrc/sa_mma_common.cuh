@@ -186,6 +186,8 @@ static __device__ __noinline__ void pool_chunk_any(uint32_t taddr, PoolOut &o, i
     }
 }
 
+static_assert(sizeof(SaArgs) <= 4096, "SaArgs travels in the kernel parameters: keep it within the classic 4 KB limit");
+
 // Batch-statistics pass: thread = cout, columns = the tile's rows.  Sum and sum of squares of the raw accumulators over the
 // `nv` real rows of the tile (fp32 over <= 128 values), added in fp64 to the cell this thread owns (no other thread of the grid
 // touches it: plain read-modify-write, reproducible bit for bit).
