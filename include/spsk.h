@@ -43,7 +43,7 @@ typedef enum spsk_status {
 
 /* Human-readable description of the last error raised on the calling thread. */
 SPSK_API const char *spsk_last_error(void);
-/* ABI version of this header (bumped on any signature change or added entry point; currently 4). */
+/* ABI version of this header (bumped on any signature change or added entry point; currently 5). */
 SPSK_API int spsk_abi_version(void);
 /* Number of CUDA kernels this library has launched in this process (all threads). */
 SPSK_API unsigned long long spsk_launch_count(void);

@@ -41,7 +41,7 @@ unsigned int *fp16_overflow_word() {
 
 extern "C" unsigned long long spsk_launch_count(void) { return spsk::g_launches.load(std::memory_order_relaxed); }
 extern "C" const char *spsk_last_error(void) { return spsk::g_err; }
-extern "C" int spsk_abi_version(void) { return 4; }  // 4: batch-statistics pass of spsk_sa_mma_forward (stats, stats_parts) + spsk_sa_mma_stats_parts
+extern "C" int spsk_abi_version(void) { return 5; }  // 4: batch-statistics pass of spsk_sa_mma_forward (stats, stats_parts) + spsk_sa_mma_stats_parts; 5: spsk_sa_pack_layer, spsk_bn_stats_reduce / _finalize, spsk_sa_mma_schedule
 
 extern "C" int spsk_fp16_overflow_poll(unsigned int *mask, int clear) {
     using namespace spsk;

@@ -68,9 +68,13 @@ def test_statistics_pass_vs_float64(name, c_feat, widths, ns, B, N, M):
     twin = pu.make_twin(feats, (c_feat + 7) // 8 * 8) if (c_feat and not pk.split) else None
 
     def run():
-        parts = torch.zeros((nparts, pk.cpad[-1], 2), dtype=torch.float64, device="cuda")
+        # one guard slice on either side of the buffer: the kernel must write exactly `nparts` slices
+        guarded = torch.full((nparts + 2, pk.cpad[-1], 2), -777.0, dtype=torch.float64, device="cuda")
+        parts = guarded[1:nparts + 1]
+        parts.zero_()
         pu.sa_mma_forward(xyz=xyz, new_xyz=new_xyz, idx=idx, chain=pk, twin=twin, features=feats if pk.split else None, stats=parts)
-        return parts
+        assert bool((guarded[0] == -777.0).all()) and bool((guarded[-1] == -777.0).all()), "statistics pass wrote outside its slices"
+        return parts.clone()
 
     parts = run()
     assert torch.equal(parts, run())                                   # per-thread cells, no atomics: reproducible bit for bit
@@ -125,6 +129,8 @@ def test_pack_layer_kernel_equals_host_packing(c_feat, widths):
         assert want.split == split
         got = plan.wbuf[:want.wtiles.numel() * 2].view(torch.float16)
         assert torch.equal(got.view(torch.int16), want.wtiles.view(torch.int16)), f"scale={use_scale}"
+        tail = plan.wbuf[want.wtiles.numel() * 2:]
+        assert tail.numel() == 0 or bool((tail == 0xAB).all()), "the pack kernel wrote past the chain's tiles"
 
 
 @pytest.mark.parametrize("momentum", [0.1, None])

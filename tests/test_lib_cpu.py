@@ -29,7 +29,7 @@ def test_identity_and_errors():
     from spsnet_b200 import _lib
 
     lib = _lib.lib
-    assert lib.spsk_abi_version() == 4
+    assert lib.spsk_abi_version() == 5
     assert lib.spsk_built_for_sm() == 100
     assert lib.spsk_ball_query(1, 8, 4, 1.0, 0, None, None, None, None) == -1
     assert b"null" in lib.spsk_last_error() or b"nsample" in lib.spsk_last_error()
