@@ -46,6 +46,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--only-backbone", action="store_true")
     a = ap.parse_args()
     from spsnet_b200 import pointnet2_modules as pm
     from spsnet_b200 import pointnet2_utils as pu
@@ -63,7 +64,7 @@ def main():
         refm = None
     B = a.batch
     rows = []
-    for name, c in LAYERS.items():
+    for name, c in ({} if a.only_backbone else LAYERS).items():
         torch.manual_seed(0)
         base = scenes.make_batch(5, B, 16384)[:, :, :3]
         xyz = torch.from_numpy(np.ascontiguousarray(base[:, :c["n"]])).cuda()
@@ -107,6 +108,7 @@ def main():
     from spsnet_b200 import backbone as bb
     from spsnet_b200.configs import kitti_iassd_cfg
 
+    torch.cuda.empty_cache()   # the per-layer arms above leave multi-GB blocks cached; start the stack from a clean allocator
     torch.manual_seed(0)
     net = bb.IASSD_Backbone(kitti_iassd_cfg(), num_class=3, input_channels=4).cuda().train()
     pts = torch.from_numpy(np.ascontiguousarray(scenes.to_points(scenes.make_batch(7, B, 16384)))).cuda()

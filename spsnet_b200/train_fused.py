@@ -140,6 +140,10 @@ def mlp_recompute(grouped: torch.Tensor, params: Sequence[torch.Tensor], eps: Se
     """The reference composition on a grouped tensor (B, C, npoint, nsample): [conv1x1 -> BN(batch stats) -> ReLU] x L -> max
     over nsample, as a torch graph (reference pointnet2_modules.py:431-436)."""
     x = grouped
+    if x.is_cuda and os.environ.get("SPSK_TRAIN_CHANNELS_LAST", "1") != "0":
+        # NHWC: the 1x1 convolutions become plain GEMMs over (B*npoint*nsample, C) for cuDNN in both directions, and BatchNorm /
+        # ReLU / max-pool follow the format; same fp32 math, measured faster than NCHW for these few-channel, many-row tensors
+        x = x.contiguous(memory_format=torch.channels_last)
     for l in range(len(params) // 3):
         w, gamma, beta = params[3 * l:3 * l + 3]
         x = F.conv2d(x, w)
