@@ -6,7 +6,8 @@
 //     3 x [Conv2d 1x1 (no bias) -> BatchNorm2d(eval) -> ReLU] ; F.max_pool2d over nsample
 // The (B,3+C,npoint,nsample) grouped tensor and all conv/BN/ReLU intermediates stay on chip.
 //
-// Machine mapping (persistent CTAs, 192 threads, 1-3 CTAs per SM depending on the chain's footprint):
+// Machine mapping (persistent CTAs: 192 threads x 1-3 per SM, 160 threads x 4 per SM for resident narrow chains, 320 threads x 1
+// for the wide streaming chains, depending on the chain's footprint):
 //   tile        = 128 grouped rows (= 128/nsample centres), looped over by each CTA
 //   job         = (layer, 128-wide cout chunk): one accumulator of <=128 TMEM columns; jobs of a tile run in
 //                 layer order through a ring of `nbuf` accumulators, so the MMAs of job j+1.. overlap the
@@ -18,8 +19,13 @@
 //                     start before the whole activation is written;
 //                 (c) last layer: max over nsample + bias + ReLU -> global (fp32 channel-major and/or fp16 point-major)
 //   warp 4      : weight producer: 1-D bulk async copies (cp.async.bulk + mbarrier complete_tx) of host-packed
-//                 weight tiles, either once (chain resident in shared memory) or through a ring of 16 KB stages
-//   warp 5      : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, fp16 operands, fp32 accumulate)
+//                 weight tiles, either once (chain resident in shared memory) or through a ring of 16 / 32 KB slots
+//                 following the host-built static schedule (SaArgs::ring)
+//   warp 5      : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, fp16 operands, fp32 accumulate); three
+//                 loops: register-resident descriptors (narrow resident chains), the tabulated static-ring schedule
+//                 (streaming chains), a general fallback
+//   statistics mode (SaArgs::stats, training-mode BatchNorm): the last layer's epilogue sums z and z^2 per cout instead
+//                 of bias + ReLU + max-pool (include/spsk.h, train_fused.py)
 //   hidden layers  (orientation A): D[row, cout]  = X[row, k] . W[cout, k]^T   M = 128 rows,  N = cout chunk
 //   last layer     (orientation B): D[cout, row]  = W[cout, k] . X[row, k]^T   M = 128 couts, N = 128 rows
 //                 so that the max over the nsample rows of a centre is a per-thread loop over TMEM columns.
@@ -30,7 +36,7 @@
 // exact and accumulate in fp32; measured end-to-end error of a 3-layer scale is ~5e-4 of the output range.
 // `split` mode (narrow chains, every K <= 64, i.e. IA-SSD layer 0 where the error does not average out): every
 // operand is carried as hi + lo fp16 halves and each product is evaluated as Xh.Wh + Xl.Wh + Xh.Wl by
-// concatenating along K ([Xh | Xl | Xh] . [Wh ; Wh ; Wl]) -- fp32-grade results (~1e-6) for 3x MMA work that
+// walking K three times ([Xh | Xl | Xh] against the packed [Wh ; Wl], Wh serving two products) -- fp32-grade results (~1e-6) for 3x MMA work that
 // these layers do not notice.  The exact-fp32 CUDA-core path is linear_ffma.cu.
 #include "sa_mma_common.cuh"
 #include <stdlib.h>
