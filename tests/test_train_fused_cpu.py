@@ -184,3 +184,48 @@ def test_gloo_world2_sync_batchnorm_equals_full_batch():
 def test_sync_group_is_none_without_a_process_group():
     bn = nn.SyncBatchNorm(8)
     assert tf.sync_group(bn) is None and tf.sync_group(nn.BatchNorm2d(8)) is None
+
+
+PLAN_CHAINS = [(1, [16, 16, 32]), (1, [32, 32, 64]), (64, [64, 64, 128]), (64, [64, 96, 128]), (128, [128, 256, 256]), (256, [256, 512, 1024]),
+               (0, [16, 32]), (5, [17, 33]), (20, [40])]
+
+
+@pytest.mark.parametrize("c_feat,widths", PLAN_CHAINS, ids=[f"c{c}-" + "x".join(map(str, w)) for c, w in PLAN_CHAINS])
+def test_train_plan_layout_equals_the_inference_packing(c_feat, widths):
+    """TrainPlan's shared weight / bias buffers: every truncated chain (pass l) and the full chain have exactly the shapes, offsets
+    and arithmetic pu.MmaChain gives the same layers at inference -- the kernels see one layout."""
+    from spsnet_b200 import pointnet2_utils as pu
+
+    cin = c_feat + 3
+    shapes, chain = [], []
+    for co in widths:
+        shapes.append((co, cin))
+        chain.append((torch.randn(cin, co), torch.zeros(co), True))
+        cin = co
+    split = c_feat <= 8 and all(tf._ceil(co, 16) <= 64 for co, _ in shapes[:-1])
+    plan = tf.TrainPlan(shapes, c_feat, True, split, "cpu")
+    assert plan.ok
+    for l in range(len(widths)):
+        want = pu.MmaChain(chain[:l + 1], c_feat, True, split=split, pair=False)
+        got = plan.chains[l]
+        assert want.split == split and want.ok == got.ok
+        assert (want.kpad, want.cpad, want.cout_last, want.cpad8) == (got.kpad, got.cpad, got.cout_last, got.cpad8)
+        wk = [(2 if split else 1) * k for k in want.kpad]
+        assert plan.w_off[l] == sum(wk[j] * want.cpad[j] * 2 for j in range(l))
+        assert plan.b_off[l] == sum(want.cpad[:l])
+        assert want.wtiles.numel() * 2 <= plan.wbuf.numel() and want.bias.numel() <= plan.bbuf.numel()
+
+
+def test_msg_train_declines_what_it_does_not_cover():
+    """CPU tensors, avg-pool, GroupAll, non-power-of-two nsample and frozen BatchNorm go to the reference composition (None)."""
+    m = pm.PointnetSAModuleMSG(npoint=8, radii=[0.5], nsamples=[16], mlps=[[4, 8, 16]], use_xyz=True).train()
+    xyz, new_xyz, feats = torch.randn(1, 32, 3), torch.randn(1, 8, 3), torch.randn(1, 4, 32)
+    assert tf.msg_train(m, xyz, new_xyz, feats) is None                      # CPU: the fused path needs the device
+    for bad in (pm.PointnetSAModuleMSG(npoint=8, radii=[0.5], nsamples=[16], mlps=[[4, 8]], pool_method="avg_pool"),
+                pm.PointnetSAModuleMSG(npoint=None, radii=[0.5], nsamples=[16], mlps=[[4, 8]]),
+                pm.PointnetSAModuleMSG(npoint=8, radii=[0.5], nsamples=[12], mlps=[[4, 8]])):
+        bad.train()
+        fake = type("T", (), {"is_cuda": True, "dtype": torch.float32, "shape": xyz.shape})()   # device checks pass, structure must not
+        assert tf.msg_train(bad, fake, new_xyz, None if bad.npoint is None else feats) is None
+    m.mlps[0][1].eval()
+    assert tf.split_layers(m.mlps[0]) is None
