@@ -263,8 +263,9 @@ typedef struct spsk_sa_mma_desc {
                                the module in train()): the chain is evaluated as usual, but the last layer's epilogue, instead of bias
                                + ReLU + max-pool, adds the raw accumulators z[row, c] of every real row into per-CTA partial sums
                                stats[(part * cpad_last + c) * 2 + {0, 1}] += {sum z, sum z*z}   (fp32 inside a 128-row tile, fp64
-                               across tiles; each (part, c) cell is owned by ONE thread: no atomics, bit-reproducible).  The caller
-                               zeroes the buffer, sums it over `part` and divides by b*m*nsample; out_cm / out16 are not written
+                               across tiles; each (part, c) cell is owned by ONE thread: no atomics, bit-reproducible).  The call
+                               zeroes the slices it accumulates into (stream-ordered memset); the caller sums them over `part` and
+                               divides by b*m*nsample; out_cm / out16 are not written
                                and may be NULL.  Plain launch shapes only (pair == 0).  Appended in ABI 4 */
     int stats_parts;        /* capacity of `stats` in parts; must be >= spsk_sa_mma_stats_parts() of this descriptor */
 } spsk_sa_mma_desc;
@@ -311,6 +312,12 @@ SPSK_API int spsk_bn_stats_reduce(const double *parts, int nparts, int cpad, int
  * (unbiased variance) unless momentum < 0; `moments` (c, 2) fp64 receives (mean, var) when non-NULL. */
 SPSK_API int spsk_bn_stats_finalize(const double *sums, int c, const float *gamma, const float *beta, float eps, float momentum,
                                     float *running_mean, float *running_var, float *scale, float *bias, double *moments, spsk_stream_t stream);
+/* Both steps in ONE launch, for statistics that stay on this rank (plain BatchNorm2d): parts -> (scale, bias), running statistics
+ * updated (momentum < 0: not), *num_batches_tracked += 1 when non-NULL (torch's int64 counter), sums (2c + 1 doubles) written
+ * when non-NULL. */
+SPSK_API int spsk_bn_stats_reduce_finalize(const double *parts, int nparts, int cpad, int c, double count, const float *gamma, const float *beta,
+                                           float eps, float momentum, float *running_mean, float *running_var, long long *num_batches_tracked,
+                                           float *scale, float *bias, double *sums, spsk_stream_t stream);
 
 /* Point-wise layer on the tensor cores:  y[row, c] = relu?( bias[c] + sum_k x[row, k] * W[c, k] )  over point-major
  * fp16 rows (replaces the aggregation / confidence / vote Conv1d + BN + ReLU stacks, pointnet2_modules.py:216-243,

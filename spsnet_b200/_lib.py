@@ -52,6 +52,7 @@ SIGNATURES = {
     "spsk_sa_pack_layer": [_p, _i, _i, _p, _i, _i, _i, _i, _i, _i, _p, _p],
     "spsk_bn_stats_reduce": [_p, _i, _i, _i, C.c_double, _p, _p],
     "spsk_bn_stats_finalize": [_p, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p],
+    "spsk_bn_stats_reduce_finalize": [_p, _i, _i, _i, C.c_double, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p],
     "spsk_sa_mma_set_profile": [_p],
     "spsk_pw_mma_forward": [_p, _p],
     "spsk_fp16_overflow_poll": [C.POINTER(C.c_uint), _i],

@@ -1138,6 +1138,10 @@ extern "C" int spsk_sa_mma_forward(const spsk_sa_mma_desc *d, spsk_stream_t stre
         SPSK_REQUIRE(d->stats_parts >= grid * (two_groups ? 2 : 1), SPSK_ERR_INVALID_ARG, "sa_mma: stats holds %d parts, this launch writes %d",
                      d->stats_parts, grid * (two_groups ? 2 : 1));
         a.out = nullptr; a.out16 = nullptr;
+        // the slices this launch accumulates into start from zero (stream-ordered; slices beyond them are not touched)
+        const size_t bytes = (size_t)grid * (two_groups ? 2 : 1) * (size_t)P.L[d->nlayers - 1].cpad * 2 * sizeof(double);
+        cudaError_t e = cudaMemsetAsync(d->stats, 0, bytes, as_stream(stream));
+        if (e != cudaSuccess) return cuda_fail(e, "sa_mma: cudaMemsetAsync(stats)");
     }
 #define SPSK_SA_LAUNCH(GV, PV)                                                                                               \
     do {                                                                                                                    \

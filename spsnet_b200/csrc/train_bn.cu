@@ -81,15 +81,12 @@ bn_stats_reduce_kernel(const double *__restrict__ parts, int nparts, int cpad, i
     }
 }
 
-__global__ void __launch_bounds__(128)
-bn_stats_finalize_kernel(const double *__restrict__ sums, int c, const float *__restrict__ gamma, const float *__restrict__ beta, float eps,
-                         float momentum, float *__restrict__ running_mean, float *__restrict__ running_var, float *__restrict__ scale,
-                         float *__restrict__ bias, double *__restrict__ moments) {
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= c) return;
-    const double total = sums[2 * c];
-    const double mean = sums[2 * ch] / total;
-    double var = sums[2 * ch + 1] / total - mean * mean;
+// sums -> (scale, bias) of the BN fold + torch's running-statistics update, for one channel
+__device__ __forceinline__ void bn_finalize_channel(int ch, double s, double q, double total, const float *gamma, const float *beta, float eps,
+                                                    float momentum, float *running_mean, float *running_var, float *scale, float *bias,
+                                                    double *moments) {
+    const double mean = s / total;
+    double var = q / total - mean * mean;
     var = var > 0.0 ? var : 0.0;
     const double g = (double)__ldg(gamma + ch) / sqrt(var + (double)eps);
     scale[ch] = (float)g;
@@ -100,6 +97,48 @@ bn_stats_finalize_kernel(const double *__restrict__ sums, int c, const float *__
         running_mean[ch] = (float)((1.0 - (double)momentum) * (double)running_mean[ch] + (double)momentum * mean);
         running_var[ch] = (float)((1.0 - (double)momentum) * (double)running_var[ch] + (double)momentum * unbiased);
     }
+}
+
+// reduce + finalize in one launch (statistics local to this rank: nothing to all-reduce in between); also bumps num_batches_tracked
+__global__ void __launch_bounds__(32 * RED_PY)
+bn_stats_reduce_finalize_kernel(const double *__restrict__ parts, int nparts, int cpad, int c, double count, const float *__restrict__ gamma,
+                                const float *__restrict__ beta, float eps, float momentum, float *__restrict__ running_mean,
+                                float *__restrict__ running_var, long long *__restrict__ num_batches_tracked, float *__restrict__ scale,
+                                float *__restrict__ bias, double *__restrict__ sums) {
+    __shared__ double2 sh[RED_PY][32];
+    const int cx = threadIdx.x, py = threadIdx.y;
+    const int ch = blockIdx.x * 32 + cx;
+    if (ch == 0 && py == 0) {
+        if (sums) sums[2 * c] = count;
+        if (num_batches_tracked) *num_batches_tracked += 1;
+    }
+    double s = 0.0, q = 0.0;
+    if (ch < c) {
+#pragma unroll 4
+        for (int p = py; p < nparts; p += RED_PY) {
+            const double2 v = *reinterpret_cast<const double2 *>(parts + ((size_t)p * cpad + ch) * 2);
+            s += v.x;
+            q += v.y;
+        }
+    }
+    sh[py][cx] = make_double2(s, q);
+    __syncthreads();
+    if (py == 0 && ch < c) {
+        s = 0.0; q = 0.0;
+#pragma unroll
+        for (int i = 0; i < RED_PY; ++i) { s += sh[i][cx].x; q += sh[i][cx].y; }
+        if (sums) { sums[2 * ch] = s; sums[2 * ch + 1] = q; }
+        bn_finalize_channel(ch, s, q, count, gamma, beta, eps, momentum, running_mean, running_var, scale, bias, nullptr);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+bn_stats_finalize_kernel(const double *__restrict__ sums, int c, const float *__restrict__ gamma, const float *__restrict__ beta, float eps,
+                         float momentum, float *__restrict__ running_mean, float *__restrict__ running_var, float *__restrict__ scale,
+                         float *__restrict__ bias, double *__restrict__ moments) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= c) return;
+    bn_finalize_channel(ch, sums[2 * ch], sums[2 * ch + 1], sums[2 * c], gamma, beta, eps, momentum, running_mean, running_var, scale, bias, moments);
 }
 
 }  // namespace spsk
@@ -142,5 +181,19 @@ extern "C" int spsk_bn_stats_finalize(const double *sums, int c, const float *ga
     bn_stats_finalize_kernel<<<(c + 127) / 128, 128, 0, as_stream(stream)>>>(sums, c, gamma, beta, eps, momentum, running_mean, running_var, scale, bias,
                                                                             moments);
     SPSK_LAUNCH_CHECK("bn_stats_finalize_kernel");
+    return SPSK_OK;
+}
+
+extern "C" int spsk_bn_stats_reduce_finalize(const double *parts, int nparts, int cpad, int c, double count, const float *gamma, const float *beta,
+                                             float eps, float momentum, float *running_mean, float *running_var, long long *num_batches_tracked,
+                                             float *scale, float *bias, double *sums, spsk_stream_t stream) {
+    using namespace spsk;
+    SPSK_REQUIRE(parts && gamma && beta && scale && bias && nparts >= 1 && c >= 1 && c <= cpad && count >= 1.0, SPSK_ERR_INVALID_ARG,
+                 "bn_stats_reduce_finalize: bad arguments");
+    SPSK_REQUIRE((reinterpret_cast<uintptr_t>(parts) & 15) == 0, SPSK_ERR_INVALID_ARG, "bn_stats_reduce_finalize: parts must be 16-byte aligned");
+    SPSK_REQUIRE((running_mean == nullptr) == (running_var == nullptr), SPSK_ERR_INVALID_ARG, "bn_stats_reduce_finalize: running_mean / running_var go together");
+    bn_stats_reduce_finalize_kernel<<<(c + 31) / 32, dim3(32, RED_PY), 0, as_stream(stream)>>>(parts, nparts, cpad, c, count, gamma, beta, eps, momentum,
+                                                                                              running_mean, running_var, num_batches_tracked, scale, bias, sums);
+    SPSK_LAUNCH_CHECK("bn_stats_reduce_finalize_kernel");
     return SPSK_OK;
 }

@@ -673,7 +673,7 @@ def sa_mma_forward(*, xyz, new_xyz, idx, chain: MmaChain, twin=None, features=No
         d.n16 = chain.cout_last if n16 is None else n16
         d.o16lo = int(o16lo)
     if stats is not None:
-        # batch-statistics pass (training-mode BN): stats (parts, cpad_last, 2) float64, zeroed by the caller; nothing else is written
+        # batch-statistics pass (training-mode BN): stats (parts, cpad_last, 2) float64 (the call zeroes the slices it uses); nothing else is written
         if stats.dtype != torch.float64 or not stats.is_contiguous() or stats.dim() != 3 or stats.shape[1] != chain.cpad[-1] or stats.shape[2] != 2:
             raise RuntimeError("sa_mma_forward: stats must be a contiguous (parts, cpad_last, 2) float64 tensor")
         d.stats, d.stats_parts = stats.data_ptr(), stats.shape[0]

@@ -221,7 +221,7 @@ class TrainPlan:
         if buf is None:
             nparts = pu.sa_mma_stats_parts(idx, n, self.chains[l])
             buf = self._parts[key] = torch.empty((nparts, self.chains[l].cpad[-1], 2), dtype=torch.float64, device=idx.device)
-        return buf.zero_()
+        return buf   # spsk_sa_mma_forward zeroes the slices it accumulates into
 
     def pack(self, l: int, weight: torch.Tensor, scale: Optional[torch.Tensor], last: bool) -> None:
         cp = _ceil(self.couts[l], 128) if last else self.cp_hidden[l]
@@ -232,12 +232,20 @@ class TrainPlan:
     def finalize(self, l: int, parts: torch.Tensor, count: int, bn: nn.Module, gamma: torch.Tensor, beta: torch.Tensor, group) -> None:
         co = self.couts[l]
         st = pu._stream()
+        track = bn.track_running_stats and bn.running_mean is not None
+        if group is None and (not track or bn.momentum is not None):
+            # statistics local to this rank: reduce + finalize + num_batches_tracked in ONE launch
+            check(lib.spsk_bn_stats_reduce_finalize(parts.data_ptr(), parts.shape[0], parts.shape[1], co, float(count), gamma.data_ptr(), beta.data_ptr(),
+                                                    float(bn.eps), float(bn.momentum) if track else -1.0,
+                                                    bn.running_mean.data_ptr() if track else None, bn.running_var.data_ptr() if track else None,
+                                                    bn.num_batches_tracked.data_ptr() if track else None, self.scale[l].data_ptr(),
+                                                    self.bbuf.data_ptr() + 4 * self.b_off[l], self.sums[l].data_ptr(), st), "bn_stats_reduce_finalize")
+            return
         check(lib.spsk_bn_stats_reduce(parts.data_ptr(), parts.shape[0], parts.shape[1], co, float(count), self.sums[l].data_ptr(), st), "bn_stats_reduce")
         if group is not None:
             import torch.distributed as dist
 
             dist.all_reduce(self.sums[l], op=dist.ReduceOp.SUM, group=group)      # SyncBatchNorm: 2c + 1 doubles
-        track = bn.track_running_stats and bn.running_mean is not None
         mom = -1.0
         if track:
             bn.num_batches_tracked.add_(1)
